@@ -1,0 +1,155 @@
+// Brownian-distance-covariance pooling for sm_100a.
+//
+// Arithmetic follows BDCovpool + Triuvec (reference libfewshot_core/model/
+// backbone/utils/bdc_pool.py:69-93), with X in R^{C x M} the channel rows of
+// one clip's feature map:
+//   G = X X^T;  D_ij = max(G_ii + G_jj - 2 G_ij, 0);  A_ij = sqrt(exp(t) D_ij + 1e-5)
+//   B_ij = A_ij - rowsum_i/C - colsum_j/C + total/C^2;   out = row-major triu(B)
+// The reference spends 7 bmm (three of them against an all-ones matrix), two
+// [B,C,C] temporaries per call and a CPU-built gather index.  Here one CTA per
+// clip streams X once through shared memory (transposed so both Gram operands
+// are 128-bit shared loads), keeps the 64x64 Gram in registers (4x4 per
+// thread), and finishes the whole epilogue on chip.  Algorithmic bytes per
+// clip: 4*C*M + 4*C(C+1)/2.
+#include "common.cuh"
+
+namespace afs {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kC = 64;          // padded channel count
+constexpr int kMC = 64;         // spatial positions per shared-memory chunk
+constexpr int kXStride = kC + 4;  // sX[m][c], 16-byte aligned rows, conflict-free 128-bit stores
+constexpr int kGStride = kC + 1;
+
+__global__ void __launch_bounds__(kThreads)
+bdc_kernel(const float* __restrict__ x, int C, int M, const float* __restrict__ log_temp, int triu,
+           float* __restrict__ out) {
+  __shared__ __align__(16) float sX[kMC * kXStride];
+  __shared__ float sA[kC * kGStride];
+  __shared__ float s_diag[kC];
+  __shared__ float s_rowsum[kC];
+  __shared__ float s_colsum[kC];
+  __shared__ float s_total;
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int ti = tid >> 4;  // Gram rows 4*ti .. 4*ti+3
+  const int tj = tid & 15;  // Gram cols 4*tj .. 4*tj+3
+  const float* xb = x + static_cast<int64_t>(b) * C * M;
+
+  float g[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[i][j] = 0.f;
+
+  // loader mapping: thread -> (position lm, channel quad c4); 64 positions x 16 quads = 1024
+  // slots, 4 per thread; lanes run along m so the global loads are coalesced.
+  for (int m0 = 0; m0 < M; m0 += kMC) {
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int slot = tid + kThreads * it;
+      const int lm = slot & (kMC - 1);
+      const int c4 = slot >> 6;
+      const int m = m0 + lm;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M) {
+        const int c = 4 * c4;
+        if (c + 0 < C) v.x = __ldg(xb + static_cast<int64_t>(c + 0) * M + m);
+        if (c + 1 < C) v.y = __ldg(xb + static_cast<int64_t>(c + 1) * M + m);
+        if (c + 2 < C) v.z = __ldg(xb + static_cast<int64_t>(c + 2) * M + m);
+        if (c + 3 < C) v.w = __ldg(xb + static_cast<int64_t>(c + 3) * M + m);
+      }
+      *reinterpret_cast<float4*>(&sX[lm * kXStride + 4 * c4]) = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int lm = 0; lm < kMC; ++lm) {
+      const float4 a = *reinterpret_cast<const float4*>(&sX[lm * kXStride + 4 * ti]);
+      const float4 c = *reinterpret_cast<const float4*>(&sX[lm * kXStride + 4 * tj]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        g[i][0] = fmaf(av[i], c.x, g[i][0]);
+        g[i][1] = fmaf(av[i], c.y, g[i][1]);
+        g[i][2] = fmaf(av[i], c.z, g[i][2]);
+        g[i][3] = fmaf(av[i], c.w, g[i][3]);
+      }
+    }
+  }
+
+  if (ti == tj) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s_diag[4 * ti + i] = g[i][i];
+  }
+  __syncthreads();
+
+  const float et = expf(__ldg(log_temp));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = 4 * ti + i, c = 4 * tj + j;
+      float d = s_diag[c] + s_diag[r] - 2.f * g[i][j];
+      d = fmaxf(d, 0.f);
+      d = et * d;
+      sA[r * kGStride + c] = (r < C && c < C) ? sqrtf(d + 1e-5f) : 0.f;
+    }
+  }
+  __syncthreads();
+  if (tid < kC) {  // row sums (dcov.bmm(I_M)): fixed order over j
+    float s = 0.f;
+    for (int j = 0; j < C; ++j) s += sA[tid * kGStride + j];
+    s_rowsum[tid] = s;
+  } else if (tid < 2 * kC) {  // column sums (I_M.bmm(dcov)): fixed order over i
+    const int c = tid - kC;
+    float s = 0.f;
+    for (int i = 0; i < C; ++i) s += sA[i * kGStride + c];
+    s_colsum[c] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int j = 0; j < C; ++j) s += s_colsum[j];
+    s_total = s;
+  }
+  __syncthreads();
+
+  const float inv = 1.0f / static_cast<float>(C);
+  const float inv2 = 1.0f / static_cast<float>(C * C);
+  const float total = s_total;
+  if (triu) {
+    float* ob = out + static_cast<int64_t>(b) * (C * (C + 1) / 2);
+    for (int idx = tid; idx < C * C; idx += kThreads) {
+      const int r = idx / C, c = idx - r * C;
+      if (c >= r) {
+        const float v = sA[r * kGStride + c] - inv * s_rowsum[r] - inv * s_colsum[c] + inv2 * total;
+        ob[r * C - (r * (r - 1)) / 2 + (c - r)] = v;
+      }
+    }
+  } else {
+    float* ob = out + static_cast<int64_t>(b) * C * C;
+    for (int idx = tid; idx < C * C; idx += kThreads) {
+      const int r = idx / C, c = idx - r * C;
+      ob[idx] = sA[r * kGStride + c] - inv * s_rowsum[r] - inv * s_colsum[c] + inv2 * total;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace afs
+
+extern "C" int afs_bdc_fwd(const float* x, int32_t B, int32_t C, int32_t M, const float* log_temp,
+                           int32_t triu, float* out, afs_stream_t stream_) {
+  using namespace afs;
+  if (x == nullptr || log_temp == nullptr || out == nullptr || B < 0 || C < 1 || M < 1)
+    return AFS_ERR_INVALID_ARG;
+  if (C > kC) return AFS_ERR_UNSUPPORTED;
+  if (B == 0) return AFS_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  bdc_kernel<<<B, kThreads, 0, stream>>>(x, C, M, log_temp, triu, out);
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
+}

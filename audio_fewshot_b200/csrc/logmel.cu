@@ -1,0 +1,372 @@
+// Fused waveform -> normalised log-mel front-end for sm_100a.
+//
+// One launch does: (optional Philox gain / time-shift / additive-noise
+// augmentation) -> reflect padding -> framing -> window -> 1024-point real FFT
+// (512-point complex radix-8 x3 in registers + shared-memory exchanges) ->
+// power -> banded mel projection -> log_mult*log10(. + eps) -> (. - mean)/std
+// -> [B, 1, n_mels, T].  Spectra never leave the SM; HBM sees the waveform once
+// (frame overlap is served by L1/L2) and the output once.  Algorithmic bytes
+// per clip: 4*L + 4*n_mels*T.
+//
+// CTA = 256 threads = 4 frame groups of 64 threads; a CTA owns 32 consecutive
+// frames of one clip (8 per group) and stages its [n_mels x 32] output tile in
+// shared memory so the global store is coalesced along time.  The mel filters
+// are triangular (<= 2 filters per bin), so the projection is a banded fp32 dot
+// product (1 009 non-zeros for 128 slaney mels) rather than a dense 513x128
+// GEMM: exact fp32, ~20x fewer flops than the dense contraction.
+//
+// There is no reference implementation of this stage; the
+// canonical spec is oracle/frontend.py.
+#include <math.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "logmel_core.cuh"
+#include "philox.cuh"
+
+struct afs_logmel_plan {
+  afs_logmel_cfg cfg;
+  int device;
+  int nnz;
+  float* d_window;   // [1024]
+  float2* d_tw1024;  // [1024]
+  int* d_band;       // [3][128]: lo, len, off
+  float* d_weights;  // [nnz]
+};
+
+namespace afs {
+namespace {
+
+using namespace logmel;
+
+constexpr int kThreads = 256;
+constexpr int kGroups = kThreads / kGroup;
+constexpr int kFramesPerCta = 32;
+constexpr int kFramesPerGroup = kFramesPerCta / kGroups;
+constexpr int kMaxNnz = 2048;
+constexpr int kTileStride = kFramesPerCta + 1;
+
+constexpr size_t kSmemFloats = kMaxNnz + 3 * kMaxMels + kNfft + kGroups * (kBufA + kBufB) +
+                               kMaxMels * kTileStride;
+constexpr size_t kSmemBytes = kSmemFloats * sizeof(float);
+
+struct Params {
+  const float* wav;
+  float* out;
+  const float* mean;
+  const float* stdv;
+  const float* window;
+  const float2* tw1024;
+  const int* band;
+  const float* weights;
+  int64_t L;
+  int nnz, B, T, hop, n_mels, pad, chunks;
+  float log_mult, log_eps;
+  // augmentation
+  float gain_lo, gain_hi, noise_lo, noise_hi;
+  int max_shift;
+  uint32_t seed_lo, seed_hi;
+  uint64_t first_clip;
+};
+
+struct AugState {
+  float g, sigma;
+  int k;
+  uint32_t c_lo, c_hi, seed_lo, seed_hi;
+};
+
+__device__ __forceinline__ void group_bar(int grp) {
+  asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
+}
+
+__device__ __forceinline__ int64_t reflect_index(int64_t idx, int64_t L) {
+  if (idx < 0) idx = -idx;
+  if (idx >= L) idx = 2 * (L - 1) - idx;
+  return idx;
+}
+
+// One augmented sample y[idx] = g * x[idx - k] + sigma * n[idx]; n[2i], n[2i+1]
+// are the (cos, sin) Box-Muller pair of the first two words of
+// Philox(counter = (i, 1, clip_lo, clip_hi), key = seed).
+__device__ __forceinline__ float aug_sample(const float* __restrict__ x, int64_t idx, int64_t L,
+                                            const AugState& a) {
+  const int64_t src = idx - a.k;
+  float v = (src >= 0 && src < L) ? __fmul_rn(a.g, __ldg(x + src)) : 0.f;
+  if (a.sigma > 0.f) {
+    u32x4 c;
+    c.x = static_cast<uint32_t>(idx >> 1); c.y = kStreamNoise; c.z = a.c_lo; c.w = a.c_hi;
+    const u32x4 r = philox4x32_10(c, a.seed_lo, a.seed_hi);
+    const float rad = sqrtf(-2.0f * logf(u01(r.x)));
+    float sn, cs;
+    sincospif(2.0f * u01(r.y), &sn, &cs);
+    const float z = (idx & 1) ? rad * sn : rad * cs;
+    v = __fadd_rn(v, __fmul_rn(a.sigma, z));
+  }
+  return v;
+}
+
+template <bool AUG>
+__global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_w = smem;
+  int* s_band = reinterpret_cast<int*>(s_w + kMaxNnz);
+  float* s_win = reinterpret_cast<float*>(s_band + 3 * kMaxMels);
+  float* s_grp = s_win + kNfft;
+  float* s_tile = s_grp + kGroups * (kBufA + kBufB);
+
+  const int tid = threadIdx.x;
+  const int grp = tid >> 6;
+  const int t = tid & 63;
+  const int clip = blockIdx.x / p.chunks;
+  const int chunk = blockIdx.x - clip * p.chunks;
+
+  for (int i = tid; i < p.nnz; i += kThreads) s_w[i] = p.weights[i];
+  for (int i = tid; i < 3 * kMaxMels; i += kThreads) s_band[i] = p.band[i];
+  for (int i = tid; i < kNfft; i += kThreads) s_win[i] = p.window[i];
+
+  ThreadTw tw;
+  load_thread_tw(tw, t, p.tw1024);
+
+  // this thread's (up to) two mel filters: t and, mirrored for balance, n_mels-1-t
+  int mel_id[2];
+  float mel_mean[2], mel_std[2];
+  mel_id[0] = (t < p.n_mels) ? t : -1;
+  mel_id[1] = (p.n_mels - 1 - t >= kGroup) ? p.n_mels - 1 - t : -1;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    mel_mean[i] = mel_id[i] >= 0 ? p.mean[mel_id[i]] : 0.f;
+    mel_std[i] = mel_id[i] >= 0 ? p.stdv[mel_id[i]] : 1.f;
+  }
+
+  const float* __restrict__ x = p.wav + static_cast<int64_t>(clip) * p.L;
+
+  AugState aug;
+  if (AUG) {
+    const uint64_t cg = p.first_clip + static_cast<uint64_t>(clip);
+    aug.c_lo = static_cast<uint32_t>(cg);
+    aug.c_hi = static_cast<uint32_t>(cg >> 32);
+    aug.seed_lo = p.seed_lo;
+    aug.seed_hi = p.seed_hi;
+    u32x4 c;
+    c.x = 0u; c.y = kStreamParams; c.z = aug.c_lo; c.w = aug.c_hi;
+    const u32x4 r = philox4x32_10(c, p.seed_lo, p.seed_hi);
+    const float gain_db = __fadd_rn(p.gain_lo, __fmul_rn(__fsub_rn(p.gain_hi, p.gain_lo), u01(r.x)));
+    aug.g = exp10f(__fmul_rn(gain_db, 0.05f));
+    const int span = 2 * p.max_shift + 1;
+    int draw = static_cast<int>(floorf(__fmul_rn(u01(r.y), static_cast<float>(span))));
+    if (draw > span - 1) draw = span - 1;
+    aug.k = draw - p.max_shift;
+    aug.sigma = __fadd_rn(p.noise_lo, __fmul_rn(__fsub_rn(p.noise_hi, p.noise_lo), u01(r.z)));
+  }
+  __syncthreads();
+
+  float* bufA = s_grp + grp * (kBufA + kBufB);
+  float* bufB = bufA + kBufA;
+
+  const int t0 = chunk * kFramesPerCta;
+  const int nfr = min(kFramesPerCta, p.T - t0);
+  const int f_begin = grp * kFramesPerGroup;
+  const int f_end = min(f_begin + kFramesPerGroup, nfr);
+  const float2* s_win2 = reinterpret_cast<const float2*>(s_win);
+
+  for (int fl = f_begin; fl < f_end; ++fl) {
+    const int64_t s0 = static_cast<int64_t>(t0 + fl) * p.hop - p.pad;
+    cpx z[8];
+    const bool interior = (s0 >= 0) && (s0 + kNfft <= p.L);
+    if (!AUG && interior && ((reinterpret_cast<uintptr_t>(x + s0) & 7) == 0)) {
+      const float2* x2 = reinterpret_cast<const float2*>(x + s0);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int n = t + 64 * r;
+        const float2 v = __ldg(x2 + n);
+        const float2 w = s_win2[n];
+        z[r].re = v.x * w.x;
+        z[r].im = v.y * w.y;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int n = t + 64 * r;
+        int64_t i0 = s0 + 2 * n, i1 = i0 + 1;
+        if (!interior) {
+          i0 = reflect_index(i0, p.L);
+          i1 = reflect_index(i1, p.L);
+        }
+        float v0, v1;
+        if (AUG) {
+          v0 = aug_sample(x, i0, p.L, aug);
+          v1 = aug_sample(x, i1, p.L, aug);
+        } else {
+          v0 = __ldg(x + i0);
+          v1 = __ldg(x + i1);
+        }
+        const float2 w = s_win2[n];
+        z[r].re = v0 * w.x;
+        z[r].im = v1 * w.y;
+      }
+    }
+    phase_a(t, z, tw, bufA);
+    group_bar(grp);
+    phase_b(t, tw, bufA, bufB);
+    group_bar(grp);
+    phase_c(t, bufB, bufA);
+    group_bar(grp);
+    phase_d(t, tw, bufA, bufB);
+    group_bar(grp);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int m = mel_id[i];
+      if (m >= 0) {
+        const int lo = s_band[m];
+        const int len = s_band[kMaxMels + m];
+        const int off = s_band[2 * kMaxMels + m];
+        const float e = mel_dot(bufB, s_w + off, lo, len);
+        const float v = p.log_mult * log10f(e + p.log_eps);
+        s_tile[m * kTileStride + fl] = (v - mel_mean[i]) / mel_std[i];
+      }
+    }
+  }
+  __syncthreads();
+
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  if (lane < nfr) {
+    float* o = p.out + (static_cast<int64_t>(clip) * p.n_mels) * p.T + t0 + lane;
+    for (int m = warp; m < p.n_mels; m += kThreads / 32) {
+      o[static_cast<int64_t>(m) * p.T] = s_tile[m * kTileStride + lane];
+    }
+  }
+}
+
+int num_frames(const afs_logmel_cfg& cfg, int64_t L) {
+  if (cfg.center) return static_cast<int>(1 + L / cfg.hop);
+  if (L < cfg.n_fft) return 0;
+  return static_cast<int>(1 + (L - cfg.n_fft) / cfg.hop);
+}
+
+}  // namespace
+}  // namespace afs
+
+extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb_host,
+                                      const float* window_host, int device,
+                                      afs_logmel_plan** plan_out) {
+  using namespace afs;
+  if (cfg == nullptr || fb_host == nullptr || window_host == nullptr || plan_out == nullptr)
+    return AFS_ERR_INVALID_ARG;
+  if (cfg->hop < 1 || cfg->n_mels < 1) return AFS_ERR_INVALID_ARG;
+  if (cfg->n_fft != kNfft || cfg->n_mels > kMaxMels) return AFS_ERR_UNSUPPORTED;
+
+  // pack each filter's non-zero span [lo, lo+len)
+  std::vector<int> band(3 * kMaxMels, 0);
+  std::vector<float> weights;
+  for (int m = 0; m < cfg->n_mels; ++m) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < kBins; ++k) {
+      if (fb_host[static_cast<size_t>(k) * cfg->n_mels + m] != 0.f) {
+        if (lo < 0) lo = k;
+        hi = k;
+      }
+    }
+    const int len = lo < 0 ? 0 : hi - lo + 1;
+    band[m] = lo < 0 ? 0 : lo;
+    band[kMaxMels + m] = len;
+    band[2 * kMaxMels + m] = static_cast<int>(weights.size());
+    for (int i = 0; i < len; ++i)
+      weights.push_back(fb_host[static_cast<size_t>(lo + i) * cfg->n_mels + m]);
+  }
+  if (weights.size() > static_cast<size_t>(kMaxNnz)) return AFS_ERR_UNSUPPORTED;
+  if (weights.empty()) weights.push_back(0.f);
+
+  std::vector<float2> tw(kNfft);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int k = 0; k < kNfft; ++k) {
+    const double a = two_pi * k / kNfft;
+    tw[k] = make_float2(static_cast<float>(cos(a)), static_cast<float>(-sin(a)));
+  }
+
+  afs_logmel_plan* plan = new (std::nothrow) afs_logmel_plan();
+  if (plan == nullptr) return AFS_ERR_INVALID_ARG;
+  plan->cfg = *cfg;
+  plan->device = device;
+  plan->nnz = static_cast<int>(weights.size());
+  plan->d_window = nullptr; plan->d_tw1024 = nullptr; plan->d_band = nullptr; plan->d_weights = nullptr;
+
+  int prev = 0;
+  cudaError_t e = cudaGetDevice(&prev);
+  if (e == cudaSuccess) e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&plan->d_window, kNfft * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&plan->d_tw1024, kNfft * sizeof(float2));
+  if (e == cudaSuccess) e = cudaMalloc(&plan->d_band, band.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&plan->d_weights, weights.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(plan->d_window, window_host, kNfft * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(plan->d_tw1024, tw.data(), kNfft * sizeof(float2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(plan->d_band, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(plan->d_weights, weights.data(), weights.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes));
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    afs_logmel_plan_destroy(plan);
+    return cuda_fail(e);
+  }
+  *plan_out = plan;
+  return AFS_OK;
+}
+
+extern "C" int afs_logmel_plan_destroy(afs_logmel_plan* plan) {
+  if (plan == nullptr) return AFS_OK;
+  cudaFree(plan->d_window);
+  cudaFree(plan->d_tw1024);
+  cudaFree(plan->d_band);
+  cudaFree(plan->d_weights);
+  delete plan;
+  return AFS_OK;
+}
+
+extern "C" int afs_logmel_num_frames(const afs_logmel_plan* plan, int64_t L) {
+  if (plan == nullptr || L < 0) return AFS_ERR_INVALID_ARG;
+  return afs::num_frames(plan->cfg, L);
+}
+
+extern "C" int afs_logmel_fwd(const afs_logmel_plan* plan, const float* wav, int32_t B, int64_t L,
+                              const float* mean, const float* std, const afs_aug_cfg* aug,
+                              uint64_t seed, uint64_t first_clip_index, float* out,
+                              afs_stream_t stream_) {
+  using namespace afs;
+  if (plan == nullptr || wav == nullptr || mean == nullptr || std == nullptr || out == nullptr ||
+      B < 0 || L < 1)
+    return AFS_ERR_INVALID_ARG;
+  const afs_logmel_cfg& cfg = plan->cfg;
+  const int pad = cfg.center ? kNfft / 2 : 0;
+  if (cfg.center && L <= pad) return AFS_ERR_INVALID_ARG;  // reflect padding needs pad < L
+  if (aug != nullptr && (aug->max_shift < 0 || aug->noise_std_lo < 0.f || aug->noise_std_hi < aug->noise_std_lo ||
+                         aug->gain_db_hi < aug->gain_db_lo))
+    return AFS_ERR_INVALID_ARG;
+  const int T = num_frames(cfg, L);
+  if (B == 0 || T <= 0) return AFS_OK;
+
+  Params p;
+  p.wav = wav; p.out = out; p.mean = mean; p.stdv = std;
+  p.window = plan->d_window; p.tw1024 = plan->d_tw1024; p.band = plan->d_band; p.weights = plan->d_weights;
+  p.L = L; p.nnz = plan->nnz; p.B = B; p.T = T; p.hop = cfg.hop; p.n_mels = cfg.n_mels; p.pad = pad;
+  p.chunks = (T + kFramesPerCta - 1) / kFramesPerCta;
+  p.log_mult = cfg.log_mult; p.log_eps = cfg.log_eps;
+  p.gain_lo = p.gain_hi = p.noise_lo = p.noise_hi = 0.f; p.max_shift = 0;
+  p.seed_lo = static_cast<uint32_t>(seed); p.seed_hi = static_cast<uint32_t>(seed >> 32);
+  p.first_clip = first_clip_index;
+  const int64_t grid = static_cast<int64_t>(B) * p.chunks;
+  if (grid > 0x7fffffffLL) return AFS_ERR_UNSUPPORTED;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (aug != nullptr) {
+    p.gain_lo = aug->gain_db_lo; p.gain_hi = aug->gain_db_hi;
+    p.noise_lo = aug->noise_std_lo; p.noise_hi = aug->noise_std_hi;
+    p.max_shift = aug->max_shift;
+    logmel_kernel<true><<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(p);
+  } else {
+    logmel_kernel<false><<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(p);
+  }
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
+}

@@ -1,0 +1,368 @@
+// ProtoNet / DeepBDC prototype head for sm_100a.
+//
+// Arithmetic follows ProtoLayer.forward (reference libfewshot_core/model/metric/
+// proto_net.py:49-63) and deepbdc.ProtoLayer.forward (deepbdc.py:34-53):
+//   p[e,w,:] = (1/S) sum_s support[e,w,s,:]
+//   euclid :  logit = -sum_d (q_d - p_d)^2      (direct difference, fp32)
+//   cosine :  logit = <q, p> / (max(|q|,1e-12) max(|p|,1e-12))
+//   dot    :  logit = <q, p>
+// The reference materialises a [t,wq,w,c] temporary and launches one ATen op
+// per step and per episode; here one CTA per (episode, row split) keeps the
+// episode's prototypes in shared memory and streams every query row from HBM
+// exactly once with 128-bit loads.  HBM-bound: 4*W*(S+Q)*D + 4*WQ*W bytes per
+// episode.
+#include "common.cuh"
+
+namespace afs {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxWay = 32;
+constexpr size_t kSmemProtoLimit = 160 * 1024;
+
+__global__ void __launch_bounds__(256) proto_mean_kernel(const float* __restrict__ feat,
+                                                         int64_t ld,
+                                                         const int32_t* __restrict__ cls_row,
+                                                         int EW, int S, int D4,
+                                                         float4* __restrict__ protos) {
+  const int64_t total = static_cast<int64_t>(EW) * D4;
+  const float inv = static_cast<float>(S);
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx / D4);
+    const int c = static_cast<int>(idx - static_cast<int64_t>(g) * D4);
+    const float* base = feat + static_cast<int64_t>(cls_row[g]) * ld + 4 * c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < S; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(base + s * ld);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    protos[idx] = make_float4(acc.x / inv, acc.y / inv, acc.z / inv, acc.w / inv);
+  }
+}
+
+template <int MODE, int WT, int RW, bool SMEM_PROTO>
+__global__ void __launch_bounds__(kThreads)
+proto_fwd_kernel(const float* __restrict__ feat, int64_t ld, const int32_t* __restrict__ cls_row,
+                 int W, int S, int D4, float* __restrict__ logits, int32_t* __restrict__ pred,
+                 const float4* __restrict__ protos_g) {
+  extern __shared__ float4 s_proto[];  // [W][D4] when SMEM_PROTO
+  __shared__ int s_qbase[kMaxWay + 1];
+  __shared__ float s_pinv[kMaxWay];
+
+  const int e = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+
+  if (tid <= W) {
+    const int g = e * W + tid;
+    s_qbase[tid] = cls_row[g] - g * S;
+  }
+  const float4* proto;
+  if (SMEM_PROTO) {
+    const float fS = static_cast<float>(S);
+    for (int idx = tid; idx < W * D4; idx += kThreads) {
+      const int w = idx / D4;
+      const int c = idx - w * D4;
+      const float* base = feat + static_cast<int64_t>(cls_row[e * W + w]) * ld + 4 * c;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < S; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(base + s * ld);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      s_proto[idx] = make_float4(acc.x / fS, acc.y / fS, acc.z / fS, acc.w / fS);
+    }
+    proto = s_proto;
+  } else {
+    proto = protos_g + static_cast<int64_t>(e) * W * D4;
+  }
+  __syncthreads();
+
+  if (MODE == AFS_PROTO_COSINE) {
+    for (int w = warp; w < W; w += kWarps) {
+      float ss = 0.f;
+      for (int c = lane; c < D4; c += 32) {
+        const float4 p = proto[w * D4 + c];
+        ss = fmaf(p.x, p.x, ss); ss = fmaf(p.y, p.y, ss);
+        ss = fmaf(p.z, p.z, ss); ss = fmaf(p.w, p.w, ss);
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) s_pinv[w] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+    __syncthreads();
+  }
+
+  const int out0 = s_qbase[0];
+  const int out1 = s_qbase[W];
+  const int ngroups = (out1 - out0 + RW - 1) / RW;
+
+  for (int grp = blockIdx.y * kWarps + warp; grp < ngroups; grp += gridDim.y * kWarps) {
+    const int o_base = out0 + grp * RW;
+    const float* qptr[RW];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      int o = o_base + r;
+      if (o >= out1) o = out1 - 1;  // tail rows recompute the last row; never stored
+      int w = 0;
+      while (s_qbase[w + 1] <= o) ++w;
+      qptr[r] = feat + static_cast<int64_t>(o + (e * W + w + 1) * S) * ld;
+    }
+
+    float acc[RW][WT];
+    float qq[RW];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      qq[r] = 0.f;
+#pragma unroll
+      for (int w = 0; w < WT; ++w) acc[r][w] = 0.f;
+    }
+
+    for (int c = lane; c < D4; c += 32) {
+      float4 q[RW];
+#pragma unroll
+      for (int r = 0; r < RW; ++r) q[r] = ldg_stream4(qptr[r] + 4 * c);
+      if (MODE == AFS_PROTO_COSINE) {
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+          qq[r] = fmaf(q[r].x, q[r].x, qq[r]); qq[r] = fmaf(q[r].y, q[r].y, qq[r]);
+          qq[r] = fmaf(q[r].z, q[r].z, qq[r]); qq[r] = fmaf(q[r].w, q[r].w, qq[r]);
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < WT; ++w) {
+        if (w < W) {
+          const float4 p = proto[w * D4 + c];
+#pragma unroll
+          for (int r = 0; r < RW; ++r) {
+            if (MODE == AFS_PROTO_EUCLIDEAN) {
+              const float dx = q[r].x - p.x, dy = q[r].y - p.y;
+              const float dz = q[r].z - p.z, dw = q[r].w - p.w;
+              acc[r][w] = fmaf(dx, dx, acc[r][w]); acc[r][w] = fmaf(dy, dy, acc[r][w]);
+              acc[r][w] = fmaf(dz, dz, acc[r][w]); acc[r][w] = fmaf(dw, dw, acc[r][w]);
+            } else {
+              acc[r][w] = fmaf(q[r].x, p.x, acc[r][w]); acc[r][w] = fmaf(q[r].y, p.y, acc[r][w]);
+              acc[r][w] = fmaf(q[r].z, p.z, acc[r][w]); acc[r][w] = fmaf(q[r].w, p.w, acc[r][w]);
+            }
+          }
+        }
+      }
+    }
+
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      if (MODE == AFS_PROTO_COSINE) qq[r] = warp_sum(qq[r]);
+#pragma unroll
+      for (int w = 0; w < WT; ++w) acc[r][w] = warp_sum(acc[r][w]);
+    }
+
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      const int o = o_base + r;
+      if (lane == r && o < out1) {
+        float best = -INFINITY;
+        int best_w = 0;
+        const float qinv = (MODE == AFS_PROTO_COSINE) ? 1.0f / fmaxf(sqrtf(qq[r]), 1e-12f) : 1.f;
+#pragma unroll
+        for (int w = 0; w < WT; ++w) {
+          if (w < W) {
+            float v;
+            if (MODE == AFS_PROTO_EUCLIDEAN) v = -acc[r][w];
+            else if (MODE == AFS_PROTO_COSINE) v = acc[r][w] * qinv * s_pinv[w];
+            else v = acc[r][w];
+            logits[static_cast<int64_t>(o) * W + w] = v;
+            if (v > best) { best = v; best_w = w; }
+          }
+        }
+        if (pred != nullptr) pred[o] = best_w;
+      }
+    }
+  }
+}
+
+template <int MODE, int WT, int RW, bool SMEM_PROTO>
+int launch_fwd(const float* feat, int64_t ld, const int32_t* cls_row, int N, int E, int W, int S,
+               int D, float* logits, int32_t* pred, const float4* protos_g,
+               cudaStream_t stream) {
+  auto kern = proto_fwd_kernel<MODE, WT, RW, SMEM_PROTO>;
+  const size_t smem = SMEM_PROTO ? static_cast<size_t>(W) * D * sizeof(float) : 0;
+  if (smem > 48 * 1024) {
+    AFS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  }
+  const int nq = N - E * W * S;
+  const int avg_groups = (nq / (E > 0 ? E : 1) + RW - 1) / RW;
+  int max_split = (avg_groups + kWarps - 1) / kWarps;
+  if (max_split < 1) max_split = 1;
+  int want = (2 * kNumSMs + E - 1) / E;
+  int nsplit = want < max_split ? want : max_split;
+  if (nsplit < 1) nsplit = 1;
+  dim3 grid(E, nsplit);
+  kern<<<grid, kThreads, smem, stream>>>(feat, ld, cls_row, W, S, D / 4, logits, pred, protos_g);
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
+}
+
+template <int MODE, bool SMEM_PROTO>
+int dispatch_way(const float* feat, int64_t ld, const int32_t* cls_row, int N, int E, int W,
+                 int S, int D, float* logits, int32_t* pred, const float4* protos_g,
+                 cudaStream_t stream) {
+  if (W <= 5)
+    return launch_fwd<MODE, 5, 4, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+  if (W <= 8)
+    return launch_fwd<MODE, 8, 2, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+  if (W <= 16)
+    return launch_fwd<MODE, 16, 1, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+  return launch_fwd<MODE, 32, 1, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+}
+
+template <bool SMEM_PROTO>
+int dispatch_mode(int mode, const float* feat, int64_t ld, const int32_t* cls_row, int N, int E,
+                  int W, int S, int D, float* logits, int32_t* pred, const float4* protos_g,
+                  cudaStream_t stream) {
+  switch (mode) {
+    case AFS_PROTO_EUCLIDEAN:
+      return dispatch_way<AFS_PROTO_EUCLIDEAN, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+    case AFS_PROTO_COSINE:
+      return dispatch_way<AFS_PROTO_COSINE, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+    case AFS_PROTO_DOT:
+      return dispatch_way<AFS_PROTO_DOT, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+    default:
+      return AFS_ERR_INVALID_ARG;
+  }
+}
+
+// Backward: one thread per feature column d, one CTA per (episode, column
+// slice); prototypes and their gradients live in registers, so nothing is
+// reduced across threads and no atomics are needed.
+//   euclid: dq = -2 sum_w G_w (q - p_w);  dp_w =  2 sum_o G_ow (q_o - p_w)
+//   dot   : dq =    sum_w G_w p_w;        dp_w =    sum_o G_ow q_o
+//   d support_{w,s} = dp_w / S
+template <int MODE, int WT>
+__global__ void __launch_bounds__(128)
+proto_bwd_kernel(const float* __restrict__ feat, int64_t ld, const int32_t* __restrict__ cls_row,
+                 int W, int S, int D, const float* __restrict__ grad_logits,
+                 float* __restrict__ grad_feat, int64_t ldg) {
+  const int e = blockIdx.x;
+  const int d = blockIdx.y * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float p[WT], dp[WT];
+  const float fS = static_cast<float>(S);
+#pragma unroll
+  for (int w = 0; w < WT; ++w) {
+    p[w] = 0.f;
+    dp[w] = 0.f;
+    if (w < W) {
+      const int row0 = cls_row[e * W + w];
+      float acc = 0.f;
+      for (int s = 0; s < S; ++s) acc += feat[static_cast<int64_t>(row0 + s) * ld + d];
+      p[w] = acc / fS;
+    }
+  }
+  for (int wc = 0; wc < W; ++wc) {
+    const int g = e * W + wc;
+    const int r0 = cls_row[g] + S;
+    const int r1 = cls_row[g + 1];
+    for (int row = r0; row < r1; ++row) {
+      const int o = row - (g + 1) * S;
+      const float q = feat[static_cast<int64_t>(row) * ld + d];
+      const float* G = grad_logits + static_cast<int64_t>(o) * W;
+      float gq = 0.f;
+#pragma unroll
+      for (int w = 0; w < WT; ++w) {
+        if (w < W) {
+          const float gw = __ldg(G + w);
+          if (MODE == AFS_PROTO_EUCLIDEAN) {
+            const float diff = q - p[w];
+            gq = fmaf(-2.f * gw, diff, gq);
+            dp[w] = fmaf(2.f * gw, diff, dp[w]);
+          } else {
+            gq = fmaf(gw, p[w], gq);
+            dp[w] = fmaf(gw, q, dp[w]);
+          }
+        }
+      }
+      grad_feat[static_cast<int64_t>(row) * ldg + d] = gq;
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < WT; ++w) {
+    if (w < W) {
+      const int row0 = cls_row[e * W + w];
+      const float v = dp[w] / fS;
+      for (int s = 0; s < S; ++s) grad_feat[static_cast<int64_t>(row0 + s) * ldg + d] = v;
+    }
+  }
+}
+
+template <int MODE>
+int launch_bwd(const float* feat, int64_t ld, const int32_t* cls_row, int E, int W, int S, int D,
+               const float* grad_logits, float* grad_feat, int64_t ldg, cudaStream_t stream) {
+  dim3 grid(E, (D + 127) / 128);
+  if (W <= 8)
+    proto_bwd_kernel<MODE, 8><<<grid, 128, 0, stream>>>(feat, ld, cls_row, W, S, D, grad_logits, grad_feat, ldg);
+  else
+    proto_bwd_kernel<MODE, 32><<<grid, 128, 0, stream>>>(feat, ld, cls_row, W, S, D, grad_logits, grad_feat, ldg);
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
+}
+
+bool args_ok(const void* feat, int64_t ld, const void* cls_row, int N, int E, int W, int S, int D) {
+  return feat != nullptr && cls_row != nullptr && E >= 0 && W >= 1 && W <= kMaxWay && S >= 1 &&
+         D >= 4 && (D % 4) == 0 && ld >= D && (ld % 4) == 0 && N >= E * W * S &&
+         (reinterpret_cast<uintptr_t>(feat) % 16) == 0;
+}
+
+}  // namespace
+}  // namespace afs
+
+extern "C" size_t afs_proto_workspace_bytes(int32_t E, int32_t W, int32_t S, int32_t D) {
+  (void)S;
+  if (E <= 0 || W <= 0 || D <= 0) return 0;
+  const size_t per_episode = static_cast<size_t>(W) * D * sizeof(float);
+  return per_episode <= afs::kSmemProtoLimit ? 0 : per_episode * static_cast<size_t>(E);
+}
+
+extern "C" int afs_proto_fwd(const float* feat, int64_t ld_feat, const int32_t* cls_row, int32_t N,
+                             int32_t E, int32_t W, int32_t S, int32_t D, int32_t mode,
+                             float* logits, int32_t* pred, void* ws, size_t ws_bytes,
+                             afs_stream_t stream_) {
+  using namespace afs;
+  if (!args_ok(feat, ld_feat, cls_row, N, E, W, S, D) || logits == nullptr) return AFS_ERR_INVALID_ARG;
+  if (E == 0 || N == E * W * S) return AFS_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t need = afs_proto_workspace_bytes(E, W, S, D);
+  if (need == 0) {
+    return dispatch_mode<true>(mode, feat, ld_feat, cls_row, N, E, W, S, D, logits, pred, nullptr, stream);
+  }
+  if (ws == nullptr || ws_bytes < need) return AFS_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(ws) % 16 != 0) return AFS_ERR_INVALID_ARG;
+  float4* protos = static_cast<float4*>(ws);
+  const int64_t total = static_cast<int64_t>(E) * W * (D / 4);
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  proto_mean_kernel<<<blocks, 256, 0, stream>>>(feat, ld_feat, cls_row, E * W, S, D / 4, protos);
+  AFS_LAUNCH_CHECK();
+  return dispatch_mode<false>(mode, feat, ld_feat, cls_row, N, E, W, S, D, logits, pred, protos, stream);
+}
+
+extern "C" int afs_proto_bwd(const float* feat, int64_t ld_feat, const int32_t* cls_row, int32_t N,
+                             int32_t E, int32_t W, int32_t S, int32_t D, int32_t mode,
+                             const float* grad_logits, float* grad_feat, int64_t ld_grad,
+                             afs_stream_t stream_) {
+  using namespace afs;
+  if (!args_ok(feat, ld_feat, cls_row, N, E, W, S, D) || grad_logits == nullptr ||
+      grad_feat == nullptr || ld_grad < D)
+    return AFS_ERR_INVALID_ARG;
+  if (E == 0) return AFS_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  switch (mode) {
+    case AFS_PROTO_EUCLIDEAN:
+      return launch_bwd<AFS_PROTO_EUCLIDEAN>(feat, ld_feat, cls_row, E, W, S, D, grad_logits, grad_feat, ld_grad, stream);
+    case AFS_PROTO_DOT:
+      return launch_bwd<AFS_PROTO_DOT>(feat, ld_feat, cls_row, E, W, S, D, grad_logits, grad_feat, ld_grad, stream);
+    default:
+      return AFS_ERR_UNSUPPORTED;
+  }
+}

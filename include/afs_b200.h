@@ -1,0 +1,168 @@
+/*
+ * afs_b200.h -- C ABI of the B200-native episodic few-shot audio hot path.
+ *
+ * One shared library (libafs_b200.so, built by audio_fewshot_b200/build.py with
+ * nvcc -gencode arch=compute_100a,code=sm_100a) exports exactly the entry points
+ * below.  Plain pointers and sizes only: no torch types, no C++ types, no
+ * exceptions across the boundary.  All data pointers are DEVICE pointers unless
+ * the parameter name ends in `_host`.  Every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*), allocates nothing (plans excepted), does
+ * not synchronise, and is re-entrant.  The caller owns every buffer.
+ *
+ * Return value: AFS_OK (0) or a negative afs_status.  afs_status_string() maps
+ * it to text; afs_last_cuda_error() returns the cudaError_t of the last failing
+ * CUDA runtime call made by the calling thread inside this library.
+ *
+ * Each entry point cites the reference interface (Jerryaa98/Audio-Fewshot,
+ * paths relative to the reference root) whose arithmetic it replaces.
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef AFS_B200_H_
+#define AFS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFS_ABI_VERSION 1
+
+typedef void* afs_stream_t; /* cudaStream_t */
+
+typedef enum afs_status {
+  AFS_OK = 0,
+  AFS_ERR_INVALID_ARG = -1,  /* null pointer, negative size, unsupported shape */
+  AFS_ERR_UNSUPPORTED = -2,  /* valid but not built (e.g. n_fft != 1024)       */
+  AFS_ERR_CUDA = -3,         /* a CUDA runtime call failed; see afs_last_cuda_error */
+  AFS_ERR_WORKSPACE = -4     /* workspace too small                              */
+} afs_status;
+
+int afs_abi_version(void);
+const char* afs_status_string(int status);
+int afs_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------
+ * (1) Fused waveform -> normalised log-mel front-end.
+ *
+ * Replaces the (absent) offline feature extraction that
+ * produced the reference's `*_spec` folders (config/headers/data.yaml:1) and
+ * the `(x-mean)/std` step of libfewshot_core/audio_augmentations.py:36-53
+ * with statistics from Auxiliary/*_Mean_Std.npy (libfewshot_core/test.py:398-399).
+ * Canonical spec (oracle/frontend.py): reflect-pad n_fft/2, frame, window,
+ * |rFFT|^2, mel projection, log_mult*log10(. + log_eps), (. - mean[m])/std[m].
+ * Output layout [B, 1, n_mels, T] fp32 contiguous, T = 1 + L/hop (center) --
+ * the `image` tensor every set_forward consumes (proto_net.py:86-90).
+ * No spectrum is ever written to HBM.
+ * ---------------------------------------------------------------------- */
+typedef struct afs_logmel_cfg {
+  int32_t n_fft;    /* 1024 (the only size built)                       */
+  int32_t hop;      /* >= 1                                             */
+  int32_t n_mels;   /* 1..128                                           */
+  int32_t center;   /* 1: reflect padding of n_fft/2 on both sides      */
+  float log_mult;   /* 10.0f for dB                                     */
+  float log_eps;    /* added to the mel power before the log            */
+} afs_logmel_cfg;
+
+/* Waveform-domain augmentation (new functionality).  Randomness
+ * is Philox4x32-10 keyed by (seed, global clip index); see oracle/philox.py.
+ * A field pair with lo == hi disables the draw (fixed value).             */
+typedef struct afs_aug_cfg {
+  float gain_db_lo, gain_db_hi; /* gain g = 10^(U[lo,hi]/20)                      */
+  int32_t max_shift;            /* time shift k ~ U{-max_shift..max_shift}, zero fill */
+  float noise_std_lo, noise_std_hi; /* additive N(0, sigma^2), sigma ~ U[lo,hi]      */
+} afs_aug_cfg;
+
+typedef struct afs_logmel_plan afs_logmel_plan; /* opaque; owns device tables */
+
+/* fb_host: dense mel filterbank [n_fft/2+1, n_mels] row-major (torchaudio
+ * melscale_fbanks layout); window_host: [n_fft].  Both HOST pointers; the
+ * plan packs each filter's contiguous non-zero band and uploads it together
+ * with the window and the FFT twiddles.  device: CUDA device ordinal.      */
+int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb_host,
+                           const float* window_host, int device, afs_logmel_plan** plan_out);
+int afs_logmel_plan_destroy(afs_logmel_plan* plan);
+/* number of output frames for clips of L samples */
+int afs_logmel_num_frames(const afs_logmel_plan* plan, int64_t L);
+
+/* wav [B, L] fp32; mean/std [n_mels] fp32 (per-bin; broadcast the scalar of
+ * Auxiliary/*_Mean_Std.npy into it); aug nullable; out [B, 1, n_mels, T].  */
+int afs_logmel_fwd(const afs_logmel_plan* plan, const float* wav, int32_t B, int64_t L,
+                   const float* mean, const float* std, const afs_aug_cfg* aug,
+                   uint64_t seed, uint64_t first_clip_index, float* out, afs_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Episode row table shared by the heads (replaces the host slicing of
+ * AbstractModel.split_by_episode, libfewshot_core/model/abstract_model.py:176-332).
+ * Rows of `feat` are episode-major, class-major; block g = e*W + w holds S
+ * support rows followed by that class's query window rows.
+ *   cls_row[g]   = first row of block g, g in [0, E*W];  cls_row[E*W] = N.
+ * Query window r of block g sits at feat row cls_row[g]+S+r and its logits
+ * go to output row cls_row[g] - g*S + r (the order torch.cat gives at
+ * proto_net.py:106-113).
+ * ---------------------------------------------------------------------- */
+
+/* (2a) ProtoNet head: prototype mean + logits, and per-row argmax.
+ * Replaces ProtoLayer.forward (libfewshot_core/model/metric/proto_net.py:34-64)
+ * and deepbdc.ProtoLayer.forward (libfewshot_core/model/metric/deepbdc.py:27-53).
+ * mode: 0 = -sum_d (q-p)^2, 1 = cosine(q, p) with eps 1e-12, 2 = raw dot q.p.
+ * feat [N, D] (row stride ld_feat floats), logits [NQ, W], pred [NQ] nullable
+ * (argmax over W, lowest index on ties), NQ = N - E*W*S.  W <= 32.  D % 4 == 0
+ * and 16-byte aligned rows.  ws: scratch of afs_proto_workspace_bytes() (0 when
+ * the prototypes of one episode fit in shared memory; then ws may be NULL).   */
+#define AFS_PROTO_EUCLIDEAN 0
+#define AFS_PROTO_COSINE 1
+#define AFS_PROTO_DOT 2
+size_t afs_proto_workspace_bytes(int32_t E, int32_t W, int32_t S, int32_t D);
+int afs_proto_fwd(const float* feat, int64_t ld_feat, const int32_t* cls_row, int32_t N,
+                  int32_t E, int32_t W, int32_t S, int32_t D, int32_t mode, float* logits,
+                  int32_t* pred, void* ws, size_t ws_bytes, afs_stream_t stream);
+
+/* Backward of (2a) for set_forward_loss (proto_net.py:148-154 under autograd):
+ * grad_feat [N, D] (row stride ld_grad) is fully overwritten.  Modes 0 and 2. */
+int afs_proto_bwd(const float* feat, int64_t ld_feat, const int32_t* cls_row, int32_t N,
+                  int32_t E, int32_t W, int32_t S, int32_t D, int32_t mode,
+                  const float* grad_logits, float* grad_feat, int64_t ld_grad,
+                  afs_stream_t stream);
+
+/* (2b) DN4 head: L2-normalised local descriptors, cosine relation, top-n_k
+ * over each class's S*HW support descriptors, summed over the query's HW
+ * descriptors.  Replaces DN4Layer.forward (libfewshot_core/model/metric/dn4.py:39-75).
+ * feat [N, C, HW]; score [NQ, W]; topk_idx [NQ, W, HW, n_k] nullable (column
+ * index in [0, S*HW), descending value, lowest index on ties); pred nullable.
+ * 1 <= n_k <= min(8, S*HW); W <= 32.  ws/ws_bytes: scratch of
+ * afs_dn4_workspace_bytes() (normalised descriptors + per-descriptor sums). */
+size_t afs_dn4_workspace_bytes(int32_t N, int32_t E, int32_t W, int32_t S, int32_t C, int32_t HW);
+int afs_dn4_fwd(const float* feat, const int32_t* cls_row, int32_t N, int32_t E, int32_t W,
+                int32_t S, int32_t C, int32_t HW, int32_t n_k, float* score, int32_t* topk_idx,
+                int32_t* pred, void* ws, size_t ws_bytes, afs_stream_t stream);
+
+/* (2c) BDC matrix: Gram, pairwise squared distance between channels, exp(t)
+ * scale, sqrt, double centring, row-major upper triangle.  Replaces
+ * BDCovpool + Triuvec (libfewshot_core/model/backbone/utils/bdc_pool.py:69-93).
+ * x [B, C, M]; log_temp: device pointer to the scalar `temperature`;
+ * out [B, C*(C+1)/2] if triu else [B, C*C].  C <= 64 built.                 */
+int afs_bdc_fwd(const float* x, int32_t B, int32_t C, int32_t M, const float* log_temp,
+                int32_t triu, float* out, afs_stream_t stream);
+
+/* (3) Window argmax -> per-query majority vote -> accuracy, all on device.
+ * Replaces majority_vote + vote_catagorical_acc
+ * (libfewshot_core/utils/utils.py:432-446) and the per-query D2H syncs.
+ * logits [NQ, W]; q_start [nq+1] window offsets (exclusive cumsum of repeats);
+ * q_target [nq]; q_pred [nq] out (mode of the window argmaxes, smallest label
+ * on ties, as torch.mode); stats: int32[4] scratch+out, stats[0] = #correct,
+ * stats[1] = nq (stats[2..3] internal); acc_pct out = 100*correct/nq.  W <= 64. */
+int afs_vote_acc(const float* logits, int32_t W, const int32_t* q_start, int32_t nq,
+                 const int32_t* q_target, int32_t* q_pred, int32_t* stats, float* acc_pct,
+                 afs_stream_t stream);
+
+/* Energy score of DeepBDC (deepbdc.py:318-319 + utils.py:449-471):
+ * u[q] = -logsumexp_w( mean over the query's windows of logits[., w] ).     */
+int afs_energy_score(const float* logits, int32_t W, const int32_t* q_start, int32_t nq,
+                     float* energy, afs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFS_B200_H_ */
