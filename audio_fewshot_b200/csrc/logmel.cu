@@ -81,12 +81,6 @@ __device__ __forceinline__ void group_bar(int grp) {
   asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
 }
 
-__device__ __forceinline__ int64_t reflect_index(int64_t idx, int64_t L) {
-  if (idx < 0) idx = -idx;
-  if (idx >= L) idx = 2 * (L - 1) - idx;
-  return idx;
-}
-
 // One augmented sample y[idx] = g * x[idx - k] + sigma * n[idx]; n[2i], n[2i+1]
 // are the (cos, sin) Box-Muller pair of the first two words of
 // Philox(counter = (i, 1, clip_lo, clip_hi), key = seed).
@@ -258,24 +252,9 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   if (cfg->hop < 1 || cfg->n_mels < 1) return AFS_ERR_INVALID_ARG;
   if (cfg->n_fft != kNfft || cfg->n_mels > kMaxMels) return AFS_ERR_UNSUPPORTED;
 
-  // pack each filter's non-zero span [lo, lo+len)
-  std::vector<int> band(3 * kMaxMels, 0);
+  std::vector<int> band;
   std::vector<float> weights;
-  for (int m = 0; m < cfg->n_mels; ++m) {
-    int lo = -1, hi = -1;
-    for (int k = 0; k < kBins; ++k) {
-      if (fb_host[static_cast<size_t>(k) * cfg->n_mels + m] != 0.f) {
-        if (lo < 0) lo = k;
-        hi = k;
-      }
-    }
-    const int len = lo < 0 ? 0 : hi - lo + 1;
-    band[m] = lo < 0 ? 0 : lo;
-    band[kMaxMels + m] = len;
-    band[2 * kMaxMels + m] = static_cast<int>(weights.size());
-    for (int i = 0; i < len; ++i)
-      weights.push_back(fb_host[static_cast<size_t>(lo + i) * cfg->n_mels + m]);
-  }
+  pack_mel_bands(fb_host, cfg->n_mels, band, weights);
   if (weights.size() > static_cast<size_t>(kMaxNnz)) return AFS_ERR_UNSUPPORTED;
   if (weights.empty()) weights.push_back(0.f);
 

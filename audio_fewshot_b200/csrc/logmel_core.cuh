@@ -205,11 +205,42 @@ AFS_HD void phase_d(int u, const ThreadTw& tw, const float* bufA, float* power) 
   }
 }
 
+// Reflect padding index (torch.stft center=True, pad_mode="reflect"); needs pad < L.
+AFS_HD int64_t reflect_index(int64_t idx, int64_t L) {
+  if (idx < 0) idx = -idx;
+  if (idx >= L) idx = 2 * (L - 1) - idx;
+  return idx;
+}
+
 // Banded mel projection of one filter: sum_i w[off+i] * P[lo+i].
 AFS_HD float mel_dot(const float* power, const float* weights, int lo, int len) {
   float acc = 0.f;
   for (int i = 0; i < len; ++i) acc += weights[i] * power[lo + i];
   return acc;
+}
+
+// Host-side packing of a dense [kBins, n_mels] filterbank into per-filter spans:
+// band[m] = first non-zero bin, band[kMaxMels+m] = span length, band[2*kMaxMels+m] = offset
+// into `weights`.  Returns the number of packed weights.
+template <typename IntVec, typename FloatVec>
+inline int pack_mel_bands(const float* fb, int n_mels, IntVec& band, FloatVec& weights) {
+  band.assign(3 * kMaxMels, 0);
+  weights.clear();
+  for (int m = 0; m < n_mels; ++m) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < kBins; ++k) {
+      if (fb[static_cast<size_t>(k) * n_mels + m] != 0.f) {
+        if (lo < 0) lo = k;
+        hi = k;
+      }
+    }
+    const int len = lo < 0 ? 0 : hi - lo + 1;
+    band[m] = lo < 0 ? 0 : lo;
+    band[kMaxMels + m] = len;
+    band[2 * kMaxMels + m] = static_cast<int>(weights.size());
+    for (int i = 0; i < len; ++i) weights.push_back(fb[static_cast<size_t>(lo + i) * n_mels + m]);
+  }
+  return static_cast<int>(weights.size());
 }
 
 }  // namespace logmel

@@ -44,9 +44,10 @@ AFS_PHILOX_HD u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1) {
   return c;
 }
 
-// uint32 -> float in (0, 1): ((r >> 8) + 0.5) * 2^-24, exact in fp32.
+// uint32 -> float in (0, 1): ((r >> 9) + 0.5) * 2^-23; every step is exact in fp32
+// (2^23 - 0.5 needs 24 mantissa bits), so the value is bit-identical on host and device.
 AFS_PHILOX_HD float u01(uint32_t r) {
-  return (static_cast<float>(r >> 8) + 0.5f) * 5.9604644775390625e-08f;
+  return (static_cast<float>(r >> 9) + 0.5f) * 1.1920928955078125e-07f;
 }
 
 // Streams (counter word y): 0 = per-clip parameters, 1 = additive noise.

@@ -1,0 +1,206 @@
+"""Tensor-level wrappers over the C ABI (include/afs_b200.h).
+
+Each function checks device / dtype / contiguity, allocates the outputs with
+torch (device memory and streams are torch's job; the arithmetic is not) and
+launches the sm_100a kernel on torch's current CUDA stream.  Nothing here
+computes on the CPU and nothing falls back to PyTorch ops: a non-CUDA tensor or
+a missing libafs_b200.so raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PROTO_MODES = {"euclidean": 0, "cos_sim": 1, "dot": 2}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.AfsError("%s must be a CUDA tensor (no CPU fallback exists)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+# --------------------------------------------------------------------------- front-end
+class LogMelPlan:
+    """Owns an afs_logmel_plan (device tables: window, twiddles, packed mel bands)."""
+
+    def __init__(self, fb, window, hop, n_mels, center=True, log_mult=10.0, log_eps=2.220446049250313e-16,
+                 device=None):
+        if device is None:
+            device = torch.cuda.current_device()
+        device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.device = device
+        fb = np.ascontiguousarray(np.asarray(fb, dtype=np.float32))
+        window = np.ascontiguousarray(np.asarray(window, dtype=np.float32))
+        n_fft = window.shape[0]
+        if fb.shape != (n_fft // 2 + 1, n_mels):
+            raise ValueError("fb must be [n_fft/2+1, n_mels], got %s" % (fb.shape,))
+        self.cfg = _lib.LogMelCfg(n_fft, int(hop), int(n_mels), 1 if center else 0, float(log_mult), float(log_eps))
+        self.n_mels = int(n_mels)
+        self._handle = C.c_void_p(0)
+        h = _lib.lib()
+        _lib.check(h.afs_logmel_plan_create(C.byref(self.cfg), fb.ctypes.data_as(C.c_void_p),
+                                            window.ctypes.data_as(C.c_void_p), device.index or 0,
+                                            C.byref(self._handle)), "afs_logmel_plan_create")
+
+    def num_frames(self, L):
+        return int(_lib.lib().afs_logmel_num_frames(self._handle, int(L)))
+
+    def forward(self, wav, mean, std, aug=None, seed=0, first_clip_index=0, out=None):
+        """wav [B, L] fp32 CUDA -> [B, 1, n_mels, T] fp32.  mean/std: [n_mels] CUDA tensors."""
+        _need_cuda(wav, "wav")
+        _need_cuda(mean, "mean")
+        _need_cuda(std, "std")
+        if wav.dim() != 2:
+            raise ValueError("wav must be [B, L]")
+        if mean.numel() != self.n_mels or std.numel() != self.n_mels:
+            raise ValueError("mean/std must have n_mels entries")
+        wav = wav.contiguous()
+        B, L = wav.shape
+        T = self.num_frames(L)
+        if out is None:
+            out = torch.empty((B, 1, self.n_mels, T), dtype=torch.float32, device=wav.device)
+        elif tuple(out.shape) != (B, 1, self.n_mels, T) or not out.is_contiguous():
+            raise ValueError("out has the wrong shape")
+        aug_ref = None
+        if aug is not None:
+            aug_ref = C.byref(_lib.AugCfg(float(aug["gain_db"][0]), float(aug["gain_db"][1]),
+                                          int(aug.get("max_shift", 0)),
+                                          float(aug["noise_std"][0]), float(aug["noise_std"][1])))
+        _lib.check(_lib.lib().afs_logmel_fwd(self._handle, _ptr(wav), B, L, _ptr(mean.contiguous()),
+                                             _ptr(std.contiguous()), aug_ref, int(seed), int(first_clip_index),
+                                             _ptr(out), _stream()), "afs_logmel_fwd")
+        return out
+
+    def __del__(self):
+        try:
+            if self._handle:
+                _lib.lib().afs_logmel_plan_destroy(self._handle)
+                self._handle = C.c_void_p(0)
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------- heads
+def _proto_call(feat, cls_row, E, W, S, mode, want_pred):
+    _need_cuda(feat, "feat")
+    _need_cuda(cls_row, "cls_row", torch.int32)
+    if feat.dim() != 2:
+        raise ValueError("feat must be [N, D]")
+    if feat.stride(1) != 1 or feat.stride(0) % 4 != 0 or feat.data_ptr() % 16 != 0:
+        feat = feat.contiguous()
+    N, D = feat.shape
+    if D % 4 != 0:
+        raise ValueError("feature dim must be a multiple of 4")
+    NQ = N - E * W * S
+    logits = torch.empty((NQ, W), dtype=torch.float32, device=feat.device)
+    pred = torch.empty((NQ,), dtype=torch.int32, device=feat.device) if want_pred else None
+    h = _lib.lib()
+    ws_bytes = int(h.afs_proto_workspace_bytes(E, W, S, D))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=feat.device) if ws_bytes else None
+    _lib.check(h.afs_proto_fwd(_ptr(feat), feat.stride(0), _ptr(cls_row), N, E, W, S, D, PROTO_MODES[mode],
+                               _ptr(logits), _ptr(pred), _ptr(ws), ws_bytes, _stream()), "afs_proto_fwd")
+    return feat, logits, pred
+
+
+class _ProtoFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, cls_row, E, W, S, mode):
+        feat_c, logits, _ = _proto_call(feat.detach(), cls_row, E, W, S, mode, False)
+        ctx.save_for_backward(feat_c, cls_row)
+        ctx.cfg = (E, W, S, mode)
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        feat, cls_row = ctx.saved_tensors
+        E, W, S, mode = ctx.cfg
+        if mode == "cos_sim":
+            raise NotImplementedError("backward of the cosine prototype head is not built")
+        N, D = feat.shape
+        grad_logits = grad_logits.contiguous().float()
+        grad_feat = torch.empty((N, D), dtype=torch.float32, device=feat.device)
+        _lib.check(_lib.lib().afs_proto_bwd(_ptr(feat), feat.stride(0), _ptr(cls_row), N, E, W, S, D,
+                                            PROTO_MODES[mode], _ptr(grad_logits), _ptr(grad_feat), D, _stream()),
+                   "afs_proto_bwd")
+        return grad_feat, None, None, None, None, None
+
+
+def proto_logits(feat, cls_row, E, W, S, mode="euclidean", want_pred=False):
+    """Prototype head.  Differentiable w.r.t. feat (modes euclidean, dot) when feat requires grad."""
+    if torch.is_grad_enabled() and feat.requires_grad:
+        logits = _ProtoFn.apply(feat, cls_row, E, W, S, mode)
+        return (logits, None) if want_pred else logits
+    _, logits, pred = _proto_call(feat, cls_row, E, W, S, mode, want_pred)
+    return (logits, pred) if want_pred else logits
+
+
+def dn4_scores(feat, cls_row, E, W, S, n_k, want_topk=False, want_pred=False):
+    """DN4 head.  feat [N, C, H, W] (or [N, C, HW]) -> score [NQ, W] (+ topk_idx [NQ, W, HW, n_k], pred)."""
+    _need_cuda(feat, "feat")
+    _need_cuda(cls_row, "cls_row", torch.int32)
+    feat = feat.contiguous()
+    N, Cc = feat.shape[0], feat.shape[1]
+    HW = int(np.prod(feat.shape[2:]))
+    NQ = N - E * W * S
+    score = torch.empty((NQ, W), dtype=torch.float32, device=feat.device)
+    topk = torch.empty((NQ, W, HW, n_k), dtype=torch.int32, device=feat.device) if want_topk else None
+    pred = torch.empty((NQ,), dtype=torch.int32, device=feat.device) if want_pred else None
+    h = _lib.lib()
+    ws_bytes = int(h.afs_dn4_workspace_bytes(N, E, W, S, Cc, HW))
+    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=feat.device)
+    _lib.check(h.afs_dn4_fwd(_ptr(feat), _ptr(cls_row), N, E, W, S, Cc, HW, int(n_k), _ptr(score), _ptr(topk),
+                             _ptr(pred), _ptr(ws), ws_bytes, _stream()), "afs_dn4_fwd")
+    return score, topk, pred
+
+
+def bdc_pool(x, log_temp, triu=True):
+    """BDC matrix of x [B, C, H, W] (or [B, C, M]) with log-temperature tensor (1 element)."""
+    _need_cuda(x, "x")
+    _need_cuda(log_temp, "log_temp")
+    x = x.contiguous()
+    B, Cc = x.shape[0], x.shape[1]
+    M = int(np.prod(x.shape[2:]))
+    out_dim = Cc * (Cc + 1) // 2 if triu else Cc * Cc
+    out = torch.empty((B, out_dim), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().afs_bdc_fwd(_ptr(x), B, Cc, M, _ptr(log_temp.contiguous()), 1 if triu else 0, _ptr(out),
+                                      _stream()), "afs_bdc_fwd")
+    return out
+
+
+def vote_acc(logits, q_start, q_target):
+    """-> (q_pred int32 [nq], acc_pct float32 0-dim tensor, stats int32 [4]) without any host sync."""
+    _need_cuda(logits, "logits")
+    _need_cuda(q_start, "q_start", torch.int32)
+    _need_cuda(q_target, "q_target", torch.int32)
+    logits = logits.contiguous()
+    nq = q_target.numel()
+    W = logits.shape[1]
+    q_pred = torch.empty((nq,), dtype=torch.int32, device=logits.device)
+    stats = torch.empty((4,), dtype=torch.int32, device=logits.device)
+    acc = torch.empty((), dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.lib().afs_vote_acc(_ptr(logits), W, _ptr(q_start), nq, _ptr(q_target), _ptr(q_pred), _ptr(stats),
+                                       _ptr(acc), _stream()), "afs_vote_acc")
+    return q_pred, acc, stats
+
+
+def energy_score(logits, q_start, nq):
+    _need_cuda(logits, "logits")
+    _need_cuda(q_start, "q_start", torch.int32)
+    logits = logits.contiguous()
+    out = torch.empty((nq,), dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.lib().afs_energy_score(_ptr(logits), logits.shape[1], _ptr(q_start), nq, _ptr(out), _stream()),
+               "afs_energy_score")
+    return out

@@ -1,0 +1,143 @@
+"""TEST INFRASTRUCTURE ONLY.  Seeded parity cases shared by oracle/make_golden.py (which runs the
+real reference on them) and tests/ (which run the oracle and the CUDA kernels on them).
+Inputs come from numpy PCG64 streams, so they are identical on every machine."""
+import zlib
+
+import numpy as np
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+# ------------------------------------------------------------------ prototype heads
+PROTO_CASES = {
+    # C1 ProtoNet/Conv64F, C2 ProtoNet/ResNet-12 1-shot, C4 DeepBDC vectors
+    "c1_euclid": dict(seed=11, E=1, W=5, S=5, Q=15, D=1600, head="proto", mode="euclidean"),
+    "c2_euclid_d12800": dict(seed=12, E=2, W=5, S=1, Q=15, D=12800, head="proto", mode="euclidean"),
+    "c4_euclid_d2080": dict(seed=13, E=4, W=5, S=5, Q=10, D=2080, head="proto", mode="euclidean"),
+    "cos_sim": dict(seed=14, E=2, W=5, S=5, Q=15, D=1600, head="proto", mode="cos_sim"),
+    "odd_way7": dict(seed=15, E=3, W=7, S=3, Q=4, D=64, head="proto", mode="euclidean"),
+    "way20": dict(seed=16, E=2, W=20, S=2, Q=3, D=128, head="proto", mode="euclidean"),
+    "bdc_1shot_dot": dict(seed=17, E=2, W=5, S=1, Q=10, D=2080, head="deepbdc", mode="dot"),
+    "bdc_5shot": dict(seed=18, E=2, W=5, S=5, Q=10, D=2080, head="deepbdc", mode="euclidean"),
+}
+
+
+def proto_features(c):
+    n = c["E"] * c["W"] * (c["S"] + c["Q"])
+    return _rng(c["seed"]).standard_normal((n, c["D"])).astype(np.float32)
+
+
+# ------------------------------------------------------------------ DN4
+DN4_CASES = {
+    "c3_5shot": dict(seed=21, E=1, W=5, S=5, Q=15, C=64, H=4, Wd=5, n_k=3),
+    "c3_1shot_q10": dict(seed=22, E=1, W=5, S=1, Q=10, C=64, H=4, Wd=5, n_k=3),
+    "nk1_two_episodes": dict(seed=23, E=2, W=5, S=5, Q=10, C=64, H=4, Wd=5, n_k=1),
+    "nk5_odd": dict(seed=24, E=2, W=3, S=2, Q=3, C=40, H=3, Wd=7, n_k=5),
+    "resnet12_map": dict(seed=25, E=1, W=5, S=5, Q=2, C=640, H=8, Wd=9, n_k=3),
+}
+
+
+def dn4_features(c):
+    n = c["E"] * c["W"] * (c["S"] + c["Q"])
+    # non-negative like post-ReLU maps, with a few exact zeros
+    x = _rng(c["seed"]).standard_normal((n, c["C"], c["H"], c["Wd"])).astype(np.float32)
+    return np.maximum(x, 0.0) + 0.01 * np.abs(x)
+
+
+# ------------------------------------------------------------------ BDC
+BDC_CASES = {
+    "c4_map": dict(seed=31, B=4, C=64, H=16, Wd=19, log_temp=float(np.log(1.0 / 200.0))),
+    "small_map": dict(seed=32, B=3, C=64, H=5, Wd=5, log_temp=-3.0),
+    "dim48": dict(seed=33, B=2, C=48, H=7, Wd=9, log_temp=-4.0),
+}
+
+
+def bdc_features(c):
+    x = _rng(c["seed"]).standard_normal((c["B"], c["C"], c["H"], c["Wd"])).astype(np.float32)
+    return np.maximum(x, 0.0)
+
+
+# ------------------------------------------------------------------ ragged split / vote
+SPLIT_CASES = {
+    "ragged_small": dict(seed=41, E=1, W=2, S=1, Q=2, W_logits=2, fixed=[2, 1, 1, 3]),
+    "ragged_e3": dict(seed=42, E=3, W=5, S=5, Q=4, W_logits=5, fixed=None),
+    "ones": dict(seed=43, E=2, W=5, S=1, Q=15, W_logits=5, fixed="ones"),
+}
+
+
+def split_repeats(c):
+    n = c["E"] * c["W"] * c["Q"]
+    if c["fixed"] == "ones":
+        return np.ones(n, dtype=np.int64)
+    if c["fixed"] is not None:
+        return np.asarray(c["fixed"], dtype=np.int64)
+    return _rng(c["seed"]).integers(1, 4, size=n).astype(np.int64)
+
+
+def split_logits(c, n_rows):
+    # coarse values so that window argmaxes tie often enough to exercise torch.mode's tie rule
+    r = _rng(c["seed"] + 1000)
+    return np.round(r.standard_normal((n_rows, c["W_logits"])) * 2.0).astype(np.float32) / 2.0
+
+
+CI_DATA = tuple(float(v) for v in _rng(51).uniform(40.0, 90.0, size=37))
+
+
+# ------------------------------------------------------------------ backbones
+BACKBONE_CASES = {
+    "conv64f_flat": ("Conv64F", dict(is_flatten=True, is_feature=False, leaky_relu=False, negative_slope=0.2,
+                                     last_pool=True, maxpool_last2=True, num_channels=1)),
+    "conv64f_dn4": ("Conv64F", dict(is_flatten=False, is_feature=False, leaky_relu=False, negative_slope=0.2,
+                                    last_pool=False, maxpool_last2=True, num_channels=1)),
+    "resnet12": ("resnet12", dict(keep_prob=0.0, avg_pool=True, is_flatten=True, maxpool_last2=True,
+                                  num_channels=1)),
+    "resnet12bdc": ("resnet12Bdc", dict(reduce_dim=64, num_channels=1)),
+}
+
+
+def backbone_input():
+    return (_rng(61).standard_normal((2, 1, 128, 157)) * 0.5).astype(np.float32)
+
+
+def perturb_bn_(net):
+    """Overwrite EVERY parameter and buffer with values derived from its name and shape, so that a
+    reference module and a product module with the same state_dict layout get identical weights
+    (and non-trivial BatchNorm statistics) without shipping a checkpoint."""
+    import torch
+
+    sd = net.state_dict()
+    for key in sorted(sd.keys()):
+        t = sd[key]
+        if key.endswith("num_batches_tracked"):
+            continue
+        r = _rng(zlib.crc32(key.encode()))
+        shape = tuple(t.shape)
+        if key.endswith("running_var") or (key.endswith("weight") and t.dim() == 1):
+            v = r.uniform(0.5, 1.5, size=shape)
+        elif key.endswith("running_mean") or key.endswith("bias"):
+            v = r.standard_normal(shape) * 0.1
+        elif key.endswith("temperature"):
+            v = np.full(shape, np.log(1.0 / 200.0))
+        else:
+            fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+            v = r.standard_normal(shape) * np.sqrt(2.0 / max(fan_in, 1))
+        with torch.no_grad():
+            t.copy_(torch.from_numpy(np.asarray(v, dtype=np.float32)))
+    return net
+
+
+# ------------------------------------------------------------------ synthetic waveforms
+def synthetic_clip_batch(seed, first_episode, n_episodes, W, S, Q, L, sample_rate=16000):
+    """[E*W*(S+Q), L] fp32, class-major rows: N(0,1)*0.1 noise + a class-dependent tone
+    0.05*sin(2 pi f_c t), f_c = 200*(c+1) Hz.  Content depends only on the global episode index."""
+    t = np.arange(L, dtype=np.float64) / sample_rate
+    out = np.empty((n_episodes, W, S + Q, L), dtype=np.float32)
+    for e in range(n_episodes):
+        r = _rng((seed, first_episode + e))
+        noise = r.standard_normal((W, S + Q, L)).astype(np.float32) * np.float32(0.1)
+        for c in range(W):
+            tone = (0.05 * np.sin(2.0 * np.pi * 200.0 * (c + 1) * t)).astype(np.float32)
+            out[e, c] = noise[c] + tone[None, :]
+    return out.reshape(n_episodes * W * (S + Q), L)

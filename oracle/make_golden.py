@@ -1,0 +1,113 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz from the REAL reference classes.
+
+Run in the authoring container (needs /root/reference):
+
+    python -m oracle.make_golden
+
+Inputs are NOT stored: every case regenerates them with
+numpy.random.default_rng(seed) (PCG64, stable across numpy versions) through
+`oracle.cases`, so the fixtures stay small (outputs only).  The GPU box has no
+/root/reference; tests there compare the CUDA kernels with these files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import cases
+from .ref_import import import_reference
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def main():
+    arch, utils, _ = import_reference()
+    from libfewshot_core.model.metric.proto_net import ProtoLayer
+    from libfewshot_core.model.metric.dn4 import DN4Layer
+    from libfewshot_core.model.metric import deepbdc as ref_deepbdc
+    from libfewshot_core.model.backbone.utils.bdc_pool import BDCovpool, Triuvec
+
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+
+    # ---- ProtoLayer (proto_net.py:34-64), fixed layout
+    out = {}
+    for name, c in cases.PROTO_CASES.items():
+        feat = torch.from_numpy(cases.proto_features(c))
+        E, W, S, Q, D = c["E"], c["W"], c["S"], c["Q"], c["D"]
+        f = feat.view(E, W, S + Q, D)
+        sup = f[:, :, :S].contiguous().view(E, W * S, D)
+        qry = f[:, :, S:].contiguous().view(E, W * Q, D)
+        if c["head"] == "proto":
+            logits = ProtoLayer()(qry, sup, W, S, Q, mode=c["mode"])
+        else:
+            logits = ref_deepbdc.ProtoLayer()(qry, sup, W, S, Q)
+        out[name] = logits.reshape(-1, W).numpy()
+    np.savez_compressed(os.path.join(OUT, "proto_layer.npz"), **out)
+
+    # ---- DN4Layer (dn4.py:39-75)
+    out = {}
+    for name, c in cases.DN4_CASES.items():
+        feat = torch.from_numpy(cases.dn4_features(c))
+        E, W, S, Q, C, H, Wd = c["E"], c["W"], c["S"], c["Q"], c["C"], c["H"], c["Wd"]
+        f = feat.view(E, W, S + Q, C, H, Wd)
+        sup = f[:, :, :S].contiguous().view(E, W * S, C, H, Wd)
+        qry = f[:, :, S:].contiguous().view(E, W * Q, C, H, Wd)
+        score = DN4Layer(c["n_k"])(qry, sup, W, S, Q)
+        out[name] = score.reshape(-1, W).numpy()
+    np.savez_compressed(os.path.join(OUT, "dn4_layer.npz"), **out)
+
+    # ---- BDCovpool + Triuvec (bdc_pool.py:69-93)
+    out = {}
+    for name, c in cases.BDC_CASES.items():
+        x = torch.from_numpy(cases.bdc_features(c))
+        t = torch.full((1, 1), float(c["log_temp"]))
+        full = BDCovpool(x, t)
+        out[name + "/full"] = full.numpy()
+        out[name + "/triu"] = Triuvec(full).reshape(x.shape[0], -1).numpy()
+    np.savez_compressed(os.path.join(OUT, "bdc_pool.npz"), **out)
+
+    # ---- split_by_episode (abstract_model.py:176-332), majority_vote, vote acc (utils.py:432-446)
+    out = {}
+    for name, c in cases.SPLIT_CASES.items():
+        E, W, S, Q = c["E"], c["W"], c["S"], c["Q"]
+        model = arch.ProtoNet(way_num=W, shot_num=S, query_num=Q, test_way=W, test_shot=S, test_query=Q,
+                              emb_func=None, device="cpu")
+        repeats = torch.from_numpy(cases.split_repeats(c))
+        n_rows = E * W * S + int(repeats.sum())
+        feats = torch.arange(n_rows, dtype=torch.float32).view(-1, 1).repeat(1, 2)  # row id as the feature
+        sup, qry, st, qt, mask = model.split_by_episode(feats, mode=1, repeats=repeats, support_size=E * W * S)
+        out[name + "/support_rows"] = sup[..., 0].numpy().astype(np.int32)
+        out[name + "/query_rows"] = np.concatenate([q[:, 0].numpy() for q in qry]).astype(np.int32)
+        out[name + "/query_len"] = np.asarray([q.shape[0] for q in qry], dtype=np.int32)
+        out[name + "/query_target"] = qt.numpy().astype(np.int32)
+        out[name + "/query_mask"] = mask
+        logits = torch.from_numpy(cases.split_logits(c, int(repeats.sum())))
+        pred = utils.majority_vote(logits.softmax(dim=1), repeats)
+        out[name + "/vote_pred"] = pred.numpy().astype(np.int32)
+        out[name + "/vote_acc"] = np.asarray(utils.vote_catagorical_acc(qt.reshape(-1), pred.to(torch.long)).item())
+        avg = utils.average_logits(logits, repeats)
+        out[name + "/energy"] = (-torch.logsumexp(avg, dim=1)).numpy()
+    m, h = utils.mean_confidence_interval(list(cases.CI_DATA))
+    out["ci/mean_h"] = np.asarray([m, h])
+    np.savez_compressed(os.path.join(OUT, "episode_vote.npz"), **out)
+
+    # ---- backbones (conv_four.py, resnet_12.py, resnet_bdc.py): eval features of seeded weights
+    out = {}
+    x = torch.from_numpy(cases.backbone_input())
+    for name, (ctor, kwargs) in cases.BACKBONE_CASES.items():
+        torch.manual_seed(0)
+        net = getattr(arch, ctor)(**kwargs).eval()
+        cases.perturb_bn_(net)
+        with torch.no_grad():
+            y = net(x)
+        out[name + "/out"] = y.numpy()
+        out[name + "/keys"] = np.asarray(sorted(net.state_dict().keys()))
+    np.savez_compressed(os.path.join(OUT, "backbones.npz"), **out)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,68 @@
+// CPU emulation of the fused log-mel kernel's per-thread phases (host logic test).
+//
+// Runs the SAME __host__ __device__ phase functions the kernel runs
+// (audio_fewshot_b200/csrc/logmel_core.cuh) with the 64 threads of a frame group
+// looped sequentially per phase (the loop boundary plays the role of bar.sync).
+// Built by tests/test_logmel_emul.py with `nvcc -x cu` (host code only is used).
+#include <math.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "logmel_core.cuh"
+
+using namespace afs::logmel;
+
+extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, const float* fb,
+                           const float* window, int n_mels, const float* mean, const float* stdv,
+                           float log_mult, float log_eps, float* out /*[n_mels, T]*/,
+                           float* power_out /*[T, 513] nullable*/) {
+  std::vector<int> band;
+  std::vector<float> weights;
+  pack_mel_bands(fb, n_mels, band, weights);
+  std::vector<float2> tw(kNfft);
+  for (int k = 0; k < kNfft; ++k) {
+    const double a = 6.283185307179586476925286766559 * k / kNfft;
+    tw[k] = make_float2(static_cast<float>(cos(a)), static_cast<float>(-sin(a)));
+  }
+  const int pad = center ? kNfft / 2 : 0;
+  const int T = center ? static_cast<int>(1 + L / hop) : static_cast<int>(1 + (L - kNfft) / hop);
+  std::vector<float> bufA(kBufA), bufB(kBufB);
+  std::vector<ThreadTw> tws(kGroup);
+  for (int t = 0; t < kGroup; ++t) load_thread_tw(tws[t], t, tw.data());
+  for (int f = 0; f < T; ++f) {
+    const int64_t s0 = static_cast<int64_t>(f) * hop - pad;
+    const bool interior = s0 >= 0 && s0 + kNfft <= L;
+    for (int t = 0; t < kGroup; ++t) {
+      cpx z[8];
+      for (int r = 0; r < 8; ++r) {
+        const int n = t + 64 * r;
+        int64_t i0 = s0 + 2 * n, i1 = i0 + 1;
+        if (!interior) { i0 = reflect_index(i0, L); i1 = reflect_index(i1, L); }
+        z[r].re = wav[i0] * window[2 * n];
+        z[r].im = wav[i1] * window[2 * n + 1];
+      }
+      phase_a(t, z, tws[t], bufA.data());
+    }
+    for (int t = 0; t < kGroup; ++t) phase_b(t, tws[t], bufA.data(), bufB.data());
+    for (int t = 0; t < kGroup; ++t) phase_c(t, bufB.data(), bufA.data());
+    for (int t = 0; t < kGroup; ++t) phase_d(t, tws[t], bufA.data(), bufB.data());
+    if (power_out) for (int k = 0; k < kBins; ++k) power_out[static_cast<size_t>(f) * kBins + k] = bufB[k];
+    for (int t = 0; t < kGroup; ++t) {
+      int mel_id[2];
+      mel_id[0] = (t < n_mels) ? t : -1;
+      mel_id[1] = (n_mels - 1 - t >= kGroup) ? n_mels - 1 - t : -1;
+      for (int i = 0; i < 2; ++i) {
+        const int m = mel_id[i];
+        if (m < 0) continue;
+        const float e = mel_dot(bufB.data(), weights.data() + band[2 * kMaxMels + m], band[m], band[kMaxMels + m]);
+        const float v = log_mult * log10f(e + log_eps);
+        out[static_cast<size_t>(m) * T + f] = (v - mean[m]) / stdv[m];
+      }
+    }
+  }
+  return T;
+}
+
+// slot bijection check for the exchange-2 swizzle
+extern "C" int emul_e2_slot(int q, int j0, int p0) { return e2_slot(q, j0, p0); }

@@ -1,0 +1,234 @@
+"""Parity of the CUDA heads (through the C ABI) with the reference goldens and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, heads
+
+pytestmark = pytest.mark.gpu
+
+
+def fixed_table(c, device):
+    from audio_fewshot_b200.episode import EpisodeTable
+    return EpisodeTable(c["E"], c["W"], c["S"], c["Q"], np.ones(c["E"] * c["W"] * c["Q"], np.int64), device)
+
+
+def ragged_table(E, W, S, Q, rep, device):
+    from audio_fewshot_b200.episode import EpisodeTable
+    return EpisodeTable(E, W, S, Q, rep, device)
+
+
+# ------------------------------------------------------------------ prototype head
+@pytest.mark.parametrize("name", sorted(cases.PROTO_CASES))
+def test_proto_matches_reference_golden(cuda, golden, name):
+    from audio_fewshot_b200 import ops
+    c = cases.PROTO_CASES[name]
+    feat = torch.from_numpy(cases.proto_features(c)).to(cuda)
+    tab = fixed_table(c, cuda)
+    logits, pred = ops.proto_logits(feat, tab.cls_row, tab.E, tab.W, tab.S, c["mode"], want_pred=True)
+    want = golden("proto_layer.npz")[name]
+    got = logits.cpu().numpy()
+    # north star: distances/logits within 1e-3 relative; predictions identical
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-3 * np.abs(want).max() * 1e-2)
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()  # what the fp32 path actually achieves
+    assert np.array_equal(got.argmax(1), want.argmax(1))
+    assert np.array_equal(pred.cpu().numpy(), want.argmax(1))
+
+
+@pytest.mark.parametrize("mode", ["euclidean", "cos_sim", "dot"])
+def test_proto_ragged_layout_matches_oracle(cuda, mode):
+    from audio_fewshot_b200 import ops
+    rng = np.random.default_rng(77)
+    E, W, S, Q, D = 3, 5, 2, 4, 320
+    rep = rng.integers(0, 4, size=E * W * Q)  # includes zero-window queries
+    rep[:Q] = 0  # a class with no query rows at all
+    n = E * W * S + int(rep.sum())
+    feat = torch.from_numpy(rng.standard_normal((n, D)).astype(np.float32))
+    tab = ragged_table(E, W, S, Q, rep, cuda)
+    got = ops.proto_logits(feat.to(cuda), tab.cls_row, E, W, S, mode).cpu()
+    sup, qry, _, _, _ = heads.split_by_episode(feat, W, S, Q, torch.from_numpy(rep), E * W * S)
+    outs = []
+    for i in range(E):
+        if mode == "dot":
+            o = heads.deepbdc_proto_layer(qry[i].unsqueeze(0), sup[i].unsqueeze(0), W, 1) if S == 1 else \
+                torch.matmul(qry[i].unsqueeze(0), sup[i].view(1, W, S, D).mean(2).transpose(-1, -2))
+        else:
+            o = heads.proto_layer(qry[i].unsqueeze(0), sup[i].unsqueeze(0), W, S, mode)
+        outs.append(o.reshape(-1, W))
+    want = torch.cat(outs)
+    assert got.shape == want.shape
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-3)
+    assert torch.equal(got.argmax(1), want.argmax(1))
+
+
+def test_proto_strided_rows_and_empty_batch(cuda):
+    from audio_fewshot_b200 import ops
+    c = dict(E=2, W=5, S=5, Q=3)
+    wide = torch.randn(80, 96, device=cuda)
+    feat = wide[:, :64]  # row stride 96, not contiguous
+    tab = fixed_table(c, cuda)
+    a = ops.proto_logits(feat, tab.cls_row, 2, 5, 5)
+    b = ops.proto_logits(feat.contiguous(), tab.cls_row, 2, 5, 5)
+    assert torch.equal(a, b)
+    with pytest.raises(Exception):
+        ops.proto_logits(feat.cpu(), tab.cls_row, 2, 5, 5)  # no CPU fallback
+
+
+def test_proto_many_episodes_is_per_episode_independent(cuda):
+    """Full bench size (BASELINE C1, 512 episodes): every episode's logits equal the ones
+    computed when that episode is launched alone (a size-independent property)."""
+    from audio_fewshot_b200 import ops
+    c = dict(E=512, W=5, S=5, Q=15)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    feat = torch.randn(512 * 100, 1600, generator=g).to(cuda)
+    tab = fixed_table(c, cuda)
+    full = ops.proto_logits(feat, tab.cls_row, 512, 5, 5)
+    one = fixed_table(dict(E=1, W=5, S=5, Q=15), cuda)
+    for e in (0, 17, 511):
+        part = ops.proto_logits(feat[e * 100:(e + 1) * 100], one.cls_row, 1, 5, 5)
+        assert torch.equal(full[e * 75:(e + 1) * 75], part)
+
+
+@pytest.mark.parametrize("mode,S", [("euclidean", 5), ("euclidean", 1), ("dot", 1), ("dot", 3)])
+def test_proto_backward_matches_autograd(cuda, mode, S):
+    from audio_fewshot_b200 import ops
+    E, W, Q, D = 3, 5, 4, 200
+    tab = fixed_table(dict(E=E, W=W, S=S, Q=Q), cuda)
+    feat = torch.randn(E * W * (S + Q), D, device=cuda, requires_grad=True)
+    gout = torch.randn(E * W * Q, W, device=cuda)
+    logits = ops.proto_logits(feat, tab.cls_row, E, W, S, mode)
+    logits.backward(gout)
+    got = feat.grad.clone()
+    ref = feat.detach().clone().requires_grad_(True)
+    f = ref.view(E, W, S + Q, D)
+    proto = f[:, :, :S].mean(2)
+    qry = f[:, :, S:].reshape(E, W * Q, D)
+    if mode == "euclidean":
+        want_logits = -((qry.unsqueeze(2) - proto.unsqueeze(1)) ** 2).sum(3)
+    else:
+        want_logits = qry @ proto.transpose(1, 2)
+    want_logits.reshape(-1, W).backward(gout)
+    torch.testing.assert_close(logits, want_logits.reshape(-1, W), rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(got, ref.grad, rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------ DN4
+def dn4_oracle(c):
+    feat = torch.from_numpy(cases.dn4_features(c))
+    E, W, S, Q = c["E"], c["W"], c["S"], c["Q"]
+    f = feat.view(E, W, S + Q, *feat.shape[1:])
+    sup = f[:, :, :S].contiguous().view(E, W * S, *feat.shape[1:])
+    qry = f[:, :, S:].contiguous().view(E, W * Q, *feat.shape[1:])
+    return heads.dn4_layer(qry, sup, W, S, c["n_k"], return_topk=True)
+
+
+@pytest.mark.parametrize("name", sorted(cases.DN4_CASES))
+def test_dn4_matches_reference_golden_and_topk(cuda, golden, name):
+    from audio_fewshot_b200 import ops
+    c = cases.DN4_CASES[name]
+    feat = torch.from_numpy(cases.dn4_features(c)).to(cuda)
+    tab = fixed_table(c, cuda)
+    score, topk, pred = ops.dn4_scores(feat, tab.cls_row, tab.E, tab.W, tab.S, c["n_k"], want_topk=True,
+                                       want_pred=True)
+    want = golden("dn4_layer.npz")[name]
+    got = score.cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-3)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    assert np.array_equal(got.argmax(1), want.argmax(1))
+    assert np.array_equal(pred.cpu().numpy(), want.argmax(1))
+    # top-k indices against torch.topk on the oracle's relation tensor (the reference discards
+    # them, dn4.py:72).  Identical except where the oracle's own values are within float noise.
+    _, topv, topi, relation = dn4_oracle(c)
+    E, W, Q = c["E"], c["W"], c["Q"]
+    HW = c["H"] * c["Wd"]
+    topi = topi.reshape(E * W * Q, W, HW, c["n_k"]).numpy()
+    relation = relation.reshape(E * W * Q, W, HW, -1).numpy()
+    mine = topk.cpu().numpy()
+    diff = np.argwhere(mine != topi)
+    for o, w, m, k in diff:
+        a, b = relation[o, w, m, mine[o, w, m, k]], relation[o, w, m, topi[o, w, m, k]]
+        assert abs(a - b) <= 4e-7, (o, w, m, k, a, b)
+    assert len(diff) <= 1e-4 * mine.size
+
+
+def test_dn4_ragged_matches_oracle(cuda):
+    from audio_fewshot_b200 import ops
+    rng = np.random.default_rng(5)
+    E, W, S, Q, C, H, Wd, n_k = 2, 3, 2, 3, 32, 3, 4, 2
+    rep = rng.integers(1, 4, size=E * W * Q)
+    n = E * W * S + int(rep.sum())
+    feat = torch.from_numpy(np.abs(rng.standard_normal((n, C, H, Wd))).astype(np.float32))
+    tab = ragged_table(E, W, S, Q, rep, cuda)
+    score, _, _ = ops.dn4_scores(feat.to(cuda), tab.cls_row, E, W, S, n_k)
+    want, _, _ = heads.dn4_forward(feat, W, S, Q, torch.from_numpy(rep), E * W * S, n_k)
+    torch.testing.assert_close(score.cpu(), want, rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------ BDC
+@pytest.mark.parametrize("name", sorted(cases.BDC_CASES))
+def test_bdc_matches_reference_golden(cuda, golden, name):
+    from audio_fewshot_b200 import ops
+    c = cases.BDC_CASES[name]
+    x = torch.from_numpy(cases.bdc_features(c)).to(cuda)
+    t = torch.full((1, 1), c["log_temp"], device=cuda)
+    g = golden("bdc_pool.npz")
+    triu = ops.bdc_pool(x, t, triu=True).cpu().numpy()
+    full = ops.bdc_pool(x, t, triu=False).cpu().numpy().reshape(c["B"], c["C"], c["C"])
+    scale = np.abs(g[name + "/full"]).max()
+    assert np.abs(full - g[name + "/full"]).max() <= 1e-3 * scale
+    assert np.abs(full - g[name + "/full"]).max() <= 2e-5 * scale
+    assert np.abs(triu - g[name + "/triu"]).max() <= 2e-5 * scale
+    assert np.abs(full - full.transpose(0, 2, 1)).max() <= 1e-5 * scale  # symmetric
+    assert np.abs(full.mean(axis=2)).max() <= 1e-4 * scale               # double-centred
+
+
+# ------------------------------------------------------------------ vote / accuracy / energy
+@pytest.mark.parametrize("name", sorted(cases.SPLIT_CASES))
+def test_vote_acc_energy_match_reference_golden(cuda, golden, name):
+    from audio_fewshot_b200 import ops
+    c = cases.SPLIT_CASES[name]
+    g = golden("episode_vote.npz")
+    rep = cases.split_repeats(c)
+    tab = ragged_table(c["E"], c["W"], c["S"], c["Q"], rep, cuda)
+    logits = torch.from_numpy(cases.split_logits(c, int(rep.sum()))).to(cuda)
+    assert np.array_equal(tab.q_target.cpu().numpy(), g[name + "/query_target"].reshape(-1))
+    q_pred, acc, stats = ops.vote_acc(logits, tab.q_start, tab.q_target)
+    assert np.array_equal(q_pred.cpu().numpy(), g[name + "/vote_pred"])  # bit-exact predictions
+    assert acc.item() == pytest.approx(float(g[name + "/vote_acc"]), rel=1e-6)
+    assert stats[1].item() == tab.nq
+    en = ops.energy_score(logits, tab.q_start, tab.nq).cpu().numpy()
+    np.testing.assert_allclose(en, g[name + "/energy"], rtol=1e-5, atol=1e-5)
+
+
+def test_vote_tie_rule_equals_torch_mode_on_cuda(cuda):
+    """The reference calls torch.mode on a CUDA slice (utils.py:443): same tie rule as ours."""
+    from audio_fewshot_b200 import ops
+    rng = np.random.default_rng(3)
+    W, nq = 4, 300
+    rep = rng.integers(1, 7, size=nq)
+    n = int(rep.sum())
+    labels = rng.integers(0, W, size=n)
+    logits = torch.zeros(n, W)
+    logits[torch.arange(n), torch.from_numpy(labels)] = 1.0
+    q_start = torch.from_numpy(np.concatenate([[0], np.cumsum(rep)]).astype(np.int32)).to(cuda)
+    q_target = torch.zeros(nq, dtype=torch.int32, device=cuda)
+    q_pred, acc, _ = ops.vote_acc(logits.to(cuda), q_start, q_target)
+    y = logits.to(cuda).argmax(1)
+    want, end = [], 0
+    for num in rep:
+        want.append(torch.mode(y[end:end + int(num)])[0].item())
+        end += int(num)
+    assert q_pred.cpu().tolist() == want
+    assert acc.item() == pytest.approx(100.0 * np.mean(np.asarray(want) == 0), rel=1e-6)
+
+
+def test_vote_large_batch_counts(cuda):
+    from audio_fewshot_b200 import ops
+    nq, W = 200_000, 5
+    logits = torch.randn(nq, W, device=cuda)
+    q_start = torch.arange(nq + 1, dtype=torch.int32, device=cuda)
+    target = torch.randint(0, W, (nq,), device=cuda, dtype=torch.int32)
+    q_pred, acc, stats = ops.vote_acc(logits, q_start, target)
+    want = (logits.argmax(1).int() == target).sum().item()
+    assert stats[0].item() == want
+    assert torch.equal(q_pred, logits.argmax(1).int())

@@ -1,0 +1,111 @@
+"""CPU tests of the host side: episode tables, config-free model plumbing, sharding."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import cases, heads
+
+
+@pytest.mark.parametrize("name", sorted(cases.SPLIT_CASES))
+def test_episode_table_equals_reference_split(golden, name):
+    from audio_fewshot_b200.episode import EpisodeTable
+    c = cases.SPLIT_CASES[name]
+    g = golden("episode_vote.npz")
+    rep = cases.split_repeats(c)
+    tab = EpisodeTable(c["E"], c["W"], c["S"], c["Q"], rep, "cpu")
+    S = c["S"]
+    cls_row = tab.cls_row.numpy()
+    sup = np.concatenate([np.arange(cls_row[k], cls_row[k] + S) for k in range(c["E"] * c["W"])])
+    qry = np.concatenate([np.arange(cls_row[k] + S, cls_row[k + 1]) for k in range(c["E"] * c["W"])])
+    assert np.array_equal(sup, g[name + "/support_rows"].reshape(-1))
+    assert np.array_equal(qry, g[name + "/query_rows"])
+    assert np.array_equal(tab.q_target.numpy(), g[name + "/query_target"].reshape(-1))
+    assert tab.NQ == int(rep.sum()) and tab.N == len(sup) + len(qry)
+    assert np.array_equal(np.diff(tab.q_start.numpy()), rep)
+    assert np.array_equal(cls_row, heads.cls_row_table(rep, c["E"], c["W"], S))
+
+
+def test_table_cache_and_errors():
+    from audio_fewshot_b200.episode import EpisodeTableCache, EpisodeTable
+    cache = EpisodeTableCache(max_entries=2)
+    a = cache.get(2, 5, 5, 15, None, "cpu")
+    assert cache.get(2, 5, 5, 15, torch.ones(150, dtype=torch.long), "cpu") is not a  # keyed separately
+    assert cache.get(2, 5, 5, 15, None, "cpu") is a
+    assert a.N == 200 and a.NQ == 150
+    with pytest.raises(ValueError):
+        EpisodeTable(2, 5, 5, 15, np.ones(10), "cpu")
+
+
+def test_model_contract_on_cpu():
+    """Constructor kwargs, reverse_setting_info, model_type, forward dispatch (no kernels launched)."""
+    from audio_fewshot_b200 import model as arch
+    cfg = {"backbone": {"name": "Conv64F", "kwargs": {"is_flatten": True, "num_channels": 1}},
+           "classifier": {"name": "ProtoNet", "kwargs": None}}
+    emb = arch.get_instance(arch, "backbone", cfg)
+    m = arch.get_instance(arch, "classifier", cfg, way_num=5, shot_num=5, query_num=15, test_way=5, test_shot=1,
+                          test_query=10, emb_func=emb, device="cpu", num_channels=1, is_clap=False)
+    assert m.model_type == arch.ModelType.METRIC
+    assert any(k.startswith("emb_func.layer1.0.weight") for k in m.state_dict())
+    m.reverse_setting_info()
+    assert (m.way_num, m.shot_num, m.query_num, m.test_shot) == (5, 1, 10, 5)
+    assert m.get_uncertainty_threshold() is None
+    assert m.eval() is m
+    from audio_fewshot_b200._lib import AfsError
+    with pytest.raises(AfsError):  # CPU tensors never silently fall back
+        m([torch.zeros(55, 1, 128, 157), torch.zeros(55), torch.ones(50, dtype=torch.long), 5])
+
+
+def test_sharding_is_a_partition():
+    from audio_fewshot_b200.dist import shard_episodes
+    for n, ws in [(10, 1), (10, 4), (1250, 8), (3, 8)]:
+        parts = [shard_episodes(n, r, ws) for r in range(ws)]
+        assert sorted(sum(parts, [])) == list(range(n))
+
+
+def test_ci_matches_reference_golden(golden):
+    from audio_fewshot_b200.dist import mean_confidence_interval
+    m, h = mean_confidence_interval(list(cases.CI_DATA))
+    np.testing.assert_allclose([m, h], golden("episode_vote.npz")["ci/mean_h"], rtol=1e-12)
+
+
+WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from audio_fewshot_b200.dist import shard_episodes, gather_episode_accuracies, mean_confidence_interval
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"], rank=int(os.environ["RANK"]),
+                        world_size=int(os.environ["WORLD_SIZE"]))
+rank, ws = dist.get_rank(), dist.get_world_size()
+n = 11
+mine = shard_episodes(n, rank, ws)
+local = torch.tensor([50.0 + g for g in mine])          # accuracy is a function of the GLOBAL index
+full = gather_episode_accuracies(local, n)
+assert full.tolist() == [50.0 + g for g in range(n)], full
+m, h = mean_confidence_interval(full.tolist())
+from audio_fewshot_b200.model.proto_net import accuracy_percent
+out = torch.eye(4)[torch.tensor([0, 1, 2, 3])]
+acc = accuracy_percent(out, torch.tensor([0, 1, 2, 0]) if rank == 0 else torch.tensor([0, 1, 2, 3]))
+assert abs(acc - 100.0 * 7 / 8) < 1e-4, acc             # summed over both ranks (utils.py:116-118)
+if rank == 0:
+    print("OK %%.6f %%.6f" %% (m, h))
+dist.barrier(); dist.destroy_process_group()
+""" % ROOT
+
+
+def test_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=120) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    m, h = [float(v) for v in outs[0][0].split()[1:3]]
+    assert m == pytest.approx(55.0) and h > 0

@@ -1,0 +1,83 @@
+"""Host logic of the fused log-mel kernel: the kernel's __host__ __device__ phase functions
+(csrc/logmel_core.cuh) run on the CPU, 64 'threads' per phase, against the float64 spec."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import frontend as fe
+
+SRC = os.path.join(ROOT, "tests", "emul", "logmel_emul.cu")
+OUT_DIR = os.path.join(ROOT, "tests", "emul", "_build")
+LIB = os.path.join(OUT_DIR, "liblogmel_emul.so")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    os.makedirs(OUT_DIR, exist_ok=True)
+    deps = [SRC, os.path.join(ROOT, "audio_fewshot_b200", "csrc", "logmel_core.cuh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-x", "cu",
+                               "-Wno-deprecated-gpu-targets",
+                               "-I", os.path.join(ROOT, "audio_fewshot_b200", "csrc"),
+                               "-I", os.path.join(ROOT, "include"), SRC, "-o", LIB])
+    lib = C.CDLL(LIB)
+    lib.emul_logmel.restype = C.c_int
+    return lib
+
+
+def run(lib, x, hop, n_mels=128, mean=-15.1, std=26.2):
+    L = x.shape[0]
+    fb = fe.mel_filterbank(n_mels=n_mels)
+    win = fe.hann_periodic()
+    T = 1 + L // hop
+    out = np.zeros((n_mels, T), np.float32)
+    power = np.zeros((T, 513), np.float32)
+    m = np.full(n_mels, mean, np.float32)
+    s = np.full(n_mels, std, np.float32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    got_T = lib.emul_logmel(vp(x), C.c_int64(L), hop, 1, vp(fb), vp(win), n_mels, vp(m), vp(s), C.c_float(10.0),
+                            C.c_float(fe.LOG_EPS), vp(out), vp(power))
+    assert got_T == T
+    return out, power, m, s
+
+
+@pytest.mark.parametrize("L,hop,n_mels", [(8000, 512, 128), (3000, 102, 128), (2049, 511, 128), (4096, 256, 80),
+                                          (1500, 512, 64)])
+def test_phases_match_float64_spec(emul, L, hop, n_mels):
+    rng = np.random.default_rng(L + hop)
+    x = (rng.standard_normal(L) * 0.1).astype(np.float32)
+    out, power, m, s = run(emul, x, hop, n_mels)
+    fr = fe.frames(x[None].astype(np.float64), hop)[0] * fe.hann_periodic().astype(np.float64)
+    pref = np.abs(np.fft.rfft(fr, axis=-1)) ** 2
+    assert np.abs(power - pref).max() / pref.max() < 2e-6
+    ref = fe.logmel_f64(x[None], hop=hop, n_mels=n_mels, mean=m, std=s)[0, 0]
+    db_err = np.abs(out - ref).max() * 26.2
+    assert db_err < 1e-4, db_err  # north-star tolerance 1e-4 (de-normalised dB)
+
+
+def test_exchange2_swizzle_is_a_bijection(emul):
+    slots = sorted(emul.emul_e2_slot(q, j, p) for q in range(8) for j in range(8) for p in range(8))
+    assert slots == list(range(512))
+    # a warp (32 consecutive threads) touches 32 distinct banks on both sides of the exchange
+    for p0 in range(8):  # write side: thread t = q + 8*j0
+        for half in range(2):
+            banks = {emul.emul_e2_slot(t & 7, t >> 3, p0) % 32 for t in range(32 * half, 32 * half + 32)}
+            assert len(banks) == 32
+    for j0 in range(8):  # read side: thread t = q + 8*p0
+        for half in range(2):
+            banks = {emul.emul_e2_slot(t & 7, j0, t >> 3) % 32 for t in range(32 * half, 32 * half + 32)}
+            assert len(banks) == 32
+
+
+def test_pure_tone_lands_in_the_right_mel_bin(emul):
+    sr, f0 = 16000, 1000.0
+    t = np.arange(16000) / sr
+    x = np.sin(2 * np.pi * f0 * t).astype(np.float32)
+    out, _, _, _ = run(emul, x, 512, mean=0.0, std=1.0)
+    fb = fe.mel_filterbank()
+    k = int(round(f0 / (sr / 1024)))
+    assert int(out[:, 5].argmax()) == int(fb[k].argmax())
