@@ -40,6 +40,7 @@ SIGNATURES = {
     "afs_abi_version": (C.c_int, []),
     "afs_status_string": (C.c_char_p, [C.c_int]),
     "afs_last_cuda_error": (C.c_int, []),
+    "afs_launch_count": (C.c_uint64, []),
     "afs_logmel_plan_create": (C.c_int, [C.POINTER(LogMelCfg), C.c_void_p, C.c_void_p, C.c_int,
                                          C.POINTER(C.c_void_p)]),
     "afs_logmel_plan_destroy": (C.c_int, [C.c_void_p]),
@@ -59,8 +60,8 @@ SIGNATURES = {
                               C.c_void_p, C.c_size_t, C.c_void_p]),
     "afs_bdc_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                               C.c_void_p, C.c_void_p]),
-    "afs_vote_acc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
-                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "afs_vote_acc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afs_energy_score": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                    C.c_void_p]),
 }

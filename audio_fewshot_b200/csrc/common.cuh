@@ -8,6 +8,7 @@
 namespace afs {
 
 extern thread_local int g_last_cuda_error;
+void count_launch();
 
 inline int cuda_fail(cudaError_t e) {
   g_last_cuda_error = static_cast<int>(e);
@@ -20,7 +21,12 @@ inline int cuda_fail(cudaError_t e) {
     if (_e != cudaSuccess) return ::afs::cuda_fail(_e); \
   } while (0)
 
-#define AFS_LAUNCH_CHECK() AFS_CUDA_TRY(cudaGetLastError())
+// One per kernel launch: counts it (afs_launch_count) and surfaces launch-configuration errors.
+#define AFS_LAUNCH_CHECK()                      \
+  do {                                          \
+    ::afs::count_launch();                      \
+    AFS_CUDA_TRY(cudaGetLastError());           \
+  } while (0)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 

@@ -16,6 +16,11 @@ from . import _lib
 PROTO_MODES = {"euclidean": 0, "cos_sim": 1, "dot": 2}
 
 
+def launch_count():
+    """Kernels launched through the C ABI by this process so far."""
+    return int(_lib.lib().afs_launch_count())
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -180,8 +185,13 @@ def bdc_pool(x, log_temp, triu=True):
     return out
 
 
-def vote_acc(logits, q_start, q_target):
-    """-> (q_pred int32 [nq], acc_pct float32 0-dim tensor, stats int32 [4]) without any host sync."""
+VOTE_TIE_RULES = {"smallest": 0, "torch_cuda": 1}
+
+
+def vote_acc(logits, q_start, q_target, tie_rule="torch_cuda"):
+    """-> (q_pred int32 [nq], acc_pct float32 0-dim tensor, stats int32 [4]) without any host sync.
+    tie_rule: "torch_cuda" = torch.mode on a CUDA slice (the reference's live path, utils.py:443);
+    "smallest" = torch.mode on a CPU tensor."""
     _need_cuda(logits, "logits")
     _need_cuda(q_start, "q_start", torch.int32)
     _need_cuda(q_target, "q_target", torch.int32)
@@ -191,7 +201,8 @@ def vote_acc(logits, q_start, q_target):
     q_pred = torch.empty((nq,), dtype=torch.int32, device=logits.device)
     stats = torch.empty((4,), dtype=torch.int32, device=logits.device)
     acc = torch.empty((), dtype=torch.float32, device=logits.device)
-    _lib.check(_lib.lib().afs_vote_acc(_ptr(logits), W, _ptr(q_start), nq, _ptr(q_target), _ptr(q_pred), _ptr(stats),
+    _lib.check(_lib.lib().afs_vote_acc(_ptr(logits), W, _ptr(q_start), nq, _ptr(q_target), VOTE_TIE_RULES[tie_rule], _ptr(q_pred),
+                                       _ptr(stats),
                                        _ptr(acc), _stream()), "afs_vote_acc")
     return q_pred, acc, stats
 

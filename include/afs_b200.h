@@ -42,6 +42,10 @@ typedef enum afs_status {
 int afs_abi_version(void);
 const char* afs_status_string(int status);
 int afs_last_cuda_error(void);
+/* Kernels launched by this library in this process so far (every entry point below counts
+ * its own launches; memsets and copies are not counted).  For benchmarks and tests that must
+ * prove the CUDA path ran.                                                               */
+uint64_t afs_launch_count(void);
 
 /* ------------------------------------------------------------------------
  * (1) Fused waveform -> normalised log-mel front-end.
@@ -150,12 +154,19 @@ int afs_bdc_fwd(const float* x, int32_t B, int32_t C, int32_t M, const float* lo
  * Replaces majority_vote + vote_catagorical_acc
  * (libfewshot_core/utils/utils.py:432-446) and the per-query D2H syncs.
  * logits [NQ, W]; q_start [nq+1] window offsets (exclusive cumsum of repeats);
- * q_target [nq]; q_pred [nq] out (mode of the window argmaxes, smallest label
- * on ties, as torch.mode); stats: int32[4] scratch+out, stats[0] = #correct,
- * stats[1] = nq (stats[2..3] internal); acc_pct out = 100*correct/nq.  W <= 64. */
+ * q_target [nq]; q_pred [nq] out (mode of the window argmaxes); stats: int32[4]
+ * scratch+out, stats[0] = #correct, stats[1] = nq (stats[2..3] internal);
+ * acc_pct out = 100*correct/nq.  W <= 64.
+ * tie_rule picks the label when several are equally frequent in a query:
+ *   AFS_VOTE_TIE_SMALLEST   = what torch.mode returns for a CPU tensor;
+ *   AFS_VOTE_TIE_TORCH_CUDA = what torch.mode returns for a CUDA tensor of <= 2048
+ *     elements -- the reference's live rule, its set_forward being CUDA-only
+ *     (proto_net.py:116-118).  See csrc/vote.cu for the rule.              */
+#define AFS_VOTE_TIE_SMALLEST 0
+#define AFS_VOTE_TIE_TORCH_CUDA 1
 int afs_vote_acc(const float* logits, int32_t W, const int32_t* q_start, int32_t nq,
-                 const int32_t* q_target, int32_t* q_pred, int32_t* stats, float* acc_pct,
-                 afs_stream_t stream);
+                 const int32_t* q_target, int32_t tie_rule, int32_t* q_pred, int32_t* stats,
+                 float* acc_pct, afs_stream_t stream);
 
 /* Energy score of DeepBDC (deepbdc.py:318-319 + utils.py:449-471):
  * u[q] = -logsumexp_w( mean over the query's windows of logits[., w] ).     */

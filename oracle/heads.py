@@ -144,15 +144,41 @@ def triuvec(x):
 
 
 # ---------------------------------------------------------------- vote / accuracy / CI
-def majority_vote(logits, query_nums):
+def torch_mode_cuda(labels):
+    """What torch.mode returns for a 1-D CUDA tensor of <= 2048 integer labels -- the rule the
+    reference's CUDA-only set_forward lives by (utils.py:443 called from proto_net.py:116).
+    PyTorch's fused small-slice kernel sorts the slice, hands sorted positions (2t, 2t+1) to
+    thread t and max-reduces (run count, position) through shuffle-down trees in which the lower
+    lane keeps ties, so among equally frequent labels the winner is the one whose run END lies in
+    the lane with the smallest bit-reversed (warp id, lane id).  Pinned by measurement on B200 /
+    torch 2.11: tools/probe_torch_mode.py -> tests/golden/torch_mode_cuda.npz."""
+    y = np.sort(np.asarray(labels).reshape(-1))
+    vals, cnt = np.unique(y, return_counts=True)
+    mx = cnt.max()
+    if mx == 1:
+        return int(y[0])
+    ends = np.cumsum(cnt) - 1
+    rev5 = lambda v: int("{:05b}".format(int(v) & 31)[::-1], 2)
+    best = None
+    for v, c, e in zip(vals, cnt, ends):
+        if c == mx:
+            lane = int(e) >> 1
+            key = (rev5(lane >> 5), rev5(lane))
+            if best is None or key < best[0]:
+                best = (key, int(v))
+    return best[1]
+
+
+def majority_vote(logits, query_nums, tie_rule="smallest"):
     """reference: majority_vote, libfewshot_core/utils/utils.py:436-446 (argmax over softmax,
-    then torch.mode per query group; returns float32 like the reference)."""
+    then torch.mode per query group; returns float32 like the reference).  tie_rule "smallest" is
+    torch.mode on this CPU; "torch_cuda" restates what the same call returns on a CUDA slice."""
     y = torch.softmax(torch.as_tensor(logits), dim=1).argmax(dim=1)
     out = torch.zeros(len(query_nums))
     end = 0
     for i, num in enumerate(query_nums):
         sl = y[end : end + int(num)]
-        out[i] = torch.mode(sl)[0]
+        out[i] = torch.mode(sl)[0] if tie_rule == "smallest" else torch_mode_cuda(sl.numpy())
         end += sl.shape[0]
     return out
 
@@ -192,7 +218,8 @@ def mean_confidence_interval(data, confidence=0.95):
 
 
 # ---------------------------------------------------------------- whole-head drivers
-def proto_forward(feat, way_num, shot_num, query_num, repeats, support_size, mode="euclidean"):
+def proto_forward(feat, way_num, shot_num, query_num, repeats, support_size, mode="euclidean",
+                  tie_rule="torch_cuda"):
     """reference: ProtoNet.set_forward after emb_func, proto_net.py:103-118.  feat [N, D] (CPU).
     Returns (output [sum R, W], acc, per-query predictions)."""
     support, query, _, query_target, _ = split_by_episode(feat, way_num, shot_num, query_num, repeats, support_size)
@@ -201,12 +228,12 @@ def proto_forward(feat, way_num, shot_num, query_num, repeats, support_size, mod
         outs.append(proto_layer(query[i].unsqueeze(0), support[i].unsqueeze(0), way_num, shot_num, mode)
                     .reshape(-1, way_num))
     output = torch.cat(outs, dim=0)
-    pred = majority_vote(output, repeats).to(torch.long)
+    pred = majority_vote(output, repeats, tie_rule).to(torch.long)  # set_forward is CUDA-only: CUDA torch.mode
     acc = vote_categorical_acc(query_target.reshape(-1), pred)
     return output, acc, pred
 
 
-def dn4_forward(feat, way_num, shot_num, query_num, repeats, support_size, n_k):
+def dn4_forward(feat, way_num, shot_num, query_num, repeats, support_size, n_k, tie_rule="torch_cuda"):
     """reference: DN4.set_forward after emb_func, dn4.py:100-118.  feat [N, C, H, W]."""
     support, query, _, query_target, _ = split_by_episode(feat, way_num, shot_num, query_num, repeats, support_size)
     outs = []
@@ -214,12 +241,12 @@ def dn4_forward(feat, way_num, shot_num, query_num, repeats, support_size, n_k):
         outs.append(dn4_layer(query[i].unsqueeze(0), support[i].unsqueeze(0), way_num, shot_num, n_k)
                     .view(-1, way_num))
     output = torch.cat(outs, 0)
-    pred = majority_vote(output, repeats).to(torch.long)
+    pred = majority_vote(output, repeats, tie_rule).to(torch.long)  # set_forward is CUDA-only: CUDA torch.mode
     acc = vote_categorical_acc(query_target.reshape(-1), pred)
     return output, acc, pred
 
 
-def deepbdc_forward(feat, way_num, shot_num, query_num, repeats, support_size):
+def deepbdc_forward(feat, way_num, shot_num, query_num, repeats, support_size, tie_rule="torch_cuda"):
     """reference: DeepBDC.set_forward after emb_func, deepbdc.py:291-319.  feat [N, D]."""
     support, query, _, query_target, _ = split_by_episode(feat, way_num, shot_num, query_num, repeats, support_size)
     outs = []
@@ -227,6 +254,6 @@ def deepbdc_forward(feat, way_num, shot_num, query_num, repeats, support_size):
         outs.append(deepbdc_proto_layer(query[i].unsqueeze(0), support[i].unsqueeze(0), way_num, shot_num)
                     .reshape(-1, way_num))
     output = torch.cat(outs, dim=0)
-    pred = majority_vote(output, repeats).to(torch.long)
+    pred = majority_vote(output, repeats, tie_rule).to(torch.long)  # set_forward is CUDA-only: CUDA torch.mode
     acc = vote_categorical_acc(query_target.reshape(-1), pred)
     return output, acc, pred, energy_score(output, repeats)

@@ -49,7 +49,7 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     h = _lib.lib()
     # null pointers / bad sizes must be refused before any CUDA call
     assert h.afs_proto_fwd(None, 0, None, 0, 0, 5, 5, 1600, 0, None, None, None, 0, None) == -1
-    assert h.afs_vote_acc(None, 5, None, 0, None, None, None, None, None) == -1
+    assert h.afs_vote_acc(None, 5, None, 0, None, 1, None, None, None, None) == -1
     assert h.afs_bdc_fwd(None, 1, 64, 10, None, 1, None, None) == -1
 
 

@@ -192,7 +192,8 @@ def test_vote_acc_energy_match_reference_golden(cuda, golden, name):
     tab = ragged_table(c["E"], c["W"], c["S"], c["Q"], rep, cuda)
     logits = torch.from_numpy(cases.split_logits(c, int(rep.sum()))).to(cuda)
     assert np.array_equal(tab.q_target.cpu().numpy(), g[name + "/query_target"].reshape(-1))
-    q_pred, acc, stats = ops.vote_acc(logits, tab.q_start, tab.q_target)
+    # the golden predictions come from the reference run on the CPU: torch.mode's CPU tie rule
+    q_pred, acc, stats = ops.vote_acc(logits, tab.q_start, tab.q_target, tie_rule="smallest")
     assert np.array_equal(q_pred.cpu().numpy(), g[name + "/vote_pred"])  # bit-exact predictions
     assert acc.item() == pytest.approx(float(g[name + "/vote_acc"]), rel=1e-6)
     assert stats[1].item() == tab.nq
@@ -200,12 +201,28 @@ def test_vote_acc_energy_match_reference_golden(cuda, golden, name):
     np.testing.assert_allclose(en, g[name + "/energy"], rtol=1e-5, atol=1e-5)
 
 
+def test_vote_matches_measured_torch_mode_cuda_golden(cuda, golden):
+    """tests/golden/torch_mode_cuda.npz: torch.mode outputs recorded on a B200 (tools/probe_torch_mode.py)."""
+    from audio_fewshot_b200 import ops
+    g = golden("torch_mode_cuda.npz")
+    n = g["n"].astype(np.int64)
+    W = 8
+    flat = np.concatenate([row[:k] for row, k in zip(g["labels"], n)]).astype(np.int64)
+    logits = torch.zeros(len(flat), W)
+    logits[torch.arange(len(flat)), torch.from_numpy(flat)] = 1.0
+    q_start = torch.from_numpy(np.concatenate([[0], np.cumsum(n)]).astype(np.int32)).to(cuda)
+    target = torch.from_numpy(g["mode"].astype(np.int32)).to(cuda)
+    q_pred, acc, stats = ops.vote_acc(logits.to(cuda), q_start, target, tie_rule="torch_cuda")
+    assert np.array_equal(q_pred.cpu().numpy(), g["mode"].astype(np.int32))
+    assert stats[0].item() == len(n) and acc.item() == 100.0
+
+
 def test_vote_tie_rule_equals_torch_mode_on_cuda(cuda):
     """The reference calls torch.mode on a CUDA slice (utils.py:443): same tie rule as ours."""
     from audio_fewshot_b200 import ops
     rng = np.random.default_rng(3)
     W, nq = 4, 300
-    rep = rng.integers(1, 7, size=nq)
+    rep = rng.integers(1, 40, size=nq)
     n = int(rep.sum())
     labels = rng.integers(0, W, size=n)
     logits = torch.zeros(n, W)

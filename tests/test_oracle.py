@@ -170,3 +170,15 @@ def test_oracle_split_equals_reference_on_random_ragged(reference):
         assert torch.equal(a[0], b[0])
         assert all(torch.equal(x, y) for x, y in zip(a[1], b[1]))
         assert torch.equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+
+
+def test_torch_mode_cuda_rule_matches_measured_golden(golden):
+    """torch.mode on CUDA does not return the smallest tied label; the oracle restates its rule and
+    is pinned by outputs recorded from torch 2.11 on a B200 (tools/probe_torch_mode.py)."""
+    g = golden("torch_mode_cuda.npz")
+    differs_from_cpu_rule = 0
+    for lab, n, m in zip(g["labels"], g["n"], g["mode"]):
+        y = lab[:n].astype(np.int64)
+        assert heads.torch_mode_cuda(y) == int(m)
+        differs_from_cpu_rule += int(torch.mode(torch.from_numpy(y))[0].item() != int(m))
+    assert differs_from_cpu_rule > 100  # the two rules really are different
