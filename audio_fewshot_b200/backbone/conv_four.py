@@ -3,11 +3,25 @@
 Same architecture, constructor kwargs and state_dict names as the reference's
 libfewshot_core/model/backbone/conv_four.py:28-128, so `*_best.pth` checkpoints load
 unchanged (layer{1..4}.0 = Conv2d with bias, layer{1..4}.1 = BatchNorm2d,
-logits.1 = BatchNorm1d(64), logits.2 = Linear(64, 1600)).  The convolutions stay on
-cuDNN: the north star names no backbone kernel.
+logits.1 = BatchNorm1d(64), logits.2 = Linear(64, 1600)).
+
+Two execution paths with the same parameters:
+  * training / autograd / CPU-constructed checks: the plain module graph (cuDNN + ATen), exactly the
+    reference's op sequence;
+  * inference on CUDA (eval mode, grad disabled, 1 input channel): `_forward_inference` --
+    block 1 is ONE sm_100a kernel (csrc/conv1.cu: conv + BatchNorm + activation + max-pool, the
+    [N,64,128,157] activation never reaches HBM), blocks 2-4 are cuDNN's fused conv+bias+ReLU on
+    channels-last tensors with BatchNorm folded into the weights (no layout round trips, no separate
+    BN / bias / ReLU passes), and BatchNorm1d is folded into the final Linear.  In the reference's
+    eager sequence those elementwise and layout kernels are 88 % of an evaluation step on B200
+    (profiles/r01_bench_launches.csv).
 """
+import numpy as np
 import torch
+import torch.nn.functional as F
 from torch import nn
+
+from .. import ops
 
 
 def pooled_extent(n, times, k=3):
@@ -44,7 +58,67 @@ class Conv64F(nn.Module):
         self.logits = nn.Sequential(nn.Dropout(p=0.3), nn.BatchNorm1d(flat, eps=1e-05, momentum=0.1, affine=True),
                                     nn.Linear(in_features=flat, out_features=1600))
 
+    # ------------------------------------------------------------------ inference path
+    def _inference_ok(self, x):
+        return (not self.training and not torch.is_grad_enabled() and x.is_cuda and not self.is_feature
+                and x.dim() == 4 and x.shape[1] == 1 and x.dtype == torch.float32
+                and self.layer1[1].track_running_stats and self.layer1[0].out_channels == 64)
+
+    def _state_key(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    @staticmethod
+    def _fold(conv, bn):
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        w = conv.weight * scale.view(-1, 1, 1, 1)
+        b = (conv.bias - bn.running_mean) * scale + bn.bias
+        return w, b
+
+    def _folded(self):
+        key = self._state_key()
+        cache = getattr(self, "_fold_cache", None)
+        if cache is not None and cache["key"] == key:
+            return cache
+        with torch.no_grad():
+            w1, b1 = self._fold(self.layer1[0], self.layer1[1])
+            cache = {"key": key,
+                     "w1": w1.reshape(64, 9).float().cpu().numpy(), "b1": b1.float().cpu().numpy(),
+                     "slope": float(getattr(self.layer1[2], "negative_slope", 0.0))}
+            for i, layer in ((2, self.layer2), (3, self.layer3), (4, self.layer4)):
+                w, b = self._fold(layer[0], layer[1])
+                cache["w%d" % i] = w.contiguous(memory_format=torch.channels_last)
+                cache["b%d" % i] = b.contiguous()
+            bn, lin = self.logits[1], self.logits[2]
+            s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            cache["wl"] = (lin.weight * s.view(1, -1)).contiguous()
+            cache["bl"] = (lin.bias + lin.weight @ (bn.bias - bn.running_mean * s)).contiguous()
+        self._fold_cache = cache
+        return cache
+
+    @staticmethod
+    def _conv_act(h, w, b, slope):
+        if slope == 0.0:
+            return torch.cudnn_convolution_relu(h, w, b, (1, 1), (1, 1), (1, 1), 1)
+        return F.leaky_relu(F.conv2d(h, w, b, padding=1), slope, inplace=True)
+
+    def _forward_inference(self, x):
+        c = self._folded()
+        h = ops.conv1_bn_act_pool3(x, c["w1"], c["b1"], c["slope"])  # [N,64,H/3,W/3] channels_last
+        h = F.max_pool2d(self._conv_act(h, c["w2"], c["b2"], c["slope"]), 3, 3)
+        h = self._conv_act(h, c["w3"], c["b3"], c["slope"])
+        if self.maxpool_last2:
+            h = F.max_pool2d(h, 3, 3)
+        h = self._conv_act(h, c["w4"], c["b4"], c["slope"])
+        if self.last_pool:
+            h = F.max_pool2d(h, 3, 3)
+        if self.is_flatten:
+            h = h.contiguous().view(h.size(0), -1)  # NCHW flatten order, as out4.view(N, -1)
+            h = torch.addmm(c["bl"], h, c["wl"].t())
+        return h
+
     def forward(self, x):
+        if self._inference_ok(x):
+            return self._forward_inference(x)
         out1 = self.layer1(x)
         out2 = self.layer2(out1)
         out3 = self.layer3(out2)

@@ -98,6 +98,27 @@ class LogMelPlan:
             pass
 
 
+# --------------------------------------------------------------------------- backbone stem
+def conv1_bn_act_pool3(x, w_folded, shift, negative_slope=0.0):
+    """Fused eval-mode first block of Conv64F.  x [N,1,H,W] CUDA fp32; w_folded [C,9] / shift [C]:
+    contiguous float32 numpy arrays (BatchNorm already folded).  Returns a channels_last
+    [N, C, H//3, W//3] tensor."""
+    _need_cuda(x, "x")
+    if x.dim() != 4 or x.shape[1] != 1:
+        raise ValueError("x must be [N, 1, H, W]")
+    x = x.contiguous()
+    N, _, H, Wd = x.shape
+    Cc = int(shift.shape[0])
+    w_folded = np.ascontiguousarray(w_folded, dtype=np.float32).reshape(Cc, 9)
+    shift = np.ascontiguousarray(shift, dtype=np.float32)
+    out = torch.empty((N, Cc, H // 3, Wd // 3), dtype=torch.float32, device=x.device,
+                      memory_format=torch.channels_last)
+    _lib.check(_lib.lib().afs_conv1_bn_act_pool3_fwd(_ptr(x), N, H, Wd, w_folded.ctypes.data_as(C.c_void_p),
+                                                     shift.ctypes.data_as(C.c_void_p), Cc, float(negative_slope),
+                                                     _ptr(out), _stream()), "afs_conv1_bn_act_pool3_fwd")
+    return out
+
+
 # --------------------------------------------------------------------------- heads
 def _proto_call(feat, cls_row, E, W, S, mode, want_pred):
     _need_cuda(feat, "feat")

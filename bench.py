@@ -7,13 +7,14 @@ Workload (BASELINE.json `metric`; SURVEY.md 8d, config C1 = config/proto_5shot_i
 Conv64F, 5w5s15q = 100 clips per episode, each clip 5 s @ 16 kHz (L = 80 000) -> log-mel [1,128,157]
 (n_fft 1024, hop 512, 128 slaney mels, KOS_0.5_alpha mean/std).  One "step" = one pass of the hot path
 over `--episodes-per-step` episodes per rank:
-    fused log-mel kernel -> Conv64F (cuDNN; not ours) -> prototype head kernel -> vote/accuracy kernel.
+    fused log-mel kernel -> Conv64F (fused conv1 kernel + cuDNN blocks 2-4) -> prototype head kernel ->
+    vote/accuracy kernel.
 Episodes are independent, so ranks never exchange data inside a step ("weak" scaling: per-GPU work is
 fixed).  Synthetic seeded waveforms, weights derived from parameter names (oracle.cases.perturb_bn_).
 
 `value`  : device-resident inputs (two rotating batches, each larger than L2).
-`e2e`    : the public call EpisodePipeline(wav_pinned_host, ...) -- H2D of the waveforms and D2H of the
-           logits + accuracy inside the timed region.
+`e2e`    : the public call EpisodePipeline.stream(pinned host batches) -- every step's H2D of the waveforms
+           and D2H of the logits + accuracy inside the timed region (copies overlap compute).
 `roofline`: the fused log-mel kernel (our dominant kernel), algorithmic bytes 4*L + 4*128*T per clip over
            its CUDA-event duration measured inside the timed region, against MEASURED_PEAKS.json.
 `cpu_baseline` / `--impl reference`: the oracle port of the reference path (torch.stft front-end spec ->
@@ -47,7 +48,7 @@ WORKLOAD = "ProtoNet Conv64F 5w5s15q, 100 clips/episode, 5 s @ 16 kHz -> log-mel
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--episodes-per-step", type=int, default=8, help="episodes per rank per step")
@@ -150,7 +151,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "episodes/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------- clocks
@@ -241,8 +242,6 @@ def run_b200(args, rank, world, local_rank):
         first = (b * world + rank) * E
         host.append(torch.from_numpy(cases.synthetic_clip_batch(1234, first, E, W, S, Q, L)).pin_memory())
     devb = [h.to(dev) for h in host]
-    out_host = torch.empty((E * W * Q, W), dtype=torch.float32).pin_memory()
-    acc_host = torch.empty((), dtype=torch.float32).pin_memory()
     wav_bytes = n_clips * L * 4
 
     def barrier():
@@ -266,19 +265,22 @@ def run_b200(args, rank, world, local_rank):
             ev[1].record()
         return model.set_forward([image, None, repeats, support_size])
 
-    def step_e2e(i):
-        output, acc = pipe(host[i % 2], repeats, support_size)
-        out_host.copy_(output, non_blocking=True)
-        acc_host.copy_(acc, non_blocking=True)
+    def run_e2e(n):
+        """n steps through the public streaming call: every step's waveforms go pinned host -> device on the
+        copy stream, its logits and accuracy come back to pinned host memory; copies overlap compute."""
+        last = None
+        for last in pipe.stream((host[i % 2] for i in range(n)), repeats, support_size):
+            pass
+        return last
 
     with torch.no_grad():
         # ---- device-resident: `value`
-        for i in range(args.warmup):
-            step_device(i)
-        barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        for i in range(args.warmup):
+            step_device(i)
+        barrier()
         launches0 = ops.launch_count()
         lm_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                      for _ in range(args.steps)]
@@ -294,12 +296,10 @@ def run_b200(args, rank, world, local_rank):
         acc_dev = float(acc.item())
 
         # ---- end to end through the public call: `e2e`
-        for i in range(args.warmup):
-            step_e2e(i)
+        run_e2e(args.warmup)
         barrier()
         t0.record()
-        for i in range(args.steps):
-            step_e2e(i)
+        out_host, acc_host = run_e2e(args.steps)
         t1.record()
         barrier()
         ms_e2e = max_over_ranks(t0.elapsed_time(t1))
@@ -334,7 +334,9 @@ def run_b200(args, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "episodes_per_step_per_gpu": E, "clips_per_step_per_gpu": n_clips,
                    "way": W, "shot": S, "query": Q, "clip_samples": L, "n_fft": 1024, "hop": HOP, "n_mels": N_MELS,
-                   "backbone": "Conv64F via cuDNN (TF32 conv allowed, the reference's PyTorch default)",
+                   "backbone": "Conv64F eval path: fused conv1+BN+ReLU+pool kernel (fp32), cuDNN conv+bias+ReLU for "
+                               "blocks 2-4 (TF32 allowed, the reference's PyTorch default)",
+                   "e2e_path": "EpisodePipeline.stream: H2D on a copy stream overlapped with compute, 2 buffers",
                    "l2_policy": "inputs larger than L2: %d MB of waveform per step, two rotating batches"
                                 % (wav_bytes // 2 ** 20),
                    "parallelism": "episodes sharded over %d rank(s), no data-path collective" % world,
@@ -351,11 +353,29 @@ def run_b200(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(args.cpu_seconds)
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Libraries (NCCL's version banner, cuDNN warnings) print to fd 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def main():
     args = parse()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

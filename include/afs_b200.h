@@ -97,6 +97,18 @@ int afs_logmel_fwd(const afs_logmel_plan* plan, const float* wav, int32_t B, int
                    uint64_t seed, uint64_t first_clip_index, float* out, afs_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * (1b) First Conv64F block, inference only: Conv2d(1->C,3x3,pad 1) + BatchNorm2d(eval) +
+ * ReLU / LeakyReLU(negative_slope) + MaxPool2d(3,3), fused.  Replaces layer1 of Conv64F
+ * (libfewshot_core/model/backbone/conv_four.py:61-66,101-103) in eval mode.
+ * x [N,1,H,Wd] fp32 (device); w_folded_host [C*9] = conv weight * gamma/sqrt(var+eps) and
+ * shift_host [C] = (bias - mean)*gamma/sqrt(var+eps) + beta are HOST pointers (they travel
+ * as kernel parameters: constant-bank operands); out [N, H/3, Wd/3, C] fp32 channels-last
+ * (the NHWC bytes of a torch channels_last [N,C,H/3,Wd/3] tensor).  C == 64 built.   */
+int afs_conv1_bn_act_pool3_fwd(const float* x, int32_t N, int32_t H, int32_t Wd,
+                               const float* w_folded_host, const float* shift_host, int32_t C,
+                               float negative_slope, float* out, afs_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Episode row table shared by the heads (replaces the host slicing of
  * AbstractModel.split_by_episode, libfewshot_core/model/abstract_model.py:176-332).
  * Rows of `feat` are episode-major, class-major; block g = e*W + w holds S

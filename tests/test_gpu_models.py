@@ -1,0 +1,241 @@
+"""GPU parity of the drop-in classes: backbones (incl. the fused Conv64F inference path) against the
+reference's golden features, set_forward / set_forward_loss of ProtoNet, DN4, DeepBDC against the oracle
+drivers on identical features, and the waveform -> logits pipeline (plain and CUDA-graph)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import backbones as obb
+from oracle import cases, heads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_convs():
+    """Backbone parity is asserted with exact-fp32 convolutions (the reference's TF32 default is not bit-stable)."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _net(cuda, name):
+    from audio_fewshot_b200 import model as arch
+    ctor, kwargs = cases.BACKBONE_CASES[name]
+    torch.manual_seed(0)
+    net = getattr(arch, ctor)(**kwargs).eval()
+    cases.perturb_bn_(net)
+    return net.to(cuda)
+
+
+@pytest.mark.parametrize("name", sorted(cases.BACKBONE_CASES))
+def test_backbones_match_reference_golden_on_gpu(cuda, golden, name):
+    g = golden("backbones.npz")
+    net = _net(cuda, name)
+    x = torch.from_numpy(cases.backbone_input()).to(cuda)
+    with torch.no_grad():
+        y = net(x)
+    want = g[name + "/out"]
+    assert tuple(y.shape) == want.shape
+    assert np.abs(y.float().cpu().numpy() - want).max() <= 2e-4 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("name", ["conv64f_flat", "conv64f_dn4"])
+def test_conv64f_inference_path_equals_module_graph(cuda, name):
+    """The fused path (conv1 kernel + folded cuDNN blocks) against the plain module graph on a bigger batch."""
+    from audio_fewshot_b200 import ops
+    net = _net(cuda, name)
+    x = torch.from_numpy((np.random.default_rng(5).standard_normal((37, 1, 128, 157)) * 0.7).astype(np.float32)).to(cuda)
+    n0 = ops.launch_count()
+    with torch.no_grad():
+        fast = net(x)
+    assert ops.launch_count() == n0 + 1  # the conv1 kernel ran
+    with torch.enable_grad():  # grad mode -> plain graph (the reference's op sequence)
+        slow = net(x).detach()
+    assert ops.launch_count() == n0 + 1
+    assert fast.shape == slow.shape
+    assert (fast - slow).abs().max().item() <= 2e-5 * slow.abs().max().item()
+
+
+def test_conv1_kernel_odd_sizes_and_leaky(cuda):
+    from audio_fewshot_b200 import ops
+    rng = np.random.default_rng(8)
+    for (N, H, Wd, slope) in [(3, 128, 157, 0.0), (2, 7, 11, 0.2), (1, 3, 3, 0.0), (130, 9, 10, 0.1)]:
+        x = torch.from_numpy(rng.standard_normal((N, 1, H, Wd)).astype(np.float32)).to(cuda)
+        w = rng.standard_normal((64, 9)).astype(np.float32) * 0.3
+        w[5] *= -1.0  # a negative BatchNorm scale folded in
+        b = rng.standard_normal(64).astype(np.float32)
+        got = ops.conv1_bn_act_pool3(x, w, b, slope)
+        assert got.is_contiguous(memory_format=torch.channels_last) or got.shape[2] * got.shape[3] == 1
+        conv = torch.nn.functional.conv2d(x.double(), torch.from_numpy(w).to(cuda).double().view(64, 1, 3, 3),
+                                          torch.from_numpy(b).to(cuda).double(), padding=1)
+        want = torch.nn.functional.max_pool2d(torch.nn.functional.leaky_relu(conv, slope), 3, 3)
+        assert got.shape == want.shape
+        assert (got.double() - want).abs().max().item() < 1e-5
+
+
+def test_folded_weights_follow_parameter_updates(cuda):
+    net = _net(cuda, "conv64f_flat")
+    x = torch.from_numpy(cases.backbone_input()).to(cuda)
+    with torch.no_grad():
+        a = net(x).clone()
+        net.layer1[0].weight.mul_(1.5)
+        net.logits[2].bias.add_(1.0)
+        b = net(x)
+        with torch.enable_grad():
+            want = net(x).detach()
+    assert not torch.allclose(a, b)
+    assert (b - want).abs().max().item() <= 2e-5 * want.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------ set_forward
+def _ragged(E, W, Q, seed):
+    return np.random.default_rng(seed).integers(1, 4, size=E * W * Q).astype(np.int64)
+
+
+class _Feat(torch.nn.Module):
+    """emb_func stand-in: the 'image' rows already are the features (heads are tested on identical inputs)."""
+
+    def forward(self, x):
+        return x
+
+
+@pytest.mark.parametrize("E,W,S,Q,D,distance", [(3, 5, 5, 4, 1600, "euclidean"), (2, 5, 1, 15, 640, "cos_sim")])
+def test_protonet_set_forward_matches_oracle(cuda, E, W, S, Q, D, distance):
+    from audio_fewshot_b200 import model as arch
+    rep = _ragged(E, W, Q, 3)
+    N = E * W * S + int(rep.sum())
+    feat = torch.from_numpy(np.random.default_rng(1).standard_normal((N, D)).astype(np.float32))
+    m = arch.ProtoNet(way_num=W, shot_num=S, query_num=Q, test_way=W, test_shot=S, test_query=Q, emb_func=_Feat(),
+                      device=cuda, distance=distance).to(cuda).eval()
+    with torch.no_grad():
+        out, acc = m([feat, torch.zeros(N), torch.from_numpy(rep), E * W * S])
+    want, want_acc, _ = heads.proto_forward(feat, W, S, Q, torch.from_numpy(rep), E * W * S, distance)
+    assert out.shape == want.shape
+    assert (out.cpu() - want).abs().max().item() <= 1e-3 * want.abs().max().item()
+    assert torch.equal(out.cpu().argmax(1), want.argmax(1))
+    assert acc.item() == pytest.approx(want_acc.item(), abs=1e-4)
+
+
+def test_dn4_set_forward_matches_oracle(cuda):
+    from audio_fewshot_b200 import model as arch
+    E, W, S, Q, C, H, Wd = 2, 5, 5, 3, 64, 4, 5
+    rep = _ragged(E, W, Q, 4)
+    N = E * W * S + int(rep.sum())
+    feat = torch.from_numpy(np.abs(np.random.default_rng(2).standard_normal((N, C, H, Wd))).astype(np.float32))
+    m = arch.DN4(n_k=3, way_num=W, shot_num=S, query_num=Q, test_way=W, test_shot=S, test_query=Q, emb_func=_Feat(),
+                 device=cuda).to(cuda).eval()
+    with torch.no_grad():
+        out, acc = m([feat, torch.zeros(N), torch.from_numpy(rep), E * W * S])
+    want, want_acc, _ = heads.dn4_forward(feat, W, S, Q, torch.from_numpy(rep), E * W * S, 3)
+    assert (out.cpu() - want).abs().max().item() <= 1e-3 * want.abs().max().item()
+    assert torch.equal(out.cpu().argmax(1), want.argmax(1))
+    assert acc.item() == pytest.approx(want_acc.item(), abs=1e-4)
+
+
+@pytest.mark.parametrize("S", [1, 5])
+def test_deepbdc_set_forward_and_energy_match_oracle(cuda, S, tmp_path, monkeypatch):
+    from audio_fewshot_b200 import model as arch
+    monkeypatch.chdir(tmp_path)  # the energy branch appends to ./test_uncertainty.npy like the reference
+    E, W, Q, D = 2, 5, 4, 2080
+    rep = _ragged(E, W, Q, 6)
+    N = E * W * S + int(rep.sum())
+    feat = torch.from_numpy((np.random.default_rng(7).standard_normal((N, D)) * 0.1).astype(np.float32))
+    m = arch.DeepBDC(way_num=W, shot_num=S, query_num=Q, test_way=W, test_shot=S, test_query=Q, emb_func=_Feat(),
+                     device=cuda).to(cuda).eval()
+    batch = [feat, torch.zeros(N), torch.from_numpy(rep), E * W * S]
+    with torch.no_grad():
+        out, acc = m(batch)
+        out5 = m.set_forward(batch, update_threshold=True, enhance_classification_via_energy=True)
+    want, want_acc, _, _ = heads.deepbdc_forward(feat, W, S, Q, torch.from_numpy(rep), E * W * S)
+    assert (out.cpu() - want).abs().max().item() <= 1e-3 * want.abs().max().item()
+    assert torch.equal(out.cpu().argmax(1), want.argmax(1))
+    assert acc.item() == pytest.approx(want_acc.item(), abs=1e-4)
+    assert len(out5) == 5
+    en = heads.energy_score(want, torch.from_numpy(rep)).numpy()
+    np.testing.assert_allclose(out5[2].cpu().numpy(), en, rtol=1e-4, atol=1e-4)
+    assert out5[3].sum() == int(0.2 * len(rep)) and out5[4].sum() == int(rep.sum())
+    thr, per_batch = m.get_uncertainty_threshold()
+    assert thr is not None and len(per_batch) == 1
+
+
+def test_protonet_set_forward_loss_gradients_match_autograd_of_oracle(cuda):
+    from audio_fewshot_b200 import model as arch
+    E, W, S, Q, D = 2, 5, 5, 6, 320
+    N = E * W * (S + Q)
+    x = np.random.default_rng(11).standard_normal((N, D)).astype(np.float32)
+    lin = torch.nn.Linear(D, D, bias=False)
+    m = arch.ProtoNet(way_num=W, shot_num=S, query_num=Q, test_way=W, test_shot=S, test_query=Q, emb_func=lin,
+                      device=cuda).to(cuda)
+    m.train()
+    out, acc, loss = m([torch.from_numpy(x), torch.zeros(N)])
+    loss.backward()
+    got = lin.weight.grad.detach().cpu()
+
+    lin2 = torch.nn.Linear(D, D, bias=False)
+    with torch.no_grad():
+        lin2.weight.copy_(lin.weight.detach().cpu())
+    feat = lin2(torch.from_numpy(x))
+    sup, qry, _, qt, _ = heads.split_by_episode(feat, W, S, Q)
+    ref_out = heads.proto_layer(qry, sup, W, S).reshape(-1, W)
+    ref_loss = torch.nn.functional.cross_entropy(ref_out, qt.reshape(-1))
+    ref_loss.backward()
+    assert loss.item() == pytest.approx(ref_loss.item(), rel=1e-4)
+    assert (got - lin2.weight.grad).abs().max().item() <= 2e-3 * lin2.weight.grad.abs().max().item()
+    assert isinstance(acc, float)
+
+
+# ------------------------------------------------------------------------------------------ pipeline
+def test_pipeline_waveform_to_logits_and_cuda_graph(cuda):
+    from audio_fewshot_b200 import model as arch
+    from audio_fewshot_b200.frontend import LogMelFrontEnd
+    from audio_fewshot_b200.pipeline import EpisodePipeline
+    from oracle import frontend as ofe
+    W, S, Q, L, E = 5, 2, 3, 16000, 2
+    mean, std = -15.114207, 26.22313
+    wav = cases.synthetic_clip_batch(3, 0, E, W, S, Q, L)
+    net = _net(cuda, "conv64f_flat")
+    model = arch.ProtoNet(way_num=W, shot_num=S, query_num=Q, test_way=W, test_shot=S, test_query=Q, emb_func=net,
+                          device=cuda).to(cuda).eval()
+    front = LogMelFrontEnd(hop_length=102, n_mels=128, mean=mean, std=std).to(cuda).eval()
+    repeats = torch.ones(E * W * Q, dtype=torch.long)
+    plain = EpisodePipeline(front, model)
+    out, acc = plain(torch.from_numpy(wav).pin_memory(), repeats, E * W * S)
+    image = torch.from_numpy(ofe.logmel_f64(wav, hop=102, mean=mean, std=std).astype(np.float32))
+    sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        feat = obb.conv64f_forward(sd, image)
+    want, want_acc, _ = heads.proto_forward(feat, W, S, Q, repeats, E * W * S)
+    assert (out.cpu() - want).abs().max().item() <= 1e-3 * want.abs().max().item()
+    assert torch.equal(out.cpu().argmax(1), want.argmax(1))
+    assert acc.item() == pytest.approx(want_acc.item(), abs=1e-4)
+
+    graphed = EpisodePipeline(front, model, use_graph=True)
+    for _ in range(2):
+        out_g, acc_g = graphed(torch.from_numpy(wav).pin_memory(), repeats, E * W * S)
+    assert torch.equal(out_g, out) and acc_g.item() == acc.item()
+    wav2 = cases.synthetic_clip_batch(4, 0, E, W, S, Q, L)
+    out_g2, _ = graphed(torch.from_numpy(wav2).pin_memory(), repeats, E * W * S)
+    out_p2, _ = plain(torch.from_numpy(wav2).pin_memory(), repeats, E * W * S)
+    assert torch.equal(out_g2, out_p2)
+
+
+def test_pipeline_stream_overlaps_copies_and_matches_single_calls(cuda):
+    from audio_fewshot_b200 import model as arch
+    from audio_fewshot_b200.frontend import LogMelFrontEnd
+    from audio_fewshot_b200.pipeline import EpisodePipeline
+    W, S, Q, L, E = 5, 1, 2, 16000, 1
+    net = _net(cuda, "conv64f_flat")
+    model = arch.ProtoNet(way_num=W, shot_num=S, query_num=Q, test_way=W, test_shot=S, test_query=Q, emb_func=net,
+                          device=cuda).to(cuda).eval()
+    front = LogMelFrontEnd(hop_length=102, n_mels=128, mean=-15.0, std=26.0).to(cuda).eval()
+    pipe = EpisodePipeline(front, model)
+    repeats = torch.ones(E * W * Q, dtype=torch.long)
+    batches = [torch.from_numpy(cases.synthetic_clip_batch(9, i, E, W, S, Q, L)).pin_memory() for i in range(5)]
+    singles = [pipe(b, repeats, E * W * S) for b in batches]
+    got = list(pipe.stream(iter(batches), repeats, E * W * S))
+    assert len(got) == 5
+    for (o1, a1), (o2, a2) in zip(singles, got):
+        assert torch.equal(o1.cpu(), o2) and a1.item() == a2.item()  # stream() returns host tensors
