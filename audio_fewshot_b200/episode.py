@@ -24,7 +24,7 @@ import torch
 
 class EpisodeTable:
     __slots__ = ("E", "W", "S", "Q", "N", "NQ", "nq", "cls_row", "q_start", "q_target", "q_target_long",
-                 "cls_row_host", "q_start_host")
+                 "cls_row_host", "q_start_host", "_rows")
 
     def __init__(self, E, W, S, Q, repeats_host, device):
         rep = np.asarray(repeats_host, dtype=np.int64).reshape(-1)
@@ -48,6 +48,23 @@ class EpisodeTable:
         self.q_start = torch.from_numpy(self.q_start_host).to(device)
         self.q_target = torch.from_numpy(q_target.astype(np.int32)).to(device)
         self.q_target_long = self.q_target.long()
+        self._rows = None
+
+    def episode_rows(self):
+        """(support_rows[e], query_rows[e]) int64 device index tensors per episode, in the order the
+        reference stacks them (abstract_model.py:274-332, mode 2): class-major, supports before queries."""
+        if self._rows is None:
+            dev = self.cls_row.device
+            sup, qry = [], []
+            for e in range(self.E):
+                blocks = range(e * self.W, (e + 1) * self.W)
+                s_idx = np.concatenate([np.arange(self.cls_row_host[g], self.cls_row_host[g] + self.S) for g in blocks])
+                q_idx = np.concatenate([np.arange(self.cls_row_host[g] + self.S, self.cls_row_host[g + 1])
+                                        for g in blocks])
+                sup.append(torch.from_numpy(s_idx.astype(np.int64)).to(dev))
+                qry.append(torch.from_numpy(q_idx.astype(np.int64)).to(dev))
+            self._rows = (sup, qry)
+        return self._rows
 
 
 class EpisodeTableCache:

@@ -128,6 +128,19 @@ def perturb_bn_(net):
     return net
 
 
+# ------------------------------------------------------------------ MAML (config C5, shrunk)
+MAML_CASE = dict(seed=71, torch_seed=5, E=2, W=5, S=2, Q=3, lr=0.01, train_iter=2, test_iter=3, feat_dim=1600,
+                 backbone=dict(is_flatten=True, is_feature=False, leaky_relu=False, negative_slope=0.2,
+                               last_pool=True, num_channels=1))
+MAML_GRAD_KEYS = ("emb_func.layer1.0.weight", "emb_func.layer3.1.bias", "emb_func.logits.1.weight",
+                  "emb_func.logits.2.bias", "classifier.layers.0.weight")
+
+
+def maml_images(c=MAML_CASE):
+    n = c["E"] * c["W"] * (c["S"] + c["Q"])
+    return (_rng(c["seed"]).standard_normal((n, 1, 128, 157)) * 0.5).astype(np.float32)
+
+
 # ------------------------------------------------------------------ synthetic waveforms (SURVEY.md 8d)
 def synthetic_clip_batch(seed, first_episode, n_episodes, W, S, Q, L, sample_rate=16000):
     """[E*W*(S+Q), L] fp32, class-major rows: N(0,1)*0.1 noise + a class-dependent tone

@@ -21,7 +21,40 @@ from .ref_import import import_reference
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
+def make_maml():
+    """MAML.set_forward_loss (maml.py:91-123) of the real reference on the CPU.  The reference's
+    BatchNorm2d_fw calls .cuda() on its scratch buffers (maml_module.py:85-86); on this GPU-less
+    machine Tensor.cuda is patched to the identity for the duration of the run -- nothing else changes."""
+    arch, utils, _ = import_reference()
+    c = cases.MAML_CASE
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        torch.manual_seed(0)
+        emb = arch.Conv64F(**c["backbone"])
+        model = arch.MAML(inner_param=dict(lr=c["lr"], train_iter=c["train_iter"], test_iter=c["test_iter"]),
+                          feat_dim=c["feat_dim"], way_num=c["W"], shot_num=c["S"], query_num=c["Q"],
+                          test_way=c["W"], test_shot=c["S"], test_query=c["Q"], emb_func=emb, device="cpu")
+        cases.perturb_bn_(model)
+        model.train()
+        x = torch.from_numpy(cases.maml_images(c))
+        torch.manual_seed(c["torch_seed"])  # Dropout(0.3) of Conv64F.logits is live during adaptation
+        output, acc, loss = model([x, torch.zeros(x.shape[0])])
+        loss.backward()
+        named = dict(model.named_parameters())
+        out = {"output": output.detach().numpy(), "acc": np.asarray(acc), "loss": np.asarray(loss.item()),
+               "keys": np.asarray(sorted(model.state_dict().keys()))}
+        for k in cases.MAML_GRAD_KEYS:
+            out["grad/" + k] = named[k].grad.numpy()
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    np.savez_compressed(os.path.join(OUT, "maml.npz"), **out)
+    print("maml.npz", os.path.getsize(os.path.join(OUT, "maml.npz")), "loss", out["loss"], "acc", out["acc"])
+
+
 def main():
+    if "--maml" in sys.argv:
+        return make_maml()
     arch, utils, _ = import_reference()
     from libfewshot_core.model.metric.proto_net import ProtoLayer
     from libfewshot_core.model.metric.dn4 import DN4Layer
@@ -105,6 +138,7 @@ def main():
         out[name + "/out"] = y.numpy()
         out[name + "/keys"] = np.asarray(sorted(net.state_dict().keys()))
     np.savez_compressed(os.path.join(OUT, "backbones.npz"), **out)
+    make_maml()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -239,3 +239,28 @@ def test_pipeline_stream_overlaps_copies_and_matches_single_calls(cuda):
     assert len(got) == 5
     for (o1, a1), (o2, a2) in zip(singles, got):
         assert torch.equal(o1.cpu(), o2) and a1.item() == a2.item()  # stream() returns host tensors
+
+
+def test_maml_set_forward_on_gpu_matches_cpu_inner_loop(cuda):
+    """The CPU inner loop is pinned to the real reference (tests/test_maml.py); here the same class adapts on
+    the GPU (dropout disabled so both devices see the same network) and votes with afs_vote_acc."""
+    from test_maml import _model
+    c = cases.MAML_CASE
+    rep = np.ones(c["E"] * c["W"] * c["Q"], dtype=np.int64)
+    x = torch.from_numpy(cases.maml_images(c))
+    outs = {}
+    for dev in ("cpu", cuda):
+        m = _model(dev)
+        m.emb_func.logits[0].p = 0.0
+        m.eval()
+        if dev == "cpu":
+            tab = m._table(x.shape[0], torch.from_numpy(rep), c["E"] * c["W"] * c["S"])
+            sup, qry = tab.episode_rows()
+            outs["cpu"] = m._adapt_all(x, tab, sup, qry).detach()
+        else:
+            with torch.no_grad():  # set_forward re-enables grad for the inner loop itself
+                out, acc = m([x, torch.zeros(x.shape[0]), torch.from_numpy(rep), c["E"] * c["W"] * c["S"]])
+            outs["gpu"] = out.cpu()
+            want_acc = (outs["cpu"].argmax(1) == tab.q_target_long).float().mean().item() * 100
+            assert acc.item() == pytest.approx(want_acc, abs=1e-3)
+    assert (outs["gpu"] - outs["cpu"]).abs().max().item() <= 5e-3 * outs["cpu"].abs().max().item()
