@@ -38,9 +38,7 @@ class BdcPool(nn.Module):
     def forward(self, x):
         if self.dr is not None and self.dr != self.input_dim:
             x = self.conv_dr_block(x)
-        if torch.is_grad_enabled() and (x.requires_grad or self.temperature.requires_grad and self.training):
-            raise NotImplementedError("backward of the BDC kernel is not built; call under torch.no_grad()")
-        return ops.bdc_pool(x, self.temperature.detach(), triu=self.is_vec)
+        return ops.bdc_pool(x, self.temperature, triu=self.is_vec)
 
 
 class ResNetBdc(nn.Module):

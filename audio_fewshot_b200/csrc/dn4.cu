@@ -226,6 +226,82 @@ dn4_reduce_kernel(const float* __restrict__ rowsum, int NQ, int W, int HW,
   if (pred != nullptr) pred[o] = best_w;
 }
 
+// ---- backward (DN4.set_forward_loss, dn4.py:122-155 under autograd) ----
+// score[o,w] = sum_m sum_{k<n_k} <q_hat[o,m,:], s_hat[w, idx[o,w,m,k], :]> with the top-k selection held
+// fixed (torch.topk's backward routes the gradient to the selected entries only).
+// One warp per query descriptor (o, m): lanes stride over channels; d q_hat is owned (plain store),
+// d s_hat is scattered with atomicAdd (several query descriptors select the same support descriptor).
+__global__ void __launch_bounds__(256)
+dn4_bwd_scatter_kernel(const float* __restrict__ nf, const int32_t* __restrict__ cls_row, int EW, int W, int S,
+                       int C, int HW, int n_k, int NQ, const int32_t* __restrict__ topk_idx,
+                       const float* __restrict__ grad_score, float* __restrict__ dnf) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= static_cast<int64_t>(NQ) * HW) return;
+  const int o = static_cast<int>(wid / HW);
+  const int m = static_cast<int>(wid - static_cast<int64_t>(o) * HW);
+  // block g of output row o: cls_row[g] - g*S <= o < cls_row[g+1] - (g+1)*S
+  int lo = 0, hi = EW - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (cls_row[mid] - mid * S <= o) lo = mid; else hi = mid - 1;
+  }
+  const int g = lo;
+  const int e = g / W;
+  const int64_t qrow = static_cast<int64_t>(o) + static_cast<int64_t>(g + 1) * S;
+  const float* qn = nf + qrow * C * HW + m;
+  float* dq = dnf + qrow * C * HW + m;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + lane;
+    float acc = 0.f;
+    const float qv = c < C ? qn[static_cast<int64_t>(c) * HW] : 0.f;
+    for (int w = 0; w < W; ++w) {
+      const float gs = grad_score[static_cast<int64_t>(o) * W + w];
+      const int64_t sup_row0 = cls_row[e * W + w];
+      const int32_t* idx = topk_idx + ((static_cast<int64_t>(o) * W + w) * HW + m) * n_k;
+      for (int k = 0; k < n_k; ++k) {
+        const int col = idx[k];
+        const int s = col / HW;
+        const int ms = col - s * HW;
+        const int64_t off = ((sup_row0 + s) * C + c) * HW + ms;
+        if (c < C) {
+          acc = fmaf(gs, nf[off], acc);
+          atomicAdd(dnf + off, gs * qv);
+        }
+      }
+    }
+    if (c < C) dq[static_cast<int64_t>(c) * HW] = acc;
+  }
+}
+
+// x_hat = x / max(|x|, eps):  dx = (d - x_hat <x_hat, d>) / |x|   (|x| >= eps),  d / eps otherwise
+__global__ void __launch_bounds__(128)
+dn4_bwd_normalize_kernel(const float* __restrict__ feat, const float* __restrict__ dnf, int64_t n_desc, int C,
+                         int HW, float* __restrict__ grad_feat) {
+  const int64_t gid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (gid >= n_desc) return;
+  const int64_t row = gid / HW;
+  const int m = static_cast<int>(gid - row * HW);
+  const float* x = feat + row * C * HW + m;
+  const float* d = dnf + row * C * HW + m;
+  float* o = grad_feat + row * C * HW + m;
+  float ss = 0.f, xd = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = x[static_cast<int64_t>(c) * HW];
+    ss = fmaf(v, v, ss);
+    xd = fmaf(v, d[static_cast<int64_t>(c) * HW], xd);
+  }
+  const float nrm = sqrtf(ss);
+  if (nrm >= 1e-12f) {
+    const float inv = 1.0f / nrm;
+    const float k = xd * inv * inv * inv;  // <x_hat, d> / |x| * (1/|x|) applied to x
+    for (int c = 0; c < C; ++c)
+      o[static_cast<int64_t>(c) * HW] = d[static_cast<int64_t>(c) * HW] * inv - x[static_cast<int64_t>(c) * HW] * k;
+  } else {
+    for (int c = 0; c < C; ++c) o[static_cast<int64_t>(c) * HW] = d[static_cast<int64_t>(c) * HW] * 1e12f;
+  }
+}
+
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 }  // namespace
@@ -272,6 +348,44 @@ extern "C" int afs_dn4_fwd(const float* feat, const int32_t* cls_row, int32_t N,
   AFS_LAUNCH_CHECK();
 
   dn4_reduce_kernel<<<(NQ + 127) / 128, 128, 0, stream>>>(rowsum, NQ, W, HW, score, pred);
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
+}
+
+extern "C" size_t afs_dn4_bwd_workspace_bytes(int32_t N, int32_t C, int32_t HW) {
+  if (N <= 0 || C <= 0 || HW <= 0) return 0;
+  return 2 * afs::align256(static_cast<size_t>(N) * C * HW * sizeof(float));
+}
+
+extern "C" int afs_dn4_bwd(const float* feat, const int32_t* cls_row, int32_t N, int32_t E, int32_t W,
+                           int32_t S, int32_t C, int32_t HW, int32_t n_k, const int32_t* topk_idx,
+                           const float* grad_score, float* grad_feat, void* ws, size_t ws_bytes,
+                           afs_stream_t stream_) {
+  using namespace afs;
+  if (feat == nullptr || cls_row == nullptr || topk_idx == nullptr || grad_score == nullptr ||
+      grad_feat == nullptr || E < 0 || W < 1 || W > kMaxWay || S < 1 || C < 1 || HW < 1 ||
+      N < E * W * S || n_k < 1 || n_k > kMaxK)
+    return AFS_ERR_INVALID_ARG;
+  if (N == 0) return AFS_OK;
+  const size_t need = afs_dn4_bwd_workspace_bytes(N, C, HW);
+  if (ws == nullptr || ws_bytes < need) return AFS_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t half = align256(static_cast<size_t>(N) * C * HW * sizeof(float));
+  float* nf = static_cast<float*>(ws);
+  float* dnf = reinterpret_cast<float*>(static_cast<char*>(ws) + half);
+  const int NQ = N - E * W * S;
+  const int64_t n_desc = static_cast<int64_t>(N) * HW;
+  dn4_normalize_kernel<<<static_cast<unsigned>((n_desc + 127) / 128), 128, 0, stream>>>(feat, n_desc, C, HW, nf);
+  AFS_LAUNCH_CHECK();
+  AFS_CUDA_TRY(cudaMemsetAsync(dnf, 0, static_cast<size_t>(N) * C * HW * sizeof(float), stream));
+  if (NQ > 0) {
+    const int64_t warps = static_cast<int64_t>(NQ) * HW;
+    dn4_bwd_scatter_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, stream>>>(
+        nf, cls_row, E * W, W, S, C, HW, n_k, NQ, topk_idx, grad_score, dnf);
+    AFS_LAUNCH_CHECK();
+  }
+  dn4_bwd_normalize_kernel<<<static_cast<unsigned>((n_desc + 127) / 128), 128, 0, stream>>>(feat, dnf, n_desc, C,
+                                                                                           HW, grad_feat);
   AFS_LAUNCH_CHECK();
   return AFS_OK;
 }

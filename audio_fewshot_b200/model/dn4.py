@@ -22,5 +22,15 @@ class DN4(MetricModel):
         return output, acc
 
     def set_forward_loss(self, batch):
-        # The DN4 kernel has no backward yet: training this head is outside the built path.
-        raise NotImplementedError("DN4.set_forward_loss: backward of the DN4 kernel is not built")
+        # dn4.py:122-155.  The reference forwards `repeats` to split_by_episode here and then compares
+        # per-window scores with per-query targets, which only lines up for one window per query.
+        image, repeats, support_size = self._unpack(batch)
+        feat = self.emb_func(image)
+        tab = self._table(feat.shape[0], repeats, support_size)
+        if tab.NQ != tab.nq:
+            raise ValueError("DN4.set_forward_loss needs one window per query (dn4.py:141-154)")
+        output, _, _ = ops.dn4_scores(feat, tab.cls_row, tab.E, tab.W, tab.S, self.n_k)
+        target = tab.q_target_long
+        loss = self.loss_func(output, target)
+        acc = accuracy_percent(output, target)
+        return output, acc, loss

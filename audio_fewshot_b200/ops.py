@@ -173,8 +173,7 @@ def proto_logits(feat, cls_row, E, W, S, mode="euclidean", want_pred=False):
     return (logits, pred) if want_pred else logits
 
 
-def dn4_scores(feat, cls_row, E, W, S, n_k, want_topk=False, want_pred=False):
-    """DN4 head.  feat [N, C, H, W] (or [N, C, HW]) -> score [NQ, W] (+ topk_idx [NQ, W, HW, n_k], pred)."""
+def _dn4_call(feat, cls_row, E, W, S, n_k, want_topk, want_pred):
     _need_cuda(feat, "feat")
     _need_cuda(cls_row, "cls_row", torch.int32)
     feat = feat.contiguous()
@@ -189,11 +188,43 @@ def dn4_scores(feat, cls_row, E, W, S, n_k, want_topk=False, want_pred=False):
     ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=feat.device)
     _lib.check(h.afs_dn4_fwd(_ptr(feat), _ptr(cls_row), N, E, W, S, Cc, HW, int(n_k), _ptr(score), _ptr(topk),
                              _ptr(pred), _ptr(ws), ws_bytes, _stream()), "afs_dn4_fwd")
+    return feat, score, topk, pred
+
+
+class _Dn4Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, cls_row, E, W, S, n_k):
+        feat_c, score, topk, _ = _dn4_call(feat.detach(), cls_row, E, W, S, n_k, True, False)
+        ctx.save_for_backward(feat_c, cls_row, topk)
+        ctx.cfg = (E, W, S, n_k)
+        return score
+
+    @staticmethod
+    def backward(ctx, grad_score):
+        feat, cls_row, topk = ctx.saved_tensors
+        E, W, S, n_k = ctx.cfg
+        N, Cc = feat.shape[0], feat.shape[1]
+        HW = int(np.prod(feat.shape[2:]))
+        grad_score = grad_score.contiguous().float()
+        grad_feat = torch.empty_like(feat)
+        h = _lib.lib()
+        ws_bytes = int(h.afs_dn4_bwd_workspace_bytes(N, Cc, HW))
+        ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=feat.device)
+        _lib.check(h.afs_dn4_bwd(_ptr(feat), _ptr(cls_row), N, E, W, S, Cc, HW, int(n_k), _ptr(topk),
+                                 _ptr(grad_score), _ptr(grad_feat), _ptr(ws), ws_bytes, _stream()), "afs_dn4_bwd")
+        return grad_feat, None, None, None, None, None
+
+
+def dn4_scores(feat, cls_row, E, W, S, n_k, want_topk=False, want_pred=False):
+    """DN4 head.  feat [N, C, H, W] (or [N, C, HW]) -> score [NQ, W] (+ topk_idx [NQ, W, HW, n_k], pred).
+    Differentiable w.r.t. feat when it requires grad (top-k selection held fixed, as torch.topk's backward)."""
+    if torch.is_grad_enabled() and isinstance(feat, torch.Tensor) and feat.requires_grad:
+        return _Dn4Fn.apply(feat, cls_row, E, W, S, n_k), None, None
+    _, score, topk, pred = _dn4_call(feat, cls_row, E, W, S, n_k, want_topk, want_pred)
     return score, topk, pred
 
 
-def bdc_pool(x, log_temp, triu=True):
-    """BDC matrix of x [B, C, H, W] (or [B, C, M]) with log-temperature tensor (1 element)."""
+def _bdc_call(x, log_temp, triu):
     _need_cuda(x, "x")
     _need_cuda(log_temp, "log_temp")
     x = x.contiguous()
@@ -203,7 +234,37 @@ def bdc_pool(x, log_temp, triu=True):
     out = torch.empty((B, out_dim), dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().afs_bdc_fwd(_ptr(x), B, Cc, M, _ptr(log_temp.contiguous()), 1 if triu else 0, _ptr(out),
                                       _stream()), "afs_bdc_fwd")
-    return out
+    return x, out
+
+
+class _BdcFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, log_temp, triu):
+        x_c, out = _bdc_call(x.detach(), log_temp.detach(), triu)
+        ctx.save_for_backward(x_c, log_temp.detach().contiguous())
+        ctx.triu = triu
+        ctx.t_shape = log_temp.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, log_temp = ctx.saved_tensors
+        B, Cc = x.shape[0], x.shape[1]
+        M = int(np.prod(x.shape[2:]))
+        grad_out = grad_out.contiguous().float()
+        grad_x = torch.empty_like(x)
+        grad_t = torch.empty((B,), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().afs_bdc_bwd(_ptr(x), B, Cc, M, _ptr(log_temp), 1 if ctx.triu else 0, _ptr(grad_out),
+                                          _ptr(grad_x), _ptr(grad_t), _stream()), "afs_bdc_bwd")
+        return grad_x, grad_t.sum().reshape(ctx.t_shape), None
+
+
+def bdc_pool(x, log_temp, triu=True):
+    """BDC matrix of x [B, C, H, W] (or [B, C, M]) with log-temperature tensor (1 element).
+    Differentiable w.r.t. x and log_temp when either requires grad."""
+    if torch.is_grad_enabled() and (x.requires_grad or log_temp.requires_grad):
+        return _BdcFn.apply(x, log_temp, triu)
+    return _bdc_call(x, log_temp, triu)[1]
 
 
 VOTE_TIE_RULES = {"smallest": 0, "torch_cuda": 1}

@@ -154,6 +154,14 @@ int afs_dn4_fwd(const float* feat, const int32_t* cls_row, int32_t N, int32_t E,
                 int32_t S, int32_t C, int32_t HW, int32_t n_k, float* score, int32_t* topk_idx,
                 int32_t* pred, void* ws, size_t ws_bytes, afs_stream_t stream);
 
+/* Backward of (2b) for DN4.set_forward_loss (dn4.py:122-155 under autograd): the top-k selection is
+ * held fixed (topk_idx from afs_dn4_fwd), grad_feat [N, C, HW] is fully overwritten.  ws: scratch of
+ * afs_dn4_bwd_workspace_bytes() (normalised descriptors + their gradient).                  */
+size_t afs_dn4_bwd_workspace_bytes(int32_t N, int32_t C, int32_t HW);
+int afs_dn4_bwd(const float* feat, const int32_t* cls_row, int32_t N, int32_t E, int32_t W, int32_t S,
+                int32_t C, int32_t HW, int32_t n_k, const int32_t* topk_idx, const float* grad_score,
+                float* grad_feat, void* ws, size_t ws_bytes, afs_stream_t stream);
+
 /* (2c) BDC matrix: Gram, pairwise squared distance between channels, exp(t)
  * scale, sqrt, double centring, row-major upper triangle.  Replaces
  * BDCovpool + Triuvec (libfewshot_core/model/backbone/utils/bdc_pool.py:69-93).
@@ -161,6 +169,12 @@ int afs_dn4_fwd(const float* feat, const int32_t* cls_row, int32_t N, int32_t E,
  * out [B, C*(C+1)/2] if triu else [B, C*C].  C <= 64 built.                 */
 int afs_bdc_fwd(const float* x, int32_t B, int32_t C, int32_t M, const float* log_temp,
                 int32_t triu, float* out, afs_stream_t stream);
+
+/* Backward of (2c) for DeepBDC.set_forward_loss (deepbdc.py:354-378 under autograd through
+ * BdcPool): grad_out as `out` of afs_bdc_fwd; grad_x [B, C, M]; grad_log_temp [B] = per-clip
+ * contributions to d loss / d temperature (the caller sums them).                           */
+int afs_bdc_bwd(const float* x, int32_t B, int32_t C, int32_t M, const float* log_temp, int32_t triu,
+                const float* grad_out, float* grad_x, float* grad_log_temp, afs_stream_t stream);
 
 /* (3) Window argmax -> per-query majority vote -> accuracy, all on device.
  * Replaces majority_vote + vote_catagorical_acc

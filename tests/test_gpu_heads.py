@@ -249,3 +249,52 @@ def test_vote_large_batch_counts(cuda):
     want = (logits.argmax(1).int() == target).sum().item()
     assert stats[0].item() == want
     assert torch.equal(q_pred, logits.argmax(1).int())
+
+
+# ------------------------------------------------------------------------------------------ backward kernels
+def test_dn4_backward_matches_autograd_of_oracle(cuda):
+    """afs_dn4_bwd against torch autograd through the reference-order DN4 layer (oracle.heads.dn4_layer)."""
+    from audio_fewshot_b200 import ops
+    from audio_fewshot_b200.episode import EpisodeTable
+    E, W, S, Q, C, H, Wd, n_k = 2, 5, 2, 3, 64, 4, 5, 3
+    N = E * W * (S + Q)
+    x = np.abs(np.random.default_rng(41).standard_normal((N, C, H, Wd))).astype(np.float32) + 0.05
+    gs = np.random.default_rng(42).standard_normal((E * W * Q, W)).astype(np.float32)
+    tab = EpisodeTable(E, W, S, Q, np.ones(E * W * Q, dtype=np.int64), cuda)
+
+    xg = torch.from_numpy(x).to(cuda).requires_grad_(True)
+    score, _, _ = ops.dn4_scores(xg, tab.cls_row, E, W, S, n_k)
+    score.backward(torch.from_numpy(gs).to(cuda))
+
+    xc = torch.from_numpy(x).requires_grad_(True)
+    sup, qry, _, _, _ = heads.split_by_episode(xc, W, S, Q)
+    want = heads.dn4_layer(qry, sup, W, S, n_k).reshape(-1, W)
+    want.backward(torch.from_numpy(gs))
+    assert (score.detach().cpu() - want.detach()).abs().max().item() <= 1e-4 * want.abs().max().item()
+    ref = xc.grad
+    assert (xg.grad.cpu() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("B,C,H,Wd,triu", [(3, 64, 16, 19, True), (2, 48, 7, 9, True), (2, 64, 5, 5, False)])
+def test_bdc_backward_matches_autograd_of_oracle(cuda, B, C, H, Wd, triu):
+    from audio_fewshot_b200 import ops
+    rng = np.random.default_rng(B * 100 + C)
+    x = np.maximum(rng.standard_normal((B, C, H, Wd)), 0.0).astype(np.float32)
+    t0 = float(np.log(1.0 / 200.0))
+    out_dim = C * (C + 1) // 2 if triu else C * C
+    go = rng.standard_normal((B, out_dim)).astype(np.float32)
+
+    xg = torch.from_numpy(x).to(cuda).requires_grad_(True)
+    tg = torch.full((1, 1), t0, device=cuda, requires_grad=True)
+    out = ops.bdc_pool(xg, tg, triu=triu)
+    out.backward(torch.from_numpy(go).to(cuda))
+
+    xc = torch.from_numpy(x).double().requires_grad_(True)
+    tc = torch.full((1, 1), t0, dtype=torch.float64, requires_grad=True)
+    full = heads.bdcovpool(xc, tc)
+    want = heads.triuvec(full).reshape(B, -1) if triu else full.reshape(B, -1)
+    want.backward(torch.from_numpy(go).double())
+    assert (out.detach().cpu().double() - want.detach()).abs().max().item() <= 1e-4 * want.abs().max().item()
+    assert (xg.grad.cpu().double() - xc.grad).abs().max().item() <= 2e-3 * xc.grad.abs().max().item()
+    assert tg.grad.shape == (1, 1)
+    assert abs(tg.grad.item() - tc.grad.item()) <= 2e-3 * abs(tc.grad.item()) + 1e-6

@@ -264,3 +264,39 @@ def test_maml_set_forward_on_gpu_matches_cpu_inner_loop(cuda):
             want_acc = (outs["cpu"].argmax(1) == tab.q_target_long).float().mean().item() * 100
             assert acc.item() == pytest.approx(want_acc, abs=1e-3)
     assert (outs["gpu"] - outs["cpu"]).abs().max().item() <= 5e-3 * outs["cpu"].abs().max().item()
+
+
+def test_dn4_and_deepbdc_set_forward_loss_train_end_to_end(cuda):
+    """set_forward_loss of DN4 (Conv64F maps) and DeepBDC (BdcPool) produce finite losses whose backward
+    reaches the backbone through afs_dn4_bwd / afs_bdc_bwd + afs_proto_bwd."""
+    from audio_fewshot_b200 import model as arch
+    from audio_fewshot_b200.backbone import BdcPool
+    E, W, S, Q = 1, 5, 2, 2
+    N = E * W * (S + Q)
+    x = torch.from_numpy((np.random.default_rng(3).standard_normal((N, 1, 128, 157)) * 0.5).astype(np.float32))
+    emb = arch.Conv64F(is_flatten=False, last_pool=False, num_channels=1)
+    dn4 = arch.DN4(n_k=3, way_num=W, shot_num=S, query_num=Q, test_way=W, test_shot=S, test_query=Q, emb_func=emb,
+                   device=cuda).to(cuda)
+    dn4.train()
+    out, acc, loss = dn4([x, torch.zeros(N)])
+    loss.backward()
+    g = emb.layer1[0].weight.grad
+    assert out.shape == (E * W * Q, W) and torch.isfinite(loss) and g is not None and g.abs().sum().item() > 0
+
+    class Trunk(torch.nn.Module):  # small stand-in trunk ending in the real BdcPool
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(1, 64, 5, stride=8)
+            self.bdc_pool = BdcPool(is_vec=True, input_dim=(64, 10, 10), dimension_reduction=None)
+
+        def forward(self, x):
+            return self.bdc_pool(torch.relu(self.conv(x)))
+
+    trunk = Trunk()
+    bdc = arch.DeepBDC(way_num=W, shot_num=S, query_num=Q, test_way=W, test_shot=S, test_query=Q, emb_func=trunk,
+                       device=cuda).to(cuda)
+    bdc.train()
+    out, acc, loss = bdc([x, torch.zeros(N)])
+    loss.backward()
+    assert torch.isfinite(loss) and trunk.conv.weight.grad.abs().sum().item() > 0
+    assert trunk.bdc_pool.temperature.grad is not None and torch.isfinite(trunk.bdc_pool.temperature.grad).all()
