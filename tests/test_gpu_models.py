@@ -300,3 +300,25 @@ def test_dn4_and_deepbdc_set_forward_loss_train_end_to_end(cuda):
     loss.backward()
     assert torch.isfinite(loss) and trunk.conv.weight.grad.abs().sum().item() > 0
     assert trunk.bdc_pool.temperature.grad is not None and torch.isfinite(trunk.bdc_pool.temperature.grad).all()
+
+
+def test_config_to_loader_to_set_forward_on_gpu(cuda):
+    """The reference's evaluation loop shape (test.py:362-393): config -> model by name -> loaders -> model(batch)."""
+    import os
+    from conftest import GOLDEN
+    from audio_fewshot_b200.config import Config, build_model
+    from audio_fewshot_b200.data import get_dataloader
+    cfg = Config(os.path.join(GOLDEN, "config", "proto_fixture.yaml"),
+                 {"test_episode": 4, "episode_size": 2, "max_windows": 3, "test_query": 2}).get_config_dict()
+    model = build_model(cfg, cuda, mode="test").eval()
+    loaders = get_dataloader(cfg, "test", model.model_type, False, cfg["modality"])
+    model.reverse_setting_info()
+    accs = []
+    with torch.no_grad():
+        for batch in zip(*loaders):
+            flat = [elem for each in batch for elem in each]
+            output, acc = model(flat)
+            assert output.shape == (int(flat[2].sum()), cfg["test_way"])
+            accs.append(acc)
+    model.reverse_setting_info()
+    assert len(accs) == 2 and all(0.0 <= a.item() <= 100.0 for a in accs)
