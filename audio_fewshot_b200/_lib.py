@@ -35,6 +35,18 @@ class AugCfg(C.Structure):
     ]
 
 
+class SpecAugCfg(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32),
+        ("n_rect", C.c_int32),
+        ("rect", (C.c_int32 * 4) * 8),
+        ("fill", C.c_float),
+        ("p0", C.c_float),
+        ("p1", C.c_float),
+        ("i0", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/afs_b200.h declares
 SIGNATURES = {
     "afs_abi_version": (C.c_int, []),
@@ -68,6 +80,8 @@ SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "afs_bdc_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                               C.c_void_p, C.c_void_p]),
+    "afs_spec_augment": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                                   C.POINTER(SpecAugCfg), C.c_void_p, C.c_void_p, C.c_void_p]),
     "afs_vote_acc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "afs_energy_score": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,

@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Per-kernel roofline table at the BASELINE configs: each head / front-end kernel timed
+alone with CUDA events, inputs larger than L2 (or L2 flushed), algorithmic bytes / duration against the
+measured HBM peak.  Prints one JSON line per kernel; `python bench_kernels.py > profiles/rNN_kernels.jsonl`.
+bench.py is the contract benchmark; this is the supporting evidence for DESIGN.md section 3."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from audio_fewshot_b200 import ops  # noqa: E402
+from audio_fewshot_b200.episode import EpisodeTable  # noqa: E402
+from audio_fewshot_b200.frontend import LogMelFrontEnd  # noqa: E402
+
+
+def peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def timeit(fn, iters=20, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()  # > L2: evicts the previous iteration's lines
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        times.append(a.elapsed_time(b))
+    return float(np.median(times)), float(np.min(times))
+
+
+def report(name, unit, units, bytes_per_unit, ms, ms_min, flops_per_unit=None, note=""):
+    peak = peak_gbs()
+    gbs = units * bytes_per_unit / (ms * 1e-3) / 1e9
+    line = {"kernel": name, "unit": unit, "units_per_launch": units, "algorithmic_bytes_per_unit": bytes_per_unit,
+            "ms_median": ms, "ms_min": ms_min, "achieved_gbs": gbs, "hbm_peak_gbs": peak, "frac_of_measured_hbm": gbs / peak,
+            "units_per_s": units / (ms * 1e-3), "note": note}
+    if flops_per_unit:
+        line["tflops"] = units * flops_per_unit / (ms * 1e-3) / 1e12
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    flush = torch.empty(160 * 2 ** 20 // 4, dtype=torch.float32, device=dev)  # 160 MB > 126 MB L2
+
+    # ---- fused log-mel, shapes S5 and S1
+    for tag, L, hop, B in (("S5 L=80000 hop=512", 80000, 512, 800), ("S1 L=16000 hop=102", 16000, 102, 800)):
+        fr = LogMelFrontEnd(hop_length=hop, n_mels=128, mean=-15.0, std=26.0).to(dev).eval()
+        wav = torch.randn(B, L, device=dev) * 0.1
+        T = 1 + L // hop
+        out = torch.empty(B, 1, 128, T, device=dev)
+        ms, mn = timeit(lambda: fr(wav, out=out), flush=flush)
+        report("logmel_kernel<false> " + tag, "clip", B, 4 * L + 4 * 128 * T, ms, mn, note="T=%d" % T)
+    fr = LogMelFrontEnd(hop_length=512, n_mels=128, mean=-15.0, std=26.0, seed=7,
+                        aug={"gain_db": (-6.0, 6.0), "max_shift": 1600, "noise_std": (0.0, 0.02)}).to(dev).train()
+    wav = torch.randn(800, 80000, device=dev) * 0.1
+    out = torch.empty(800, 1, 128, 157, device=dev)
+    ms, mn = timeit(lambda: fr(wav, out=out), flush=flush)
+    report("logmel_kernel<true> S5 + Philox gain/shift/noise", "clip", 800, 4 * 80000 + 4 * 128 * 157, ms, mn)
+
+    # ---- conv1 stem
+    img = torch.randn(800, 1, 128, 157, device=dev)
+    w = np.random.default_rng(0).standard_normal((64, 9)).astype(np.float32)
+    b = np.zeros(64, np.float32)
+    ms, mn = timeit(lambda: ops.conv1_bn_act_pool3(img, w, b, 0.0), flush=flush)
+    report("conv1_bn_act_pool3_kernel", "clip", 800, 4 * 128 * 157 + 4 * 64 * 42 * 52, ms, mn,
+           flops_per_unit=2 * 64 * 42 * 52 * 81, note="fp32 SIMT; flops count the 9 conv positions per pooled pixel")
+
+    # ---- prototype head: C1 (D=1600, 5w5s15q), C2 (D=12800, 5w1s15q), C4 vectors (D=2080, 5w5s10q)
+    for tag, E, W, S, Q, D, mode in (("C1 D=1600 5w5s15q", 256, 5, 5, 15, 1600, "euclidean"),
+                                     ("C2 D=12800 5w1s15q", 64, 5, 1, 15, 12800, "euclidean"),
+                                     ("C4 D=2080 5w5s10q", 256, 5, 5, 10, 2080, "euclidean"),
+                                     ("C1 cosine", 256, 5, 5, 15, 1600, "cos_sim")):
+        N = E * W * (S + Q)
+        feat = torch.randn(N, D, device=dev)
+        tab = EpisodeTable(E, W, S, Q, np.ones(E * W * Q, dtype=np.int64), dev)
+        ms, mn = timeit(lambda: ops.proto_logits(feat, tab.cls_row, E, W, S, mode), flush=flush)
+        report("proto_fwd_kernel " + tag, "episode", E, 4 * W * (S + Q) * D + 4 * W * Q * W, ms, mn,
+               flops_per_unit=3 * W * Q * W * D + W * S * D)
+
+    # ---- DN4: C3 Conv64F maps [64,4,5], 5w5s15q n_k=3; ResNet-12 maps [640,8,9] 5w5s10q
+    for tag, E, W, S, Q, C, H, Wd in (("C3 map 64x4x5 5w5s15q", 128, 5, 5, 15, 64, 4, 5),
+                                      ("ResNet-12 map 640x8x9 5w5s10q", 4, 5, 5, 10, 640, 8, 9)):
+        N = E * W * (S + Q)
+        feat = torch.rand(N, C, H, Wd, device=dev)
+        tab = EpisodeTable(E, W, S, Q, np.ones(E * W * Q, dtype=np.int64), dev)
+        ms, mn = timeit(lambda: ops.dn4_scores(feat, tab.cls_row, E, W, S, 3), flush=flush)
+        HW = H * Wd
+        report("dn4 (normalize+main+reduce) " + tag, "episode", E, 4 * W * (S + Q) * C * HW + 4 * W * Q * W, ms, mn,
+               flops_per_unit=2 * (W * Q * HW) * (W * S * HW) * C)
+
+    # ---- BDC matrix: C4 map [64,16,19]
+    x = torch.relu(torch.randn(2000, 64, 16, 19, device=dev))
+    t = torch.full((1, 1), float(np.log(1 / 200.0)), device=dev)
+    ms, mn = timeit(lambda: ops.bdc_pool(x, t), flush=flush)
+    report("bdc_kernel C4 map 64x16x19", "clip", 2000, 4 * 64 * 304 + 4 * 2080, ms, mn, flops_per_unit=2 * 64 * 64 * 304)
+
+    # ---- vote + accuracy, 5-way, one window per query
+    nq = 75 * 4096
+    logits = torch.randn(nq, 5, device=dev)
+    q_start = torch.arange(nq + 1, dtype=torch.int32, device=dev)
+    target = torch.randint(0, 5, (nq,), dtype=torch.int32, device=dev)
+    ms, mn = timeit(lambda: ops.vote_acc(logits, q_start, target), flush=flush)
+    report("vote_kernel 5-way", "episode", 4096, 4 * 75 * 5 + 4 * 75 * 3, ms, mn, note="logits + q_start + target + pred")
+
+
+if __name__ == "__main__":
+    main()

@@ -199,6 +199,43 @@ int afs_vote_acc(const float* logits, int32_t W, const int32_t* q_start, int32_t
 int afs_energy_score(const float* logits, int32_t W, const int32_t* q_start, int32_t nq,
                      float* energy, afs_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * (4) Spectrogram-domain augmentation, fused with its de-/re-normalisation.
+ * Replaces augment_spectrogram (libfewshot_core/audio_augmentations.py:531-604) and the eight
+ * augmentations it dispatches to (:56-528) between denormalize_spectrogram (:16-33) and
+ * normalize_spectrogram (:36-53).  in/out: `planes` contiguous [H, W] fp32 planes (every
+ * (batch, channel) pair of the reference's [B,C,H,W] / [C,H,W] / [H,W] inputs); mean/std: the
+ * scalar pair of Auxiliary/*_Mean_Std.npy.  The random parameters are drawn by the host (the
+ * reference draws them with Python's `random`) and arrive in `cfg`:
+ *   CUTOUT                 n_rect rectangles rect[k] = {top, left, height, width}, value `fill`
+ *   LINEAR_FILTER          filter_curve [H] (device): per-frequency gain
+ *   NOISE_SUPPRESSION      p0 = noise_percentile/100, p1 = suppression_strength
+ *   NOISE_MATCHING         p0 = target_noise_level, i0 = smoothing_window
+ *   BACKGROUND_SUBTRACTION p0 = percentile/100 (quantile along time, per frequency row)
+ *   CONTRAST               p0 = contrast_factor, p1 = clip_percentile/100 (>= 1: no clipping)
+ *   FOREGROUND_NORM        p0 = 1 - top_k_percent/100
+ *   WIENER                 p0 = noise_floor_percentile/100, p1 = gain_factor
+ * Quantiles are torch.quantile's (linear interpolation, fp32 rank arithmetic), found exactly. */
+#define AFS_AUG_CUTOUT 0
+#define AFS_AUG_LINEAR_FILTER 1
+#define AFS_AUG_NOISE_SUPPRESSION 2
+#define AFS_AUG_NOISE_MATCHING 3
+#define AFS_AUG_BACKGROUND_SUBTRACTION 4
+#define AFS_AUG_CONTRAST 5
+#define AFS_AUG_FOREGROUND_NORM 6
+#define AFS_AUG_WIENER 7
+typedef struct afs_specaug_cfg {
+  int32_t type;
+  int32_t n_rect;
+  int32_t rect[8][4];
+  float fill;
+  float p0, p1;
+  int32_t i0;
+} afs_specaug_cfg;
+int afs_spec_augment(const float* in, int32_t planes, int32_t H, int32_t W, float mean, float std,
+                     const afs_specaug_cfg* cfg, const float* filter_curve, float* out,
+                     afs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,6 +128,28 @@ def perturb_bn_(net):
     return net
 
 
+# ------------------------------------------------------------------ spectrogram-domain augmentations
+AUG_MEAN, AUG_STD = -15.114207, 26.22313  # Auxiliary/Clean_Mean_Std.npy
+AUG_FIXED = {  # explicit kwargs: no random draw except the ones inside cutout / linear_filter
+    "cutout": dict(num_cutouts=2, cutout_size_ratio=(0.1, 0.3), fill_value=0.0),
+    "linear_filter": dict(num_points=4, filter_strength=0.5),
+    "noise_suppression": dict(noise_percentile=20, suppression_strength=0.5),
+    # smoothing_window=1: with any window > 1 the reference itself raises (F.pad(reflect) on a 4-D tensor with a
+    # 2-tuple, audio_augmentations.py:432) -- recorded in the golden as "raises", see DESIGN.md
+    "noise_matching": dict(target_noise_level=None, smoothing_window=1),
+    "background_subtraction": dict(percentile=10),
+    "contrast_enhancement": dict(contrast_factor=1.5, clip_percentile=95),
+    "foreground_norm": dict(top_k_percent=20),
+    "wiener_filter": dict(noise_floor_percentile=15, gain_factor=2.0),
+}
+AUG_RANDOM_SEEDS = tuple(range(100, 114))  # augmentation_type='random': the type and its parameters are drawn
+
+
+def aug_input(shape=(2, 1, 32, 41), seed=81):
+    """A NORMALISED spectrogram batch (what augment_spectrogram receives)."""
+    return _rng(seed).standard_normal(shape).astype(np.float32)
+
+
 # ------------------------------------------------------------------ MAML (config C5, shrunk)
 MAML_CASE = dict(seed=71, torch_seed=5, E=2, W=5, S=2, Q=3, lr=0.01, train_iter=2, test_iter=3, feat_dim=1600,
                  backbone=dict(is_flatten=True, is_feature=False, leaky_relu=False, negative_slope=0.2,

@@ -52,9 +52,43 @@ def make_maml():
     print("maml.npz", os.path.getsize(os.path.join(OUT, "maml.npz")), "loss", out["loss"], "acc", out["acc"])
 
 
+def make_augment():
+    """augment_spectrogram of the real reference (audio_augmentations.py:531-604) on seeded planes."""
+    import random
+    _, _, aug = import_reference()
+    out = {}
+    x = torch.from_numpy(cases.aug_input())
+    for t, kw in cases.AUG_FIXED.items():
+        random.seed(7)
+        out["fixed/" + t] = aug.augment_spectrogram(x, cases.AUG_MEAN, cases.AUG_STD, augmentation_type=t, **kw).numpy()
+    raised = []
+    for sd in cases.AUG_RANDOM_SEEDS:
+        random.seed(sd)
+        try:
+            out["random/%d" % sd] = aug.augment_spectrogram(x, cases.AUG_MEAN, cases.AUG_STD).numpy()
+        except NotImplementedError:  # 'noise_matching' drawn: the reference's reflect pad fails (see cases.py)
+            raised.append(sd)
+    out["random/raised"] = np.asarray(raised, dtype=np.int64)
+    random.seed(7)
+    try:
+        aug.augment_spectrogram(x, cases.AUG_MEAN, cases.AUG_STD, augmentation_type="noise_matching", smoothing_window=5)
+        out["noise_matching_window5_raises"] = np.asarray(0)
+    except NotImplementedError:
+        out["noise_matching_window5_raises"] = np.asarray(1)
+    big = torch.from_numpy(cases.aug_input((1, 1, 128, 157), seed=82))
+    for t in ("noise_suppression", "background_subtraction"):
+        random.seed(9)
+        out["full/" + t] = aug.augment_spectrogram(big, cases.AUG_MEAN, cases.AUG_STD, augmentation_type=t,
+                                                   **cases.AUG_FIXED[t]).numpy()
+    np.savez_compressed(os.path.join(OUT, "augment.npz"), **out)
+    print("augment.npz", os.path.getsize(os.path.join(OUT, "augment.npz")))
+
+
 def main():
     if "--maml" in sys.argv:
         return make_maml()
+    if "--augment" in sys.argv:
+        return make_augment()
     arch, utils, _ = import_reference()
     from libfewshot_core.model.metric.proto_net import ProtoLayer
     from libfewshot_core.model.metric.dn4 import DN4Layer
@@ -139,6 +173,7 @@ def main():
         out[name + "/keys"] = np.asarray(sorted(net.state_dict().keys()))
     np.savez_compressed(os.path.join(OUT, "backbones.npz"), **out)
     make_maml()
+    make_augment()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

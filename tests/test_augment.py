@@ -1,0 +1,92 @@
+"""Spectrogram-domain augmentations: the oracle restatement against outputs of the real reference
+(tests/golden/augment.npz), and -- on the GPU -- the fused kernel against both."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import augment as oaug
+from oracle import cases
+
+TOL = dict(rtol=2e-5, atol=2e-5)
+
+
+def test_oracle_matches_reference_golden_fixed_parameters(golden):
+    g = golden("augment.npz")
+    x = torch.from_numpy(cases.aug_input())
+    for t, kw in cases.AUG_FIXED.items():
+        random.seed(7)
+        got = oaug.augment_spectrogram(x, cases.AUG_MEAN, cases.AUG_STD, augmentation_type=t, **kw).numpy()
+        np.testing.assert_allclose(got, g["fixed/" + t], err_msg=t, **TOL)
+
+
+def test_oracle_draws_parameters_in_reference_order(golden):
+    g = golden("augment.npz")
+    x = torch.from_numpy(cases.aug_input())
+    raised = set(int(v) for v in g["random/raised"])
+    assert int(g["noise_matching_window5_raises"]) == 1  # the reference cannot run this branch at all
+    kinds = set()
+    for sd in cases.AUG_RANDOM_SEEDS:
+        random.seed(sd)
+        kinds.add(random.choice(oaug.CHOICES))
+        random.seed(sd)
+        if sd in raised:
+            assert random.choice(oaug.CHOICES) == "noise_matching"
+            continue
+        got = oaug.augment_spectrogram(x, cases.AUG_MEAN, cases.AUG_STD).numpy()
+        np.testing.assert_allclose(got, g["random/%d" % sd], err_msg=str(sd), **TOL)
+    assert len(kinds) >= 5
+
+
+@pytest.mark.gpu
+def test_kernel_matches_reference_golden(cuda, golden):
+    from audio_fewshot_b200 import augment as aug
+    g = golden("augment.npz")
+    x = torch.from_numpy(cases.aug_input()).to(cuda)
+    for t, kw in cases.AUG_FIXED.items():
+        random.seed(7)
+        got = aug.augment_spectrogram(x, cases.AUG_MEAN, cases.AUG_STD, augmentation_type=t, **kw).cpu().numpy()
+        np.testing.assert_allclose(got, g["fixed/" + t], err_msg=t, **TOL)
+    raised = set(int(v) for v in g["random/raised"])
+    for sd in cases.AUG_RANDOM_SEEDS:
+        random.seed(sd)
+        got = aug.augment_spectrogram(x, cases.AUG_MEAN, cases.AUG_STD).cpu().numpy()
+        if sd not in raised:  # same type and same parameters drawn as the reference
+            np.testing.assert_allclose(got, g["random/%d" % sd], err_msg=str(sd), **TOL)
+    big = torch.from_numpy(cases.aug_input((1, 1, 128, 157), seed=82)).to(cuda)
+    for t in ("noise_suppression", "background_subtraction"):
+        random.seed(9)
+        got = aug.augment_spectrogram(big, cases.AUG_MEAN, cases.AUG_STD, augmentation_type=t,
+                                      **cases.AUG_FIXED[t]).cpu().numpy()
+        np.testing.assert_allclose(got, g["full/" + t], err_msg=t, **TOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(3, 2, 128, 157), (5, 64, 31), (128, 157), (1, 1, 7, 300)])
+def test_kernel_matches_oracle_on_other_shapes(cuda, shape):
+    """Every type, default (drawn) parameters, 2-/3-/4-D inputs incl. the smoothed noise_matching branch the
+    reference cannot execute (restated as intended: reflect pad of the last axis + box filter)."""
+    from audio_fewshot_b200 import augment as aug
+    x = torch.from_numpy(np.random.default_rng(len(shape)).standard_normal(shape).astype(np.float32))
+    for i, t in enumerate(oaug.CHOICES):
+        random.seed(50 + i)
+        want = oaug.augment_spectrogram(x, cases.AUG_MEAN, cases.AUG_STD, augmentation_type=t).numpy()
+        random.seed(50 + i)
+        got = aug.augment_spectrogram(x.to(cuda), cases.AUG_MEAN, cases.AUG_STD, augmentation_type=t).cpu().numpy()
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, err_msg=t, rtol=5e-5, atol=5e-5)
+
+
+@pytest.mark.gpu
+def test_batch_augment_and_errors(cuda):
+    from audio_fewshot_b200 import augment as aug
+    from audio_fewshot_b200._lib import AfsError
+    x = torch.randn(2, 1, 16, 20, device=cuda)
+    random.seed(3)
+    out = aug.batch_augment_spectrogram(x, 0.0, 1.0, num_augmentations=3, augmentation_type="linear_filter")
+    assert out.shape == (6, 1, 16, 20)
+    with pytest.raises(AfsError):
+        aug.augment_spectrogram(x.cpu(), 0.0, 1.0, augmentation_type="cutout")
+    with pytest.raises(ValueError):
+        aug.augment_spectrogram(x, 0.0, 1.0, augmentation_type="nope")
