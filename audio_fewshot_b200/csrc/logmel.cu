@@ -47,8 +47,9 @@ constexpr int kFramesPerCta = 32;
 constexpr int kFramesPerGroup = kFramesPerCta / kGroups;
 constexpr int kMaxNnz = 2048;
 constexpr int kTileStride = kFramesPerCta + 1;
+constexpr int kGroupFloats = kBufA + kBufB + kMelBatch * kPStride;
 
-constexpr size_t kSmemFloats = kMaxNnz + 3 * kMaxMels + kNfft + kGroups * (kBufA + kBufB) +
+constexpr size_t kSmemFloats = kMaxNnz + 3 * kMaxMels + kNfft + 2 * kTwbdEntries + kGroups * kGroupFloats +
                                kMaxMels * kTileStride;
 constexpr size_t kSmemBytes = kSmemFloats * sizeof(float);
 
@@ -101,14 +102,45 @@ __device__ __forceinline__ float aug_sample(const float* __restrict__ x, int64_t
   return v;
 }
 
+// Raw (augmented, reflect-padded, NOT yet windowed) samples 2n, 2n+1 for n = t + 64 r of the frame that
+// starts at sample s0.  Issued one frame ahead of their use so the global-load latency hides behind the
+// previous frame's FFT.
+template <bool AUG>
+__device__ __forceinline__ void load_frame(const float* __restrict__ x, int64_t s0, int64_t L, int t,
+                                           const AugState& aug, float2 (&raw)[8]) {
+  const bool interior = (s0 >= 0) && (s0 + kNfft <= L);
+  if (!AUG && interior && ((reinterpret_cast<uintptr_t>(x + s0) & 7) == 0)) {
+    const float2* x2 = reinterpret_cast<const float2*>(x + s0);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) raw[r] = __ldg(x2 + t + 64 * r);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      int64_t i0 = s0 + 2 * (t + 64 * r), i1 = i0 + 1;
+      if (!interior) {
+        i0 = reflect_index(i0, L);
+        i1 = reflect_index(i1, L);
+      }
+      if (AUG) {
+        raw[r].x = aug_sample(x, i0, L, aug);
+        raw[r].y = aug_sample(x, i1, L, aug);
+      } else {
+        raw[r].x = __ldg(x + i0);
+        raw[r].y = __ldg(x + i1);
+      }
+    }
+  }
+}
+
 template <bool AUG>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
   float* s_w = smem;
   int* s_band = reinterpret_cast<int*>(s_w + kMaxNnz);
   float* s_win = reinterpret_cast<float*>(s_band + 3 * kMaxMels);
-  float* s_grp = s_win + kNfft;
-  float* s_tile = s_grp + kGroups * (kBufA + kBufB);
+  float2* s_twbd = reinterpret_cast<float2*>(s_win + kNfft);
+  float* s_grp = reinterpret_cast<float*>(s_twbd + kTwbdEntries);
+  float* s_tile = s_grp + kGroups * kGroupFloats;
 
   const int tid = threadIdx.x;
   const int grp = tid >> 6;
@@ -119,19 +151,22 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
   for (int i = tid; i < p.nnz; i += kThreads) s_w[i] = p.weights[i];
   for (int i = tid; i < 3 * kMaxMels; i += kThreads) s_band[i] = p.band[i];
   for (int i = tid; i < kNfft; i += kThreads) s_win[i] = p.window[i];
+  for (int i = tid; i < kTwbdEntries; i += kThreads) s_twbd[i] = twbd_entry(i, p.tw1024);
 
   ThreadTw tw;
   load_thread_tw(tw, t, p.tw1024);
 
   // this thread's (up to) two mel filters: t and, mirrored for balance, n_mels-1-t
   int mel_id[2];
-  float mel_mean[2], mel_std[2];
+  float mel_scale[2], mel_shift[2];
   mel_id[0] = (t < p.n_mels) ? t : -1;
   mel_id[1] = (p.n_mels - 1 - t >= kGroup) ? p.n_mels - 1 - t : -1;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    mel_mean[i] = mel_id[i] >= 0 ? p.mean[mel_id[i]] : 0.f;
-    mel_std[i] = mel_id[i] >= 0 ? p.stdv[mel_id[i]] : 1.f;
+    const float sd = mel_id[i] >= 0 ? p.stdv[mel_id[i]] : 1.f;
+    const float mu = mel_id[i] >= 0 ? p.mean[mel_id[i]] : 0.f;
+    mel_scale[i] = p.log_mult * 0.30102999566398120f / sd;
+    mel_shift[i] = -mu / sd;
   }
 
   const float* __restrict__ x = p.wav + static_cast<int64_t>(clip) * p.L;
@@ -154,10 +189,10 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
     aug.k = draw - p.max_shift;
     aug.sigma = __fadd_rn(p.noise_lo, __fmul_rn(__fsub_rn(p.noise_hi, p.noise_lo), u01(r.z)));
   }
-  __syncthreads();
 
-  float* bufA = s_grp + grp * (kBufA + kBufB);
+  float* bufA = s_grp + grp * kGroupFloats;
   float* bufB = bufA + kBufA;
+  float* bufP = bufB + kBufB;  // kMelBatch power spectra
 
   const int t0 = chunk * kFramesPerCta;
   const int nfr = min(kFramesPerCta, p.T - t0);
@@ -165,60 +200,41 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
   const int f_end = min(f_begin + kFramesPerGroup, nfr);
   const float2* s_win2 = reinterpret_cast<const float2*>(s_win);
 
+  float2 raw[8];
+  if (f_begin < f_end) load_frame<AUG>(x, static_cast<int64_t>(t0 + f_begin) * p.hop - p.pad, p.L, t, aug, raw);
+  __syncthreads();
+
   for (int fl = f_begin; fl < f_end; ++fl) {
-    const int64_t s0 = static_cast<int64_t>(t0 + fl) * p.hop - p.pad;
     cpx z[8];
-    const bool interior = (s0 >= 0) && (s0 + kNfft <= p.L);
-    if (!AUG && interior && ((reinterpret_cast<uintptr_t>(x + s0) & 7) == 0)) {
-      const float2* x2 = reinterpret_cast<const float2*>(x + s0);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int n = t + 64 * r;
-        const float2 v = __ldg(x2 + n);
-        const float2 w = s_win2[n];
-        z[r].re = v.x * w.x;
-        z[r].im = v.y * w.y;
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int n = t + 64 * r;
-        int64_t i0 = s0 + 2 * n, i1 = i0 + 1;
-        if (!interior) {
-          i0 = reflect_index(i0, p.L);
-          i1 = reflect_index(i1, p.L);
-        }
-        float v0, v1;
-        if (AUG) {
-          v0 = aug_sample(x, i0, p.L, aug);
-          v1 = aug_sample(x, i1, p.L, aug);
-        } else {
-          v0 = __ldg(x + i0);
-          v1 = __ldg(x + i1);
-        }
-        const float2 w = s_win2[n];
-        z[r].re = v0 * w.x;
-        z[r].im = v1 * w.y;
-      }
+    for (int r = 0; r < 8; ++r) {
+      const float2 w = s_win2[t + 64 * r];
+      z[r].re = raw[r].x * w.x;
+      z[r].im = raw[r].y * w.y;
     }
+    if (fl + 1 < f_end)  // prefetch the next frame while this one is transformed
+      load_frame<AUG>(x, static_cast<int64_t>(t0 + fl + 1) * p.hop - p.pad, p.L, t, aug, raw);
+    const int slot = (fl - f_begin) % kMelBatch;
     phase_a(t, z, tw, bufA);
     group_bar(grp);
-    phase_b(t, tw, bufA, bufB);
+    phase_b(t, s_twbd, bufA, bufB);
     group_bar(grp);
     phase_c(t, bufB, bufA);
     group_bar(grp);
-    phase_d(t, tw, bufA, bufB);
+    phase_d(t, s_twbd, bufA, bufP + slot * kPStride);
     group_bar(grp);
+    if (slot == kMelBatch - 1 || fl + 1 == f_end) {
+      const int fl0 = fl - slot;  // first frame of this batch
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int m = mel_id[i];
-      if (m >= 0) {
-        const int lo = s_band[m];
-        const int len = s_band[kMaxMels + m];
-        const int off = s_band[2 * kMaxMels + m];
-        const float e = mel_dot(bufB, s_w + off, lo, len);
-        const float v = p.log_mult * log10f(e + p.log_eps);
-        s_tile[m * kTileStride + fl] = (v - mel_mean[i]) / mel_std[i];
+      for (int i = 0; i < 2; ++i) {
+        const int m = mel_id[i];
+        if (m >= 0) {
+          float acc[kMelBatch];
+          mel_dot_batch(bufP, s_w + s_band[2 * kMaxMels + m], s_band[m], s_band[kMaxMels + m], acc);
+#pragma unroll
+          for (int f = 0; f < kMelBatch; ++f)
+            if (f <= slot) s_tile[m * kTileStride + fl0 + f] = norm_db(acc[f], p.log_eps, mel_scale[i], mel_shift[i]);
+        }
       }
     }
   }

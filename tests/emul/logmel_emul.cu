@@ -27,7 +27,9 @@ extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, con
   }
   const int pad = center ? kNfft / 2 : 0;
   const int T = center ? static_cast<int>(1 + L / hop) : static_cast<int>(1 + (L - kNfft) / hop);
-  std::vector<float> bufA(kBufA), bufB(kBufB);
+  std::vector<float> bufA(kBufA), bufB(kBufB), bufP(kMelBatch * kPStride, 0.f);
+  std::vector<float2> twbd(kTwbdEntries);
+  for (int i = 0; i < kTwbdEntries; ++i) twbd[i] = twbd_entry(i, tw.data());
   std::vector<ThreadTw> tws(kGroup);
   for (int t = 0; t < kGroup; ++t) load_thread_tw(tws[t], t, tw.data());
   for (int f = 0; f < T; ++f) {
@@ -44,20 +46,26 @@ extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, con
       }
       phase_a(t, z, tws[t], bufA.data());
     }
-    for (int t = 0; t < kGroup; ++t) phase_b(t, tws[t], bufA.data(), bufB.data());
+    for (int t = 0; t < kGroup; ++t) phase_b(t, twbd.data(), bufA.data(), bufB.data());
     for (int t = 0; t < kGroup; ++t) phase_c(t, bufB.data(), bufA.data());
-    for (int t = 0; t < kGroup; ++t) phase_d(t, tws[t], bufA.data(), bufB.data());
-    if (power_out) for (int k = 0; k < kBins; ++k) power_out[static_cast<size_t>(f) * kBins + k] = bufB[k];
-    for (int t = 0; t < kGroup; ++t) {
+    const int slot = f % kMelBatch;
+    float* power = bufP.data() + slot * kPStride;
+    for (int t = 0; t < kGroup; ++t) phase_d(t, twbd.data(), bufA.data(), power);
+    if (power_out) for (int k = 0; k < kBins; ++k) power_out[static_cast<size_t>(f) * kBins + k] = power[k];
+    if (slot != kMelBatch - 1 && f + 1 != T) continue;
+    for (int t = 0; t < kGroup; ++t) {  // batched mel projection, as the kernel's epilogue
       int mel_id[2];
       mel_id[0] = (t < n_mels) ? t : -1;
       mel_id[1] = (n_mels - 1 - t >= kGroup) ? n_mels - 1 - t : -1;
       for (int i = 0; i < 2; ++i) {
         const int m = mel_id[i];
         if (m < 0) continue;
-        const float e = mel_dot(bufB.data(), weights.data() + band[2 * kMaxMels + m], band[m], band[kMaxMels + m]);
-        const float v = log_mult * log10f(e + log_eps);
-        out[static_cast<size_t>(m) * T + f] = (v - mean[m]) / stdv[m];
+        float acc[kMelBatch];
+        mel_dot_batch(bufP.data(), weights.data() + band[2 * kMaxMels + m], band[m], band[kMaxMels + m], acc);
+        const float scale = log_mult * 0.30102999566398120f / stdv[m];
+        const float shift = -mean[m] / stdv[m];
+        for (int b = 0; b <= slot; ++b)
+          out[static_cast<size_t>(m) * T + (f - slot) + b] = norm_db(acc[b], log_eps, scale, shift);
       }
     }
   }

@@ -1,0 +1,13 @@
+"""Launch the fused log-mel kernel a few times at the bench shape (for ncu captures)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from audio_fewshot_b200.frontend import LogMelFrontEnd
+dev = torch.device("cuda", 0)
+fr = LogMelFrontEnd(hop_length=512, n_mels=128, mean=-15.0, std=26.0).to(dev).eval()
+wav = torch.randn(800, 80000, device=dev) * 0.1
+out = torch.empty(800, 1, 128, 157, device=dev)
+for _ in range(5):
+    fr(wav, out=out)
+torch.cuda.synchronize()
+print("ok", float(out.mean()))
