@@ -104,13 +104,13 @@ class Conv64F(nn.Module):
     def _forward_inference(self, x):
         c = self._folded()
         h = ops.conv1_bn_act_pool3(x, c["w1"], c["b1"], c["slope"])  # [N,64,H/3,W/3] channels_last
-        h = F.max_pool2d(self._conv_act(h, c["w2"], c["b2"], c["slope"]), 3, 3)
+        h = ops.maxpool3_channels_last(self._conv_act(h, c["w2"], c["b2"], c["slope"]))
         h = self._conv_act(h, c["w3"], c["b3"], c["slope"])
         if self.maxpool_last2:
-            h = F.max_pool2d(h, 3, 3)
+            h = ops.maxpool3_channels_last(h)
         h = self._conv_act(h, c["w4"], c["b4"], c["slope"])
         if self.last_pool:
-            h = F.max_pool2d(h, 3, 3)
+            h = ops.maxpool3_channels_last(h)
         if self.is_flatten:
             h = h.contiguous().view(h.size(0), -1)  # NCHW flatten order, as out4.view(N, -1)
             h = torch.addmm(c["bl"], h, c["wl"].t())

@@ -119,6 +119,20 @@ def conv1_bn_act_pool3(x, w_folded, shift, negative_slope=0.0):
     return out
 
 
+def maxpool3_channels_last(x):
+    """MaxPool2d(3, 3) of a channels_last [N, C, H, W] CUDA tensor -> channels_last [N, C, H//3, W//3]."""
+    _need_cuda(x, "x")
+    if x.dim() != 4 or x.shape[1] % 4 != 0:
+        raise ValueError("x must be [N, C, H, W] with C % 4 == 0")
+    x = x.contiguous(memory_format=torch.channels_last)
+    N, Cc, H, Wd = x.shape
+    out = torch.empty((N, Cc, H // 3, Wd // 3), dtype=torch.float32, device=x.device,
+                      memory_format=torch.channels_last)
+    _lib.check(_lib.lib().afs_maxpool3_nhwc_fwd(_ptr(x), N, H, Wd, Cc, _ptr(out), _stream()),
+               "afs_maxpool3_nhwc_fwd")
+    return out
+
+
 # --------------------------------------------------------------------------- heads
 def _proto_call(feat, cls_row, E, W, S, mode, want_pred):
     _need_cuda(feat, "feat")

@@ -108,6 +108,12 @@ int afs_conv1_bn_act_pool3_fwd(const float* x, int32_t N, int32_t H, int32_t Wd,
                                const float* w_folded_host, const float* shift_host, int32_t C,
                                float negative_slope, float* out, afs_stream_t stream);
 
+/* (1c) MaxPool2d(3, 3) on channels-last activations: x [N, H, W, C] -> out [N, H/3, W/3, C], fp32,
+ * C % 4 == 0, 16-byte aligned.  Replaces the nn.MaxPool2d(3, 3) after each Conv64F block
+ * (libfewshot_core/model/backbone/conv_four.py:65,71,77,84) on the inference path.           */
+int afs_maxpool3_nhwc_fwd(const float* x, int32_t N, int32_t H, int32_t W, int32_t C, float* out,
+                          afs_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Episode row table shared by the heads (replaces the host slicing of
  * AbstractModel.split_by_episode, libfewshot_core/model/abstract_model.py:176-332).
