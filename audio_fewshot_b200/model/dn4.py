@@ -8,16 +8,20 @@ from .proto_net import accuracy_percent
 
 
 class DN4(MetricModel):
-    def __init__(self, n_k=3, **kwargs):
+    def __init__(self, n_k=3, precision="fp32", **kwargs):
+        """precision (not a reference kwarg): "fp32" keeps the bit-stable head; "tf32" runs the cosine relation
+        on the tcgen05 tensor cores in evaluation (Conv64F-sized maps)."""
         super().__init__(**kwargs)
         self.n_k = n_k
+        self.precision = precision
         self.loss_func = nn.CrossEntropyLoss()
 
     def set_forward(self, batch, update_threshold=False, enhance_classification_via_energy=False):
         image, repeats, support_size = self._unpack(batch)
         feat = self.emb_func(image)  # [N, C, H, W]
         tab = self._table(feat.shape[0], repeats, support_size)
-        output, _, _ = ops.dn4_scores(feat, tab.cls_row, tab.E, tab.W, tab.S, self.n_k)
+        precision = self.precision if (feat.shape[1] % 8 == 0 and feat.shape[1] <= 128) else "fp32"
+        output, _, _ = ops.dn4_scores(feat, tab.cls_row, tab.E, tab.W, tab.S, self.n_k, precision=precision)
         _, acc, _ = ops.vote_acc(output, tab.q_start, tab.q_target)
         return output, acc
 

@@ -187,6 +187,25 @@ def proto_logits(feat, cls_row, E, W, S, mode="euclidean", want_pred=False):
     return (logits, pred) if want_pred else logits
 
 
+def _dn4_tc_call(feat, cls_row, E, W, S, n_k, want_topk, want_pred):
+    """Tensor-core (tcgen05 TF32) DN4 head; same outputs as _dn4_call."""
+    _need_cuda(feat, "feat")
+    _need_cuda(cls_row, "cls_row", torch.int32)
+    feat = feat.contiguous()
+    N, Cc = feat.shape[0], feat.shape[1]
+    HW = int(np.prod(feat.shape[2:]))
+    NQ = N - E * W * S
+    score = torch.empty((NQ, W), dtype=torch.float32, device=feat.device)
+    topk = torch.empty((NQ, W, HW, n_k), dtype=torch.int32, device=feat.device) if want_topk else None
+    pred = torch.empty((NQ,), dtype=torch.int32, device=feat.device) if want_pred else None
+    h = _lib.lib()
+    ws_bytes = int(h.afs_dn4_tc_workspace_bytes(N, E, W, S, HW))
+    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=feat.device)
+    _lib.check(h.afs_dn4_fwd_tc(_ptr(feat), _ptr(cls_row), N, E, W, S, Cc, HW, int(n_k), _ptr(score), _ptr(topk),
+                                _ptr(pred), _ptr(ws), ws_bytes, _stream()), "afs_dn4_fwd_tc")
+    return feat, score, topk, pred
+
+
 def _dn4_call(feat, cls_row, E, W, S, n_k, want_topk, want_pred):
     _need_cuda(feat, "feat")
     _need_cuda(cls_row, "cls_row", torch.int32)
@@ -229,12 +248,17 @@ class _Dn4Fn(torch.autograd.Function):
         return grad_feat, None, None, None, None, None
 
 
-def dn4_scores(feat, cls_row, E, W, S, n_k, want_topk=False, want_pred=False):
+def dn4_scores(feat, cls_row, E, W, S, n_k, want_topk=False, want_pred=False, precision="fp32"):
     """DN4 head.  feat [N, C, H, W] (or [N, C, HW]) -> score [NQ, W] (+ topk_idx [NQ, W, HW, n_k], pred).
-    Differentiable w.r.t. feat when it requires grad (top-k selection held fixed, as torch.topk's backward)."""
+    Differentiable w.r.t. feat when it requires grad (top-k selection held fixed, as torch.topk's backward).
+    precision: "fp32" = bit-stable SIMT path (parity with the reference's indices); "tf32" = tcgen05 tensor-core
+    path (C % 8 == 0, C <= 128), scores to ~1e-4, indices may differ at near-ties."""
+    if precision not in ("fp32", "tf32"):
+        raise ValueError("precision must be 'fp32' or 'tf32'")
     if torch.is_grad_enabled() and isinstance(feat, torch.Tensor) and feat.requires_grad:
         return _Dn4Fn.apply(feat, cls_row, E, W, S, n_k), None, None
-    _, score, topk, pred = _dn4_call(feat, cls_row, E, W, S, n_k, want_topk, want_pred)
+    call = _dn4_tc_call if precision == "tf32" else _dn4_call
+    _, score, topk, pred = call(feat, cls_row, E, W, S, n_k, want_topk, want_pred)
     return score, topk, pred
 
 

@@ -160,6 +160,16 @@ int afs_dn4_fwd(const float* feat, const int32_t* cls_row, int32_t N, int32_t E,
                 int32_t S, int32_t C, int32_t HW, int32_t n_k, float* score, int32_t* topk_idx,
                 int32_t* pred, void* ws, size_t ws_bytes, afs_stream_t stream);
 
+/* (2b') The same head with the cosine relation on the tensor cores: tcgen05 TF32 MMA into tensor
+ * memory, top-n_k read straight out of TMEM, L2-normalisation fused into the operand staging (no
+ * normalised copy in HBM).  Scores agree with afs_dn4_fwd to ~1e-4 relative; top-k indices may differ
+ * at near-ties (TF32 operands), so afs_dn4_fwd remains the bit-stable parity path.  Built for
+ * C % 8 == 0 and C <= 128 (AFS_ERR_UNSUPPORTED otherwise).  ws: afs_dn4_tc_workspace_bytes().   */
+size_t afs_dn4_tc_workspace_bytes(int32_t N, int32_t E, int32_t W, int32_t S, int32_t HW);
+int afs_dn4_fwd_tc(const float* feat, const int32_t* cls_row, int32_t N, int32_t E, int32_t W, int32_t S,
+                   int32_t C, int32_t HW, int32_t n_k, float* score, int32_t* topk_idx, int32_t* pred,
+                   void* ws, size_t ws_bytes, afs_stream_t stream);
+
 /* Backward of (2b) for DN4.set_forward_loss (dn4.py:122-155 under autograd): the top-k selection is
  * held fixed (topk_idx from afs_dn4_fwd), grad_feat [N, C, HW] is fully overwritten.  ws: scratch of
  * afs_dn4_bwd_workspace_bytes() (normalised descriptors + their gradient).                  */

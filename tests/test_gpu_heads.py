@@ -151,6 +151,54 @@ def test_dn4_matches_reference_golden_and_topk(cuda, golden, name):
     assert len(diff) <= 1e-4 * mine.size
 
 
+@pytest.mark.parametrize("name", [n for n in sorted(cases.DN4_CASES) if cases.DN4_CASES[n]["C"] <= 128])
+def test_dn4_tensor_core_path_matches_reference_golden(cuda, golden, name):
+    """tcgen05 TF32 path (csrc/dn4_tc.cu): scores within the north star's 1e-3 relative of the reference's
+    DN4Layer; selected descriptors are the oracle's top-k except where two cosines differ by less than TF32
+    resolution; same argmax."""
+    from audio_fewshot_b200 import ops
+    c = cases.DN4_CASES[name]
+    feat = torch.from_numpy(cases.dn4_features(c)).to(cuda)
+    tab = fixed_table(c, cuda)
+    score, topk, pred = ops.dn4_scores(feat, tab.cls_row, tab.E, tab.W, tab.S, c["n_k"], want_topk=True,
+                                       want_pred=True, precision="tf32")
+    want = golden("dn4_layer.npz")[name]
+    got = score.cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-3 * np.abs(want).max()
+    assert np.abs(got - want).max() <= 3e-4 * np.abs(want).max()  # measured ~5e-5 with round-to-nearest operands
+    assert np.array_equal(pred.cpu().numpy(), got.argmax(1))
+    _, topv, topi, relation = dn4_oracle(c)
+    E, W, Q = c["E"], c["W"], c["Q"]
+    HW = c["H"] * c["Wd"]
+    topi = topi.reshape(E * W * Q, W, HW, c["n_k"]).numpy()
+    relation = relation.reshape(E * W * Q, W, HW, -1).numpy()
+    mine = topk.cpu().numpy()
+    assert mine.min() >= 0 and mine.max() < relation.shape[-1]
+    diff = np.argwhere(mine != topi)
+    for o, w, m, k in diff:  # a different pick must be a near-tie at TF32 resolution
+        a, b = relation[o, w, m, mine[o, w, m, k]], relation[o, w, m, topi[o, w, m, k]]
+        assert abs(a - b) <= 2e-3, (o, w, m, k, a, b)
+    assert len(diff) <= 0.02 * mine.size
+
+
+def test_dn4_tensor_core_path_ragged_multi_tile_and_unsupported(cuda):
+    from audio_fewshot_b200 import ops
+    from audio_fewshot_b200._lib import AfsError
+    rng = np.random.default_rng(15)
+    E, W, S, Q, C, H, Wd, n_k = 3, 5, 8, 3, 64, 4, 5, 3  # S*HW = 160 support descriptors: two column tiles
+    rep = rng.integers(1, 4, size=E * W * Q)
+    n = E * W * S + int(rep.sum())
+    feat = torch.from_numpy(np.abs(rng.standard_normal((n, C, H, Wd))).astype(np.float32)).to(cuda)
+    tab = ragged_table(E, W, S, Q, rep, cuda)
+    a, _, _ = ops.dn4_scores(feat, tab.cls_row, E, W, S, n_k)
+    b, _, _ = ops.dn4_scores(feat, tab.cls_row, E, W, S, n_k, precision="tf32")
+    assert (a - b).abs().max().item() <= 3e-4 * a.abs().max().item()
+    wide = torch.rand(2 * 5 * 3, 640, 2, 2, device=cuda)
+    tab2 = ragged_table(2, 5, 1, 2, np.ones(20, dtype=np.int64), cuda)
+    with pytest.raises(AfsError):
+        ops.dn4_scores(wide, tab2.cls_row, 2, 5, 1, 2, precision="tf32")
+
+
 def test_dn4_ragged_matches_oracle(cuda):
     from audio_fewshot_b200 import ops
     rng = np.random.default_rng(5)
