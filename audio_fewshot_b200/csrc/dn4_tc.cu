@@ -124,6 +124,47 @@ __device__ __forceinline__ void fill_row(float* tile, int r, const float* __rest
   }
 }
 
+// ---- branch-free streaming top-NK -------------------------------------------------------------------
+// A relation value and its column inside the 128-column tile travel as ONE sortable 32-bit key: the fp32
+// bit pattern mapped to an order-preserving unsigned integer, low 7 bits replaced by (127 - column).  A
+// sorted insert is then 2*NK-1 integer min/max instructions with no branch (the per-lane `if (x > worst)`
+// of a scalar insertion diverges on almost every column: 32 lanes each own a different row).  The 7 bits
+// cost 2^-16 relative resolution on the value, below the TF32 rounding of the operands; ties resolve
+// to the lower column, as torch.topk / the fp32 path.
+__device__ __forceinline__ uint32_t topk_key(uint32_t bits, int col_in_tile) {
+  const uint32_t mono = bits ^ (static_cast<uint32_t>(static_cast<int32_t>(bits) >> 31) | 0x80000000u);
+  return (mono & ~127u) | static_cast<uint32_t>(127 - col_in_tile);
+}
+__device__ __forceinline__ float topk_key_value(uint32_t key) {
+  const uint32_t mono = key & ~127u;
+  const uint32_t bits = (mono & 0x80000000u) ? (mono ^ 0x80000000u) : ~mono;
+  return __uint_as_float(bits);
+}
+template <int NK>
+__device__ __forceinline__ void topk_push(uint32_t (&t)[NK], uint32_t key) {
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const uint32_t hi = max(t[k], key);
+    key = min(t[k], key);
+    t[k] = hi;
+  }
+}
+// scalar sorted insert of (value, global column) into the running result (once per selected key per tile)
+template <int NK>
+__device__ __forceinline__ void topk_merge(float (&tv)[NK], int (&ti)[NK], float x, int col) {
+  if (x > tv[NK - 1] || (x == tv[NK - 1] && col < ti[NK - 1])) {
+    tv[NK - 1] = x;
+    ti[NK - 1] = col;
+#pragma unroll
+    for (int k = NK - 1; k > 0; --k) {
+      if (tv[k] > tv[k - 1] || (tv[k] == tv[k - 1] && ti[k] < ti[k - 1])) {
+        const float fv = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = fv;
+        const int iv = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = iv;
+      }
+    }
+  }
+}
+
 template <int NK>
 __global__ void __launch_bounds__(kTcThreads)
 dn4_tc_kernel(const float* __restrict__ feat, const int32_t* __restrict__ cls_row, int W, int S, int C, int HW,
@@ -227,27 +268,32 @@ dn4_tc_kernel(const float* __restrict__ feat, const int32_t* __restrict__ cls_ro
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
         // ---- epilogue: my row of the 128 x 128 relation tile -> running top-NK (descending, lowest column on ties)
+        uint32_t tk[NK];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) tk[k] = 0u;  // below every real key (keys of finite values are > 0)
+        const int valid = NS - ct * kTcCols;   // columns of this tile that exist (>= kTcCols for full tiles)
 #pragma unroll 1
         for (int c0 = 0; c0 < kTcCols; c0 += 32) {
           uint32_t v[32];
+          if (c0 >= valid) break;  // tile-uniform: nothing left in this column tile
           tmem_ld32(t_row + static_cast<uint32_t>(c0), v);
+          if (c0 + 32 <= valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int cj = ct * kTcCols + c0 + j;
-            const float x = __uint_as_float(v[j]);
-            if (cj < NS && x > tv[NK - 1]) {
-              tv[NK - 1] = x;
-              ti[NK - 1] = cj;
+            for (int j = 0; j < 32; ++j) topk_push<NK>(tk, topk_key(v[j], c0 + j));
+          } else {
 #pragma unroll
-              for (int k = NK - 1; k > 0; --k) {
-                if (tv[k] > tv[k - 1]) {  // strict: an equal earlier (lower) column stays in front
-                  const float fv = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = fv;
-                  const int iv = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = iv;
-                }
+            for (int g8 = 0; g8 < 4; ++g8) {  // boundary chunk: whole groups of 8 are skipped by a uniform branch
+              if (c0 + 8 * g8 < valid) {
+#pragma unroll
+                for (int j = 8 * g8; j < 8 * g8 + 8; ++j)
+                  if (c0 + j < valid) topk_push<NK>(tk, topk_key(v[j], c0 + j));
               }
             }
           }
         }
+#pragma unroll
+        for (int k = 0; k < NK; ++k)
+          if (tk[k] != 0u) topk_merge<NK>(tv, ti, topk_key_value(tk[k]), ct * kTcCols + 127 - static_cast<int>(tk[k] & 127u));
       }
       if (live) {
         float sum = 0.f;

@@ -1,0 +1,473 @@
+// DN4 head, warp-specialised Blackwell pipeline: TMA -> shared memory (128B swizzle) -> tcgen05.mma (TF32)
+// -> tensor memory -> tcgen05.ld -> top-k in registers.  sm_100a.
+//
+// Second generation of csrc/dn4_tc.cu (same arithmetic: DN4Layer.forward, reference
+// libfewshot_core/model/metric/dn4.py:52-73).  dn4_tc.cu stages operands with ordinary loads and runs
+// load -> MMA -> epilogue back to back; here the three stages overlap:
+//   warp 4   TMA producer: one thread issues cp.async.bulk.tensor loads of [128 descriptors x 32 channels]
+//            boxes (128-byte rows, hardware 128B swizzle) and arms the stage's mbarrier with expect_tx;
+//   warp 5   MMA issuer: one thread waits for the operands, issues C/8 tcgen05.mma.kind::tf32 into one of
+//            two 128-column TMEM accumulators and commits to the "operands free" / "accumulator full"
+//            mbarriers; it also owns the TMEM allocation (256 columns);
+//   warps 0-3 epilogue: thread i owns accumulator row i (TMEM lane i): tcgen05.ld, running top-n_k,
+//            then releases the accumulator stage.
+// Operands come from a small pre-pass (dn4_tc_prep_kernel) that writes the L2-normalised, TF32-rounded
+// descriptors K-major ([descriptor][C]) with queries compacted in output order and supports in class
+// order, so every operand tile is a contiguous row range: a plain 2-D TMA box.
+//
+// Built for C % 32 == 0, C <= 128 (one 128-byte swizzle atom per 32 channels); other widths use
+// dn4_tc.cu (C % 8 == 0) or the fp32 path dn4.cu.
+#include <cuda.h>
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace afs {
+namespace {
+
+constexpr int kThreads2 = 192;
+constexpr int kRows2 = 128;   // UMMA M
+constexpr int kCols2 = 128;   // UMMA N
+constexpr int kMaxWay2 = 32;
+constexpr uint32_t kAtomBytes = 128u * 128u;  // one [128 rows x 32 floats] swizzle-128B operand block
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [rows, C] fp32 row-major tensor, boxes of 32 channels x 128 rows, 128B swizzle, zero fill out of bounds
+bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint32_t C) {
+  EncodeTiledFn fn = encode_tiled();
+  if (fn == nullptr) return false;
+  const cuuint64_t gdim[2] = {C, rows};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(C) * sizeof(float)};
+  const cuuint32_t box[2] = {32, kRows2};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait2(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): rows are 128 B, 8-row groups 1024 B
+// apart (SBO), LBO unused (1), version 1, layout type 2.  `addr` may point 32*k bytes into the first row to
+// select the k-th group of 8 channels inside the swizzle atom.
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
+  uint64_t d = static_cast<uint64_t>((addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((kCols2 >> 3) << 17) | ((kRows2 >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32b(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- pre-pass: normalise, round to TF32, write K-major; queries compacted in output-row order
+__global__ void __launch_bounds__(128)
+dn4_tc_prep_kernel(const float* __restrict__ feat, const int32_t* __restrict__ cls_row, int64_t n_desc, int EW, int S,
+                   int C, int HW, float* __restrict__ nfq, float* __restrict__ nfs) {
+  const int64_t gid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (gid >= n_desc) return;
+  const int64_t row = gid / HW;
+  const int m = static_cast<int>(gid - row * HW);
+  int lo = 0, hi = EW - 1;  // block g with cls_row[g] <= row < cls_row[g+1]
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (cls_row[mid] <= row) lo = mid; else hi = mid - 1;
+  }
+  const int g = lo;
+  const int pos = static_cast<int>(row - cls_row[g]);
+  float* dst = pos < S ? nfs + ((static_cast<int64_t>(g) * S + pos) * HW + m) * C
+                       : nfq + ((row - static_cast<int64_t>(g + 1) * S) * HW + m) * C;
+  const float* src = feat + row * C * HW + m;
+  float ss = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = __ldg(src + static_cast<int64_t>(c) * HW);
+    ss = fmaf(v, v, ss);
+  }
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
+  for (int c = 0; c < C; c += 4) {
+    float4 v;
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(__ldg(src + static_cast<int64_t>(c + 0) * HW) * inv)); v.x = __uint_as_float(r);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(__ldg(src + static_cast<int64_t>(c + 1) * HW) * inv)); v.y = __uint_as_float(r);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(__ldg(src + static_cast<int64_t>(c + 2) * HW) * inv)); v.z = __uint_as_float(r);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(__ldg(src + static_cast<int64_t>(c + 3) * HW) * inv)); v.w = __uint_as_float(r);
+    *reinterpret_cast<float4*>(dst + c) = v;
+  }
+}
+
+struct Bars {
+  uint64_t full_a, empty_a;
+  uint64_t full_b[2], empty_b[2];
+  uint64_t tmem_full[2], tmem_empty[2];
+};
+
+// ---- branch-free streaming top-NK -------------------------------------------------------------------
+// A relation value and its column inside the 128-column tile travel as ONE sortable 32-bit key: the fp32
+// bit pattern mapped to an order-preserving unsigned integer, low 7 bits replaced by (127 - column).  A
+// sorted insert is then 2*NK-1 integer min/max instructions with no branch (the per-lane `if (x > worst)`
+// of a scalar insertion diverges on almost every column: 32 lanes each own a different row).  The 7 bits
+// cost 2^-16 relative resolution on the value, below the TF32 rounding of the operands; ties resolve
+// to the lower column, as torch.topk / the fp32 path.
+__device__ __forceinline__ uint32_t topk_key(uint32_t bits, int col_in_tile) {
+  const uint32_t mono = bits ^ (static_cast<uint32_t>(static_cast<int32_t>(bits) >> 31) | 0x80000000u);
+  return (mono & ~127u) | static_cast<uint32_t>(127 - col_in_tile);
+}
+__device__ __forceinline__ float topk_key_value(uint32_t key) {
+  const uint32_t mono = key & ~127u;
+  const uint32_t bits = (mono & 0x80000000u) ? (mono ^ 0x80000000u) : ~mono;
+  return __uint_as_float(bits);
+}
+template <int NK>
+__device__ __forceinline__ void topk_push(uint32_t (&t)[NK], uint32_t key) {
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const uint32_t hi = max(t[k], key);
+    key = min(t[k], key);
+    t[k] = hi;
+  }
+}
+// scalar sorted insert of (value, global column) into the running result (once per selected key per tile)
+template <int NK>
+__device__ __forceinline__ void topk_merge(float (&tv)[NK], int (&ti)[NK], float x, int col) {
+  if (x > tv[NK - 1] || (x == tv[NK - 1] && col < ti[NK - 1])) {
+    tv[NK - 1] = x;
+    ti[NK - 1] = col;
+#pragma unroll
+    for (int k = NK - 1; k > 0; --k) {
+      if (tv[k] > tv[k - 1] || (tv[k] == tv[k - 1] && ti[k] < ti[k - 1])) {
+        const float fv = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = fv;
+        const int iv = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = iv;
+      }
+    }
+  }
+}
+
+template <int NK>
+__global__ void __launch_bounds__(kThreads2)
+dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_s,
+               const int32_t* __restrict__ cls_row, int W, int S, int C, int HW, float* __restrict__ rowsum,
+               int32_t* __restrict__ topk_idx) {
+  extern __shared__ uint8_t s_raw[];
+  __shared__ __align__(8) Bars bars;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_qbase[kMaxWay2 + 1];
+
+  const int e = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int KH = C / 32;  // 128-byte K blocks per descriptor
+  const uint32_t blk_bytes = static_cast<uint32_t>(KH) * kAtomBytes;
+  const uint32_t base = (s_u32(s_raw) + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
+  const uint32_t a_addr = base;
+  const uint32_t b_addr0 = base + blk_bytes;
+
+  if (tid <= W) {
+    const int g = e * W + tid;
+    s_qbase[tid] = cls_row[g] - g * S;
+  }
+  if (tid == 0) {
+    mbar_init(s_u32(&bars.full_a), 1);
+    mbar_init(s_u32(&bars.empty_a), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_u32(&bars.full_b[s]), 1);
+      mbar_init(s_u32(&bars.empty_b[s]), 1);
+      mbar_init(s_u32(&bars.tmem_full[s]), 1);
+      mbar_init(s_u32(&bars.tmem_empty[s]), 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {  // two 128-column accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&s_tmem)), "r"(256u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem;
+
+  const int out0 = s_qbase[0];
+  const int out1 = s_qbase[W];
+  const int NS = S * HW;
+  const int n_rows = (out1 - out0) * HW;
+  const int n_tiles = (n_rows + kRows2 - 1) / kRows2;
+  const int n_ctiles = (NS + kCols2 - 1) / kCols2;
+
+  if (warp == 4) {
+    // ================= TMA producer (one thread) =================
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        mbar_wait2(s_u32(&bars.empty_a), (tcount & 1u) ^ 1u);  // MMAs of the previous tile have read A
+        mbar_expect_tx(s_u32(&bars.full_a), blk_bytes);
+        const int qrow0 = out0 * HW + tile * kRows2;
+        for (int kh = 0; kh < KH; ++kh)
+          tma_load_2d(a_addr + static_cast<uint32_t>(kh) * kAtomBytes, &map_q, kh * 32, qrow0, s_u32(&bars.full_a));
+        for (int w = 0; w < W; ++w) {
+          const int srow_base = (e * W + w) * S * HW;
+          for (int ct = 0; ct < n_ctiles; ++ct, ++it) {
+            const uint32_t st = it & 1u, ph = (it >> 1) & 1u;
+            mbar_wait2(s_u32(&bars.empty_b[st]), ph ^ 1u);
+            mbar_expect_tx(s_u32(&bars.full_b[st]), blk_bytes);
+            for (int kh = 0; kh < KH; ++kh)
+              tma_load_2d(b_addr0 + st * blk_bytes + static_cast<uint32_t>(kh) * kAtomBytes, &map_s, kh * 32,
+                          srow_base + ct * kCols2, s_u32(&bars.full_b[st]));
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        mbar_wait2(s_u32(&bars.full_a), tcount & 1u);
+        for (int w = 0; w < W; ++w) {
+          for (int ct = 0; ct < n_ctiles; ++ct, ++it) {
+            const uint32_t st = it & 1u, ph = (it >> 1) & 1u;
+            mbar_wait2(s_u32(&bars.full_b[st]), ph);
+            mbar_wait2(s_u32(&bars.tmem_empty[st]), ph ^ 1u);  // epilogue has drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_tmem = tmem_base + st * kCols2;
+            for (int kh = 0; kh < KH; ++kh) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t da = desc_sw128(a_addr + static_cast<uint32_t>(kh) * kAtomBytes + k4 * 32u);
+                const uint64_t db = desc_sw128(b_addr0 + st * blk_bytes + static_cast<uint32_t>(kh) * kAtomBytes + k4 * 32u);
+                const uint32_t acc = (kh | k4) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p;\n\t"
+                    "setp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+                    "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(kIdesc2), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+                    : "memory");
+              }
+            }
+            umma_commit(s_u32(&bars.empty_b[st]));    // operand stage reusable once these MMAs finish
+            umma_commit(s_u32(&bars.tmem_full[st]));  // accumulator ready for the epilogue
+          }
+        }
+        umma_commit(s_u32(&bars.empty_a));
+      }
+    }
+  } else {
+    // ================= epilogue warps 0..3: accumulator row == TMEM lane == tid =================
+    uint32_t it = 0;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int dr = tile * kRows2 + tid;
+      const bool live = dr < n_rows;
+      const int o = out0 + dr / HW;
+      const int m = dr - (dr / HW) * HW;
+      for (int w = 0; w < W; ++w) {
+        float tv[NK];
+        int ti[NK];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) { tv[k] = -INFINITY; ti[k] = INT_MAX; }
+        for (int ct = 0; ct < n_ctiles; ++ct, ++it) {
+          const uint32_t st = it & 1u, ph = (it >> 1) & 1u;
+          mbar_wait2(s_u32(&bars.tmem_full[st]), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t tk[NK];
+#pragma unroll
+          for (int k = 0; k < NK; ++k) tk[k] = 0u;  // below every real key (keys of finite values are > 0)
+          const int valid = NS - ct * kCols2;   // columns of this tile that exist (>= kCols2 for full tiles)
+#pragma unroll 1
+          for (int c0 = 0; c0 < kCols2; c0 += 32) {
+            uint32_t v[32];
+            if (c0 >= valid) break;  // tile-uniform: nothing left in this column tile
+            tmem_ld32b(t_row + st * kCols2 + static_cast<uint32_t>(c0), v);
+            if (c0 + 32 <= valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) topk_push<NK>(tk, topk_key(v[j], c0 + j));
+            } else {
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {  // boundary chunk: whole groups of 8 are skipped by a uniform branch
+                if (c0 + 8 * g8 < valid) {
+#pragma unroll
+                  for (int j = 8 * g8; j < 8 * g8 + 8; ++j)
+                    if (c0 + j < valid) topk_push<NK>(tk, topk_key(v[j], c0 + j));
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < NK; ++k)
+            if (tk[k] != 0u) topk_merge<NK>(tv, ti, topk_key_value(tk[k]), ct * kCols2 + 127 - static_cast<int>(tk[k] & 127u));
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_u32(&bars.tmem_empty[st]));
+        }
+        if (live) {
+          float sum = 0.f;
+#pragma unroll
+          for (int k = 0; k < NK; ++k) sum += tv[k];
+          const int64_t rb = (static_cast<int64_t>(o) * W + w) * HW + m;
+          rowsum[rb] = sum;
+          if (topk_idx != nullptr) {
+#pragma unroll
+            for (int k = 0; k < NK; ++k) topk_idx[rb * NK + k] = ti[k];
+          }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+  }
+}
+
+__global__ void __launch_bounds__(128)
+dn4_tc2_reduce_kernel(const float* __restrict__ rowsum, int NQ, int W, int HW, float* __restrict__ score,
+                      int32_t* __restrict__ pred) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= NQ) return;
+  float best = -INFINITY;
+  int best_w = 0;
+  for (int w = 0; w < W; ++w) {
+    const float* p = rowsum + (static_cast<int64_t>(o) * W + w) * HW;
+    float s = 0.f;
+    for (int m = 0; m < HW; ++m) s += p[m];
+    score[static_cast<int64_t>(o) * W + w] = s;
+    if (s > best) { best = s; best_w = w; }
+  }
+  if (pred != nullptr) pred[o] = best_w;
+}
+
+template <int NK>
+cudaError_t launch_tc2(dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& mq, const CUtensorMap& ms,
+                       const int32_t* cls_row, int W, int S, int C, int HW, float* rowsum, int32_t* topk_idx) {
+  cudaError_t e = cudaFuncSetAttribute(dn4_tc2_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  dn4_tc2_kernel<NK><<<grid, kThreads2, smem, stream>>>(mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx);
+  return cudaSuccess;
+}
+
+size_t align256b(size_t x) { return (x + 255) / 256 * 256; }
+
+}  // namespace
+}  // namespace afs
+
+extern "C" size_t afs_dn4_tc2_workspace_bytes(int32_t N, int32_t E, int32_t W, int32_t S, int32_t C, int32_t HW) {
+  if (N <= 0 || E <= 0 || W <= 0 || S <= 0 || C <= 0 || HW <= 0) return 0;
+  const int64_t nq = static_cast<int64_t>(N) - static_cast<int64_t>(E) * W * S;
+  if (nq <= 0) return 0;
+  return afs::align256b(static_cast<size_t>(nq) * HW * C * sizeof(float)) +
+         afs::align256b(static_cast<size_t>(E) * W * S * HW * C * sizeof(float)) +
+         afs::align256b(static_cast<size_t>(nq) * W * HW * sizeof(float));
+}
+
+extern "C" int afs_dn4_fwd_tc2(const float* feat, const int32_t* cls_row, int32_t N, int32_t E, int32_t W,
+                               int32_t S, int32_t C, int32_t HW, int32_t n_k, float* score, int32_t* topk_idx,
+                               int32_t* pred, void* ws, size_t ws_bytes, afs_stream_t stream_) {
+  using namespace afs;
+  if (feat == nullptr || cls_row == nullptr || score == nullptr || E < 0 || W < 1 || W > kMaxWay2 || S < 1 ||
+      C < 1 || HW < 1 || N < E * W * S || n_k < 1 || n_k > 8 || n_k > S * HW)
+    return AFS_ERR_INVALID_ARG;
+  if ((C & 31) != 0 || C > 128) return AFS_ERR_UNSUPPORTED;
+  const int NQ = N - E * W * S;
+  if (E == 0 || NQ == 0) return AFS_OK;
+  if (E > 65535) return AFS_ERR_UNSUPPORTED;
+  if (ws == nullptr || ws_bytes < afs_dn4_tc2_workspace_bytes(N, E, W, S, C, HW) ||
+      (reinterpret_cast<uintptr_t>(ws) & 255) != 0)
+    return AFS_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const uint64_t q_rows = static_cast<uint64_t>(NQ) * HW, s_rows = static_cast<uint64_t>(E) * W * S * HW;
+  float* nfq = static_cast<float*>(ws);
+  float* nfs = reinterpret_cast<float*>(static_cast<char*>(ws) + align256b(q_rows * C * sizeof(float)));
+  float* rowsum = reinterpret_cast<float*>(reinterpret_cast<char*>(nfs) + align256b(s_rows * C * sizeof(float)));
+
+  CUtensorMap mq, ms;
+  if (!make_map(&mq, nfq, q_rows, C) || !make_map(&ms, nfs, s_rows, C)) return AFS_ERR_UNSUPPORTED;
+
+  const int64_t n_desc = static_cast<int64_t>(N) * HW;
+  dn4_tc_prep_kernel<<<static_cast<unsigned>((n_desc + 127) / 128), 128, 0, stream>>>(feat, cls_row, n_desc, E * W, S, C,
+                                                                                     HW, nfq, nfs);
+  AFS_LAUNCH_CHECK();
+
+  const int64_t avg_rows = static_cast<int64_t>(NQ) * HW / E;
+  int tiles = static_cast<int>((avg_rows + kRows2 - 1) / kRows2);
+  if (tiles < 1) tiles = 1;
+  const dim3 grid(tiles, 1, E);
+  const size_t smem = 3 * static_cast<size_t>(C / 32) * kAtomBytes + 1024;
+  cudaError_t err = cudaSuccess;
+  switch (n_k) {
+    case 1: err = launch_tc2<1>(grid, smem, stream, mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx); break;
+    case 2: err = launch_tc2<2>(grid, smem, stream, mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx); break;
+    case 3: err = launch_tc2<3>(grid, smem, stream, mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx); break;
+    case 4: err = launch_tc2<4>(grid, smem, stream, mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx); break;
+    case 5: err = launch_tc2<5>(grid, smem, stream, mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx); break;
+    case 6: err = launch_tc2<6>(grid, smem, stream, mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx); break;
+    case 7: err = launch_tc2<7>(grid, smem, stream, mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx); break;
+    default: err = launch_tc2<8>(grid, smem, stream, mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx); break;
+  }
+  if (err != cudaSuccess) return cuda_fail(err);
+  AFS_LAUNCH_CHECK();
+  dn4_tc2_reduce_kernel<<<(NQ + 127) / 128, 128, 0, stream>>>(rowsum, NQ, W, HW, score, pred);
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
+}

@@ -187,8 +187,10 @@ def proto_logits(feat, cls_row, E, W, S, mode="euclidean", want_pred=False):
     return (logits, pred) if want_pred else logits
 
 
-def _dn4_tc_call(feat, cls_row, E, W, S, n_k, want_topk, want_pred):
-    """Tensor-core (tcgen05 TF32) DN4 head; same outputs as _dn4_call."""
+def _dn4_tc_call(feat, cls_row, E, W, S, n_k, want_topk, want_pred, staged=False):
+    """Tensor-core (tcgen05 TF32) DN4 head; same outputs as _dn4_call.  C % 32 == 0 runs the TMA-fed
+    pipeline (csrc/dn4_tc2.cu); other C % 8 == 0 widths (or staged=True) the register-staged kernel
+    (csrc/dn4_tc.cu)."""
     _need_cuda(feat, "feat")
     _need_cuda(cls_row, "cls_row", torch.int32)
     feat = feat.contiguous()
@@ -199,6 +201,12 @@ def _dn4_tc_call(feat, cls_row, E, W, S, n_k, want_topk, want_pred):
     topk = torch.empty((NQ, W, HW, n_k), dtype=torch.int32, device=feat.device) if want_topk else None
     pred = torch.empty((NQ,), dtype=torch.int32, device=feat.device) if want_pred else None
     h = _lib.lib()
+    if Cc % 32 == 0 and not staged:  # TMA-fed, warp-specialised pipeline
+        ws_bytes = int(h.afs_dn4_tc2_workspace_bytes(N, E, W, S, Cc, HW))
+        ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=feat.device)
+        _lib.check(h.afs_dn4_fwd_tc2(_ptr(feat), _ptr(cls_row), N, E, W, S, Cc, HW, int(n_k), _ptr(score),
+                                     _ptr(topk), _ptr(pred), _ptr(ws), ws_bytes, _stream()), "afs_dn4_fwd_tc2")
+        return feat, score, topk, pred
     ws_bytes = int(h.afs_dn4_tc_workspace_bytes(N, E, W, S, HW))
     ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=feat.device)
     _lib.check(h.afs_dn4_fwd_tc(_ptr(feat), _ptr(cls_row), N, E, W, S, Cc, HW, int(n_k), _ptr(score), _ptr(topk),
@@ -253,10 +261,13 @@ def dn4_scores(feat, cls_row, E, W, S, n_k, want_topk=False, want_pred=False, pr
     Differentiable w.r.t. feat when it requires grad (top-k selection held fixed, as torch.topk's backward).
     precision: "fp32" = bit-stable SIMT path (parity with the reference's indices); "tf32" = tcgen05 tensor-core
     path (C % 8 == 0, C <= 128), scores to ~1e-4, indices may differ at near-ties."""
-    if precision not in ("fp32", "tf32"):
-        raise ValueError("precision must be 'fp32' or 'tf32'")
+    if precision not in ("fp32", "tf32", "tf32_staged"):
+        raise ValueError("precision must be 'fp32', 'tf32' or 'tf32_staged'")
     if torch.is_grad_enabled() and isinstance(feat, torch.Tensor) and feat.requires_grad:
         return _Dn4Fn.apply(feat, cls_row, E, W, S, n_k), None, None
+    if precision == "tf32_staged":
+        _, score, topk, pred = _dn4_tc_call(feat, cls_row, E, W, S, n_k, want_topk, want_pred, staged=True)
+        return score, topk, pred
     call = _dn4_tc_call if precision == "tf32" else _dn4_call
     _, score, topk, pred = call(feat, cls_row, E, W, S, n_k, want_topk, want_pred)
     return score, topk, pred

@@ -19,12 +19,15 @@ for (E,W,S,Q,C,HW,nk,rag) in cases:
     torch.cuda.synchronize()
     rel = ((s1-s0).abs().max()/s0.abs().max()).item()
     agree = (i0==i1).float().mean().item()
-    print("case",(E,W,S,Q,C,HW,nk,rag),"rel err %.2e"%rel,"idx agree %.4f"%agree,"pred equal",bool((p0==p1).all()), flush=True)
+    s2,i2,p2 = ops.dn4_scores(feat, tab.cls_row, E,W,S,nk, want_topk=True, want_pred=True, precision="tf32_staged")
+    torch.cuda.synchronize()
+    print("case",(E,W,S,Q,C,HW,nk,rag),"rel err %.2e"%rel,"idx agree %.4f"%agree,"pred equal",bool((p0==p1).all()),
+          "| tma vs staged: max diff %.2e idx equal %s" % ((s1-s2).abs().max().item(), bool((i1==i2).all())), flush=True)
 # timing at C3 x128 episodes
 E,W,S,Q,C,HW,nk = 128,5,5,15,64,20,3
 feat = torch.rand(E*W*(S+Q),C,HW,device=dev)
 tab = EpisodeTable(E,W,S,Q,np.ones(E*W*Q,dtype=np.int64),dev)
-for prec in ("fp32","tf32"):
+for prec in ("fp32","tf32_staged","tf32"):
     for _ in range(3): ops.dn4_scores(feat, tab.cls_row, E,W,S,nk, precision=prec)
     torch.cuda.synchronize()
     a,b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
