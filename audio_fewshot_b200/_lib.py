@@ -61,6 +61,8 @@ SIGNATURES = {
                                  C.POINTER(AugCfg), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "afs_conv1_bn_act_pool3_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                              C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    "afs_conv1_bn_act_pool3_fwd_tf32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                                  C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "afs_maxpool3_nhwc_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p]),
     "afs_proto_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

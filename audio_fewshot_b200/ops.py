@@ -99,10 +99,11 @@ class LogMelPlan:
 
 
 # --------------------------------------------------------------------------- backbone stem
-def conv1_bn_act_pool3(x, w_folded, shift, negative_slope=0.0):
+def conv1_bn_act_pool3(x, w_folded, shift, negative_slope=0.0, tf32=False):
     """Fused eval-mode first block of Conv64F.  x [N,1,H,W] CUDA fp32; w_folded [C,9] / shift [C]:
     contiguous float32 numpy arrays (BatchNorm already folded).  Returns a channels_last
-    [N, C, H//3, W//3] tensor."""
+    [N, C, H//3, W//3] tensor.  tf32=True runs the tcgen05 tensor-core kernel (TF32 operands, the precision
+    class of cuDNN's default convolutions); tf32=False the exact-fp32 SIMT kernel."""
     _need_cuda(x, "x")
     if x.dim() != 4 or x.shape[1] != 1:
         raise ValueError("x must be [N, 1, H, W]")
@@ -113,9 +114,9 @@ def conv1_bn_act_pool3(x, w_folded, shift, negative_slope=0.0):
     shift = np.ascontiguousarray(shift, dtype=np.float32)
     out = torch.empty((N, Cc, H // 3, Wd // 3), dtype=torch.float32, device=x.device,
                       memory_format=torch.channels_last)
-    _lib.check(_lib.lib().afs_conv1_bn_act_pool3_fwd(_ptr(x), N, H, Wd, w_folded.ctypes.data_as(C.c_void_p),
-                                                     shift.ctypes.data_as(C.c_void_p), Cc, float(negative_slope),
-                                                     _ptr(out), _stream()), "afs_conv1_bn_act_pool3_fwd")
+    fn = _lib.lib().afs_conv1_bn_act_pool3_fwd_tf32 if tf32 else _lib.lib().afs_conv1_bn_act_pool3_fwd
+    _lib.check(fn(_ptr(x), N, H, Wd, w_folded.ctypes.data_as(C.c_void_p), shift.ctypes.data_as(C.c_void_p), Cc,
+                  float(negative_slope), _ptr(out), _stream()), "afs_conv1_bn_act_pool3_fwd")
     return out
 
 

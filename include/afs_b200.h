@@ -108,6 +108,14 @@ int afs_conv1_bn_act_pool3_fwd(const float* x, int32_t N, int32_t H, int32_t Wd,
                                const float* w_folded_host, const float* shift_host, int32_t C,
                                float negative_slope, float* out, afs_stream_t stream);
 
+/* (1b') The same block on the tensor cores: nine tcgen05 TF32 GEMMs per tile of 128 pooled pixels (one per
+ * pooling-window position, K = 9 taps padded to 16), max over the nine accumulators taken in tensor memory
+ * lanes.  TF32 operands, fp32 accumulation -- the precision class of the reference's default convolutions
+ * (torch.backends.cudnn.allow_tf32 = True); afs_conv1_bn_act_pool3_fwd stays the exact-fp32 kernel.        */
+int afs_conv1_bn_act_pool3_fwd_tf32(const float* x, int32_t N, int32_t H, int32_t Wd,
+                                    const float* w_folded_host, const float* shift_host, int32_t C,
+                                    float negative_slope, float* out, afs_stream_t stream);
+
 /* (1c) MaxPool2d(3, 3) on channels-last activations: x [N, H, W, C] -> out [N, H/3, W/3, C], fp32,
  * C % 4 == 0, 16-byte aligned.  Replaces the nn.MaxPool2d(3, 3) after each Conv64F block
  * (libfewshot_core/model/backbone/conv_four.py:65,71,77,84) on the inference path.           */

@@ -77,6 +77,21 @@ def test_conv1_kernel_odd_sizes_and_leaky(cuda):
         assert (got.double() - want).abs().max().item() < 1e-5
 
 
+def test_conv1_tensor_core_stem_matches_fp32_stem_at_tf32_tolerance(cuda):
+    """csrc/conv1_tc.cu (tcgen05 TF32, max-pool over TMEM accumulators) against csrc/conv1.cu (exact fp32)."""
+    from audio_fewshot_b200 import ops
+    rng = np.random.default_rng(18)
+    for (N, H, Wd, slope) in [(3, 128, 157, 0.0), (2, 7, 11, 0.2), (1, 3, 3, 0.0), (130, 9, 10, 0.1)]:
+        x = torch.from_numpy(rng.standard_normal((N, 1, H, Wd)).astype(np.float32)).to(cuda)
+        w = rng.standard_normal((64, 9)).astype(np.float32) * 0.3
+        w[5] *= -1.0
+        b = rng.standard_normal(64).astype(np.float32)
+        exact = ops.conv1_bn_act_pool3(x, w, b, slope)
+        tc = ops.conv1_bn_act_pool3(x, w, b, slope, tf32=True)
+        assert tc.shape == exact.shape
+        assert (tc - exact).abs().max().item() <= 2e-3 * exact.abs().max().item()  # TF32 operands: ~1e-3 relative
+
+
 def test_maxpool3_channels_last_matches_torch(cuda):
     from audio_fewshot_b200 import ops
     for shape in [(5, 64, 42, 52), (3, 64, 14, 17), (2, 8, 3, 3), (1, 64, 4, 5)]:
