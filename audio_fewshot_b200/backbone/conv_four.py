@@ -46,7 +46,7 @@ class Conv64F(nn.Module):
         super().__init__()
         self.is_flatten, self.is_feature = is_flatten, is_feature
         self.last_pool, self.maxpool_last2 = last_pool, maxpool_last2
-        self.stem_tf32 = False  # True: tensor-core stem when TF32 convolutions are acceptable
+        self.stem_tf32 = None  # None: follow torch.backends.cudnn.allow_tf32
         act = nn.LeakyReLU(negative_slope=negative_slope, inplace=True) if leaky_relu else nn.ReLU(inplace=False)
         trk = use_running_statistics
         self.layer1 = _conv_block(num_channels, 64, act, True, trk)
@@ -104,9 +104,11 @@ class Conv64F(nn.Module):
 
     def _forward_inference(self, x):
         c = self._folded()
-        # exact-fp32 SIMT stem by default.  The tcgen05 TF32 stem (csrc/conv1_tc.cu) is correct but, at 8 warps
-        # per SM, still latency-bound and slower on B200 (0.41 vs 0.36 ms per 800 clips, profiles/): opt-in.
-        h = ops.conv1_bn_act_pool3(x, c["w1"], c["b1"], c["slope"], tf32=self.stem_tf32)  # channels_last
+        # tcgen05 TF32 stem (csrc/conv1_tc.cu, 0.28 ms per 800 clips) when the caller allows TF32 convolutions --
+        # PyTorch's and the reference's default, and the switch that governs the cuDNN blocks below -- otherwise
+        # the exact-fp32 SIMT stem (csrc/conv1.cu, 0.36 ms).  stem_tf32 = True/False forces one of them.
+        tf32 = torch.backends.cudnn.allow_tf32 if self.stem_tf32 is None else self.stem_tf32
+        h = ops.conv1_bn_act_pool3(x, c["w1"], c["b1"], c["slope"], tf32=tf32)  # [N,64,H/3,W/3] channels_last
         h = ops.maxpool3_channels_last(self._conv_act(h, c["w2"], c["b2"], c["slope"]))
         h = self._conv_act(h, c["w3"], c["b3"], c["slope"])
         if self.maxpool_last2:

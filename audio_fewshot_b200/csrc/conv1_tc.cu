@@ -78,33 +78,42 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
   const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int64_t n_steps = 3 * my_tiles;
 
-  float p[5][5];   // this thread's input patch (current tile being built)
+  float p[5][5];   // this thread's input patch (tile being built)
+  float pn[5][5];  // patch of the NEXT tile, loaded two steps ahead so its global latency is off the critical path
   float best[kCh1];
+
+  auto load_patch = [&](int64_t tile_iter) {
+    const int64_t tile = blockIdx.x + tile_iter * gridDim.x;
+    int64_t pix = tile * kPix1 + tid;
+    if (pix >= total_pix) pix = total_pix - 1;  // tail rows recompute the last pixel; never stored
+    const int per = PH * PW;
+    const int64_t n = pix / per;
+    const int r = static_cast<int>(pix - n * per);
+    const int ph = r / PW, pw = r - ph * PW;
+    const float* img = x + n * static_cast<int64_t>(H) * Wd;
+    const int y0 = 3 * ph - 1, x0 = 3 * pw - 1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int yy = y0 + i;
+      const bool yin = (yy >= 0) && (yy < H);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int xx = x0 + j;
+        pn[i][j] = (yin && xx >= 0 && xx < Wd) ? __ldg(img + static_cast<int64_t>(yy) * Wd + xx) : 0.f;
+      }
+    }
+  };
 
   // writes the three im2col rows of window row g (positions (g,0..2)) of this thread's pooled pixel
   auto build = [&](int64_t step) {
     const int g = static_cast<int>(step % 3);
-    if (g == 0) {
-      const int64_t tile = blockIdx.x + (step / 3) * gridDim.x;
-      int64_t pix = tile * kPix1 + tid;
-      if (pix >= total_pix) pix = total_pix - 1;  // tail rows recompute the last pixel; never stored
-      const int per = PH * PW;
-      const int64_t n = pix / per;
-      const int r = static_cast<int>(pix - n * per);
-      const int ph = r / PW, pw = r - ph * PW;
-      const float* img = x + n * static_cast<int64_t>(H) * Wd;
-      const int y0 = 3 * ph - 1, x0 = 3 * pw - 1;
+    if (g == 0) {  // the patch was requested two steps ago (or in the prologue)
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int yy = y0 + i;
-        const bool yin = (yy >= 0) && (yy < H);
+      for (int i = 0; i < 5; ++i)
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const int xx = x0 + j;
-          p[i][j] = (yin && xx >= 0 && xx < Wd) ? to_tf32(__ldg(img + static_cast<int64_t>(yy) * Wd + xx)) : 0.f;
-        }
-      }
+        for (int j = 0; j < 5; ++j) p[i][j] = to_tf32(pn[i][j]);
     }
+    if (g == 1 && step / 3 + 1 < my_tiles) load_patch(step / 3 + 1);
     float4* dst = reinterpret_cast<float4*>(s_buf + (step & 1) * kBufBytes) + tid;
 #pragma unroll
     for (int gg = 0; gg < 3; ++gg) {
@@ -121,7 +130,10 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
   };
 
   uint32_t phase = 0;
-  if (n_steps > 0) build(0);
+  if (n_steps > 0) {
+    load_patch(0);
+    build(0);
+  }
   for (int64_t step = 0; step < n_steps; ++step) {
     fence_async_smem();   // im2col rows of this step -> visible to the tensor core
     fence_before();       // the previous step's TMEM reads are ordered before the barrier
@@ -146,30 +158,23 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
     fence_after();
 
     const int g = static_cast<int>(step % 3);
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {  // 32 channels at a time: 3 windows x 32 columns
-#pragma unroll 1
-      for (int dx = 0; dx < 3; ++dx) {
-        uint32_t v[32];
-        tmem_ld32(t_row + static_cast<uint32_t>(dx * kCh1 + half * 32), v);
-        if (g == 0 && dx == 0) {
-          if (half == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) best[j] = __uint_as_float(v[j]);
-          } else {
+    for (int half = 0; half < 2; ++half) {  // 32 channels at a time: three windows x 32 columns, loads batched
+      uint32_t v0[32], v1[32];
+      tmem_ld32_nowait(t_row + static_cast<uint32_t>(0 * kCh1 + half * 32), v0);
+      tmem_ld32_nowait(t_row + static_cast<uint32_t>(1 * kCh1 + half * 32), v1);
+      tmem_wait_ld();
+      if (g == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) best[32 + j] = __uint_as_float(v[j]);
-          }
-        } else {
-          if (half == 0) {
+        for (int j = 0; j < 32; ++j) best[half * 32 + j] = fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j]));
+      } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) best[j] = fmaxf(best[j], __uint_as_float(v[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) best[32 + j] = fmaxf(best[32 + j], __uint_as_float(v[j]));
-          }
-        }
+        for (int j = 0; j < 32; ++j)
+          best[half * 32 + j] = fmaxf(best[half * 32 + j], fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
       }
+      tmem_ld32(t_row + static_cast<uint32_t>(2 * kCh1 + half * 32), v0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) best[half * 32 + j] = fmaxf(best[half * 32 + j], __uint_as_float(v0[j]));
     }
     if (g == 2) {
       const int64_t tile = blockIdx.x + (step / 3) * gridDim.x;
