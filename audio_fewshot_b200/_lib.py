@@ -72,6 +72,10 @@ SIGNATURES = {
     "afs_proto_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.c_void_p]),
+    "afs_proto_bwd_cos_workspace_bytes": (C.c_size_t, [C.c_int32] * 4),
+    "afs_proto_bwd_cos": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t,
+                                    C.c_void_p]),
     "afs_dn4_workspace_bytes": (C.c_size_t, [C.c_int32] * 6),
     "afs_dn4_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                               C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

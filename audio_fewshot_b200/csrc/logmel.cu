@@ -102,6 +102,26 @@ __device__ __forceinline__ float aug_sample(const float* __restrict__ x, int64_t
   return v;
 }
 
+// Both samples of an aligned pair (idx even, idx + 1): they share one Philox block and one Box-Muller draw
+// (cos for the even sample, sin for the odd one), so the pair costs one RNG evaluation instead of two.
+__device__ __forceinline__ float2 aug_pair(const float* __restrict__ x, int64_t idx, int64_t L, const AugState& a) {
+  const int64_t s0 = idx - a.k, s1 = s0 + 1;
+  float2 v;
+  v.x = (s0 >= 0 && s0 < L) ? __fmul_rn(a.g, __ldg(x + s0)) : 0.f;
+  v.y = (s1 >= 0 && s1 < L) ? __fmul_rn(a.g, __ldg(x + s1)) : 0.f;
+  if (a.sigma > 0.f) {
+    u32x4 c;
+    c.x = static_cast<uint32_t>(idx >> 1); c.y = kStreamNoise; c.z = a.c_lo; c.w = a.c_hi;
+    const u32x4 r = philox4x32_10(c, a.seed_lo, a.seed_hi);
+    const float rad = sqrtf(-2.0f * logf(u01(r.x)));
+    float sn, cs;
+    sincospif(2.0f * u01(r.y), &sn, &cs);
+    v.x = __fadd_rn(v.x, __fmul_rn(a.sigma, rad * cs));
+    v.y = __fadd_rn(v.y, __fmul_rn(a.sigma, rad * sn));
+  }
+  return v;
+}
+
 // Raw (augmented, reflect-padded, NOT yet windowed) samples 2n, 2n+1 for n = t + 64 r of the frame that
 // starts at sample s0.  Issued one frame ahead of their use so the global-load latency hides behind the
 // previous frame's FFT.
@@ -122,8 +142,12 @@ __device__ __forceinline__ void load_frame(const float* __restrict__ x, int64_t 
         i1 = reflect_index(i1, L);
       }
       if (AUG) {
-        raw[r].x = aug_sample(x, i0, L, aug);
-        raw[r].y = aug_sample(x, i1, L, aug);
+        if (interior && (i0 & 1) == 0) {
+          raw[r] = aug_pair(x, i0, L, aug);
+        } else {
+          raw[r].x = aug_sample(x, i0, L, aug);
+          raw[r].y = aug_sample(x, i1, L, aug);
+        }
       } else {
         raw[r].x = __ldg(x + i0);
         raw[r].y = __ldg(x + i1);

@@ -296,6 +296,106 @@ proto_bwd_kernel(const float* __restrict__ feat, int64_t ld, const int32_t* __re
   }
 }
 
+// ---- cosine mode backward (MetaBaseline, reference meta_baseline.py:305-332 under autograd) ----
+// logit_ow = <q_o, p_w> / (nq_o np_w),  n = max(|.|, 1e-12)  (F.normalize).  With c = logit_ow:
+//   dq_o  = sum_w G_ow ( p_w / (nq_o np_w) - c q_o / nq_o^2 )      (second term only where |q_o| >= eps)
+//   dp_w  = sum_o G_ow ( q_o / (nq_o np_w) - c p_w / np_w^2 )
+// Row norms come from a small pre-pass (one warp per row); prototypes are recomputed per column as above.
+__global__ void __launch_bounds__(256)
+proto_norms_kernel(const float* __restrict__ feat, int64_t ld, const int32_t* __restrict__ cls_row, int EW, int W,
+                   int S, int D, int NQ, float* __restrict__ qnorm, float* __restrict__ pnorm) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= NQ + EW) return;
+  float ss = 0.f;
+  if (wid < NQ) {  // query output row o -> feature row
+    int lo = 0, hi = EW - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (cls_row[mid] - mid * S <= wid) lo = mid; else hi = mid - 1;
+    }
+    const float* q = feat + (static_cast<int64_t>(wid) + static_cast<int64_t>(lo + 1) * S) * ld;
+    for (int d = lane; d < D; d += 32) ss = fmaf(q[d], q[d], ss);
+    ss = warp_sum(ss);
+    if (lane == 0) qnorm[wid] = sqrtf(ss);
+  } else {
+    const int g = wid - NQ;
+    const float* s0 = feat + static_cast<int64_t>(cls_row[g]) * ld;
+    const float fS = static_cast<float>(S);
+    for (int d = lane; d < D; d += 32) {
+      float acc = 0.f;
+      for (int s = 0; s < S; ++s) acc += s0[static_cast<int64_t>(s) * ld + d];
+      const float pv = acc / fS;
+      ss = fmaf(pv, pv, ss);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) pnorm[g] = sqrtf(ss);
+  }
+}
+
+template <int WT>
+__global__ void __launch_bounds__(128)
+proto_bwd_cos_kernel(const float* __restrict__ feat, int64_t ld, const int32_t* __restrict__ cls_row, int W, int S,
+                     int D, const float* __restrict__ grad_logits, const float* __restrict__ logits,
+                     const float* __restrict__ qnorm, const float* __restrict__ pnorm,
+                     float* __restrict__ grad_feat, int64_t ldg) {
+  const int e = blockIdx.x;
+  const int d = blockIdx.y * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float p[WT], dp[WT], ip[WT];
+  bool pbig[WT];
+  const float fS = static_cast<float>(S);
+#pragma unroll
+  for (int w = 0; w < WT; ++w) {
+    p[w] = 0.f; dp[w] = 0.f; ip[w] = 0.f; pbig[w] = false;
+    if (w < W) {
+      const int row0 = cls_row[e * W + w];
+      float acc = 0.f;
+      for (int s = 0; s < S; ++s) acc += feat[static_cast<int64_t>(row0 + s) * ld + d];
+      p[w] = acc / fS;
+      const float n = __ldg(pnorm + e * W + w);
+      pbig[w] = n >= 1e-12f;
+      ip[w] = 1.0f / fmaxf(n, 1e-12f);
+    }
+  }
+  for (int wc = 0; wc < W; ++wc) {
+    const int g = e * W + wc;
+    const int r0 = cls_row[g] + S;
+    const int r1 = cls_row[g + 1];
+    for (int row = r0; row < r1; ++row) {
+      const int o = row - (g + 1) * S;
+      const float q = feat[static_cast<int64_t>(row) * ld + d];
+      const float nq = __ldg(qnorm + o);
+      const bool qbig = nq >= 1e-12f;
+      const float iq = 1.0f / fmaxf(nq, 1e-12f);
+      const float* G = grad_logits + static_cast<int64_t>(o) * W;
+      const float* Cv = logits + static_cast<int64_t>(o) * W;
+      float gq = 0.f;
+#pragma unroll
+      for (int w = 0; w < WT; ++w) {
+        if (w < W) {
+          const float gw = __ldg(G + w);
+          const float c = __ldg(Cv + w);
+          const float s = gw * iq * ip[w];
+          gq = fmaf(s, p[w], gq);
+          if (qbig) gq = fmaf(-gw * c * iq * iq, q, gq);
+          dp[w] = fmaf(s, q, dp[w]);
+          if (pbig[w]) dp[w] = fmaf(-gw * c * ip[w] * ip[w], p[w], dp[w]);
+        }
+      }
+      grad_feat[static_cast<int64_t>(row) * ldg + d] = gq;
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < WT; ++w) {
+    if (w < W) {
+      const int row0 = cls_row[e * W + w];
+      const float v = dp[w] / fS;
+      for (int s = 0; s < S; ++s) grad_feat[static_cast<int64_t>(row0 + s) * ldg + d] = v;
+    }
+  }
+}
+
 template <int MODE>
 int launch_bwd(const float* feat, int64_t ld, const int32_t* cls_row, int E, int W, int S, int D,
                const float* grad_logits, float* grad_feat, int64_t ldg, cudaStream_t stream) {
@@ -345,6 +445,41 @@ extern "C" int afs_proto_fwd(const float* feat, int64_t ld_feat, const int32_t* 
   proto_mean_kernel<<<blocks, 256, 0, stream>>>(feat, ld_feat, cls_row, E * W, S, D / 4, protos);
   AFS_LAUNCH_CHECK();
   return dispatch_mode<false>(mode, feat, ld_feat, cls_row, N, E, W, S, D, logits, pred, protos, stream);
+}
+
+extern "C" size_t afs_proto_bwd_cos_workspace_bytes(int32_t N, int32_t E, int32_t W, int32_t S) {
+  if (N <= 0 || E <= 0 || W <= 0 || S <= 0) return 0;
+  const int64_t nq = static_cast<int64_t>(N) - static_cast<int64_t>(E) * W * S;
+  return nq < 0 ? 0 : (static_cast<size_t>(nq) + static_cast<size_t>(E) * W) * sizeof(float);
+}
+
+extern "C" int afs_proto_bwd_cos(const float* feat, int64_t ld_feat, const int32_t* cls_row, int32_t N, int32_t E,
+                                 int32_t W, int32_t S, int32_t D, const float* logits, const float* grad_logits,
+                                 float* grad_feat, int64_t ld_grad, void* ws, size_t ws_bytes,
+                                 afs_stream_t stream_) {
+  using namespace afs;
+  if (!args_ok(feat, ld_feat, cls_row, N, E, W, S, D) || logits == nullptr || grad_logits == nullptr ||
+      grad_feat == nullptr || ld_grad < D)
+    return AFS_ERR_INVALID_ARG;
+  if (E == 0) return AFS_OK;
+  const int NQ = N - E * W * S;
+  if (ws == nullptr || ws_bytes < afs_proto_bwd_cos_workspace_bytes(N, E, W, S)) return AFS_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* qnorm = static_cast<float*>(ws);
+  float* pnorm = qnorm + NQ;
+  const int64_t warps = static_cast<int64_t>(NQ) + static_cast<int64_t>(E) * W;
+  proto_norms_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, stream>>>(feat, ld_feat, cls_row, E * W, W,
+                                                                                         S, D, NQ, qnorm, pnorm);
+  AFS_LAUNCH_CHECK();
+  dim3 grid(E, (D + 127) / 128);
+  if (W <= 8)
+    proto_bwd_cos_kernel<8><<<grid, 128, 0, stream>>>(feat, ld_feat, cls_row, W, S, D, grad_logits, logits, qnorm, pnorm,
+                                                      grad_feat, ld_grad);
+  else
+    proto_bwd_cos_kernel<32><<<grid, 128, 0, stream>>>(feat, ld_feat, cls_row, W, S, D, grad_logits, logits, qnorm, pnorm,
+                                                       grad_feat, ld_grad);
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
 }
 
 extern "C" int afs_proto_bwd(const float* feat, int64_t ld_feat, const int32_t* cls_row, int32_t N,

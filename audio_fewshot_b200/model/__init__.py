@@ -5,6 +5,7 @@ from .abstract_model import AbstractModel, MetricModel, ModelType
 from .deepbdc import DeepBDC
 from .dn4 import DN4
 from .maml import MAML, MetaModel, convert_maml_module
+from .meta_baseline import MetaBaseline
 from .proto_net import ProtoNet
 
 
@@ -15,5 +16,5 @@ def get_instance(module, name, config, **kwargs):
     return getattr(module, config[name]["name"])(**kwargs)
 
 
-__all__ = ["AbstractModel", "MetricModel", "ModelType", "MetaModel", "ProtoNet", "DN4", "DeepBDC", "MAML", "convert_maml_module", "Conv64F", "resnet12",
+__all__ = ["AbstractModel", "MetricModel", "ModelType", "MetaModel", "ProtoNet", "DN4", "DeepBDC", "MAML", "MetaBaseline", "convert_maml_module", "Conv64F", "resnet12",
            "resnet12Bdc", "BdcPool", "get_instance"]

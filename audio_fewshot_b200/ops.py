@@ -160,19 +160,29 @@ class _ProtoFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, cls_row, E, W, S, mode):
         feat_c, logits, _ = _proto_call(feat.detach(), cls_row, E, W, S, mode, False)
-        ctx.save_for_backward(feat_c, cls_row)
+        if mode == "cos_sim":
+            ctx.save_for_backward(feat_c, cls_row, logits)
+        else:
+            ctx.save_for_backward(feat_c, cls_row)
         ctx.cfg = (E, W, S, mode)
         return logits
 
     @staticmethod
     def backward(ctx, grad_logits):
-        feat, cls_row = ctx.saved_tensors
         E, W, S, mode = ctx.cfg
-        if mode == "cos_sim":
-            raise NotImplementedError("backward of the cosine prototype head is not built")
+        feat, cls_row = ctx.saved_tensors[0], ctx.saved_tensors[1]
         N, D = feat.shape
         grad_logits = grad_logits.contiguous().float()
         grad_feat = torch.empty((N, D), dtype=torch.float32, device=feat.device)
+        if mode == "cos_sim":
+            logits = ctx.saved_tensors[2]
+            h = _lib.lib()
+            ws_bytes = int(h.afs_proto_bwd_cos_workspace_bytes(N, E, W, S))
+            ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=feat.device)
+            _lib.check(h.afs_proto_bwd_cos(_ptr(feat), feat.stride(0), _ptr(cls_row), N, E, W, S, D, _ptr(logits),
+                                           _ptr(grad_logits), _ptr(grad_feat), D, _ptr(ws), ws_bytes, _stream()),
+                       "afs_proto_bwd_cos")
+            return grad_feat, None, None, None, None, None
         _lib.check(_lib.lib().afs_proto_bwd(_ptr(feat), feat.stride(0), _ptr(cls_row), N, E, W, S, D,
                                             PROTO_MODES[mode], _ptr(grad_logits), _ptr(grad_feat), D, _stream()),
                    "afs_proto_bwd")

@@ -78,6 +78,12 @@ def main():
     ms, mn = timeit(lambda: ops.conv1_bn_act_pool3(img, w, b, 0.0), flush=flush)
     report("conv1_bn_act_pool3_kernel", "clip", 800, 4 * 128 * 157 + 4 * 64 * 42 * 52, ms, mn,
            flops_per_unit=2 * 64 * 42 * 52 * 81, note="fp32 SIMT; flops count the 9 conv positions per pooled pixel")
+    ms, mn = timeit(lambda: ops.conv1_bn_act_pool3(img, w, b, 0.0, tf32=True), flush=flush)
+    report("conv1_tc_kernel (tcgen05 TF32)", "clip", 800, 4 * 128 * 157 + 4 * 64 * 42 * 52, ms, mn,
+           flops_per_unit=2 * 64 * 42 * 52 * 81, note="useful flops; the MMAs pad K 9 -> 16")
+    act = torch.randn(800, 64, 42, 52, device=dev).contiguous(memory_format=torch.channels_last)
+    ms, mn = timeit(lambda: ops.maxpool3_channels_last(act), flush=flush)
+    report("maxpool3_nhwc_kernel [800,64,42,52]", "clip", 800, 4 * 64 * (42 * 52 + 14 * 17), ms, mn)
 
     # ---- prototype head: C1 (D=1600, 5w5s15q), C2 (D=12800, 5w1s15q), C4 vectors (D=2080, 5w5s10q)
     for tag, E, W, S, Q, D, mode in (("C1 D=1600 5w5s15q", 256, 5, 5, 15, 1600, "euclidean"),
@@ -99,8 +105,12 @@ def main():
         tab = EpisodeTable(E, W, S, Q, np.ones(E * W * Q, dtype=np.int64), dev)
         ms, mn = timeit(lambda: ops.dn4_scores(feat, tab.cls_row, E, W, S, 3), flush=flush)
         HW = H * Wd
-        report("dn4 (normalize+main+reduce) " + tag, "episode", E, 4 * W * (S + Q) * C * HW + 4 * W * Q * W, ms, mn,
+        report("dn4 fp32 (normalize+main+reduce) " + tag, "episode", E, 4 * W * (S + Q) * C * HW + 4 * W * Q * W, ms, mn,
                flops_per_unit=2 * (W * Q * HW) * (W * S * HW) * C)
+        if C <= 128:
+            ms, mn = timeit(lambda: ops.dn4_scores(feat, tab.cls_row, E, W, S, 3, precision="tf32"), flush=flush)
+            report("dn4 tf32 TMA+tcgen05 (prep+main+reduce) " + tag, "episode", E,
+                   4 * W * (S + Q) * C * HW + 4 * W * Q * W, ms, mn, flops_per_unit=2 * (W * Q * HW) * (W * S * HW) * C)
 
     # ---- BDC matrix: C4 map [64,16,19]
     x = torch.relu(torch.randn(2000, 64, 16, 19, device=dev))

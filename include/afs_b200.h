@@ -156,6 +156,14 @@ int afs_proto_bwd(const float* feat, int64_t ld_feat, const int32_t* cls_row, in
                   const float* grad_logits, float* grad_feat, int64_t ld_grad,
                   afs_stream_t stream);
 
+/* Backward of the cosine mode (MetaBaseline.set_forward_loss, libfewshot_core/model/metric/
+ * meta_baseline.py:305-332 under autograd; the temperature factor stays outside, in the caller).
+ * logits: the forward output (cosines) [NQ, W]; ws: afs_proto_bwd_cos_workspace_bytes() (row norms). */
+size_t afs_proto_bwd_cos_workspace_bytes(int32_t N, int32_t E, int32_t W, int32_t S);
+int afs_proto_bwd_cos(const float* feat, int64_t ld_feat, const int32_t* cls_row, int32_t N, int32_t E,
+                      int32_t W, int32_t S, int32_t D, const float* logits, const float* grad_logits,
+                      float* grad_feat, int64_t ld_grad, void* ws, size_t ws_bytes, afs_stream_t stream);
+
 /* (2b) DN4 head: L2-normalised local descriptors, cosine relation, top-n_k
  * over each class's S*HW support descriptors, summed over the query's HW
  * descriptors.  Replaces DN4Layer.forward (libfewshot_core/model/metric/dn4.py:39-75).

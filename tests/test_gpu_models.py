@@ -347,3 +347,39 @@ def test_config_to_loader_to_set_forward_on_gpu(cuda):
             accs.append(acc)
     model.reverse_setting_info()
     assert len(accs) == 2 and all(0.0 <= a.item() <= 100.0 for a in accs)
+
+
+def test_metabaseline_forward_and_cosine_backward_match_autograd_of_oracle(cuda):
+    """MetaBaseline (reference meta_baseline.py): temp * cos(q, proto); gradients through afs_proto_bwd_cos."""
+    from audio_fewshot_b200 import model as arch
+    E, W, S, Q, D = 2, 5, 3, 4, 192
+    N = E * W * (S + Q)
+    x = np.random.default_rng(21).standard_normal((N, D)).astype(np.float32)
+    lin = torch.nn.Linear(D, D, bias=False)
+    m = arch.MetaBaseline(way_num=W, shot_num=S, query_num=Q, test_way=W, test_shot=S, test_query=Q, emb_func=lin,
+                          device=cuda).to(cuda)
+    assert float(m.temp) == 10.0 and "temp" in m.state_dict()
+    m.train()
+    out, acc, loss = m([torch.from_numpy(x), torch.zeros(N)])
+    loss.backward()
+
+    lin2 = torch.nn.Linear(D, D, bias=False)
+    with torch.no_grad():
+        lin2.weight.copy_(lin.weight.detach().cpu())
+    temp = torch.tensor(10.0, requires_grad=True)
+    feat = lin2(torch.from_numpy(x))
+    sup, qry, _, qt, _ = heads.split_by_episode(feat, W, S, Q)
+    ref_out = heads.proto_layer(qry, sup, W, S, "cos_sim").reshape(-1, W) * temp
+    ref_loss = torch.nn.functional.cross_entropy(ref_out, qt.reshape(-1))
+    ref_loss.backward()
+    assert (out.detach().cpu() - ref_out.detach()).abs().max().item() <= 1e-4 * ref_out.abs().max().item()
+    assert loss.item() == pytest.approx(ref_loss.item(), rel=1e-4)
+    g, gr = lin.weight.grad.detach().cpu(), lin2.weight.grad
+    assert (g - gr).abs().max().item() <= 2e-3 * gr.abs().max().item()
+    assert m.temp.grad.item() == pytest.approx(temp.grad.item(), rel=1e-3)
+    m.eval()
+    rep = np.random.default_rng(2).integers(1, 3, size=E * W * Q)
+    n2 = E * W * S + int(rep.sum())
+    with torch.no_grad():
+        out2, acc2 = m([torch.randn(n2, D), torch.zeros(n2), torch.from_numpy(rep), E * W * S])
+    assert out2.shape == (int(rep.sum()), W) and 0.0 <= acc2.item() <= 100.0
