@@ -59,10 +59,16 @@ SIGNATURES = {
     "afs_logmel_num_frames": (C.c_int, [C.c_void_p, C.c_int64]),
     "afs_logmel_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.POINTER(AugCfg), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "afs_logmel_fwd_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.POINTER(AugCfg), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "afs_conv1_bn_act_pool3_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                              C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "afs_conv1_bn_act_pool3_fwd_tf32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                                   C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    "afs_conv3x3_c64_packed_floats": (C.c_size_t, []),
+    "afs_conv3x3_c64_pack_weights": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "afs_conv3x3_c64_bn_act_fwd_tf32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                                  C.c_float, C.c_int32, C.c_void_p, C.c_void_p]),
     "afs_maxpool3_nhwc_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p]),
     "afs_proto_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

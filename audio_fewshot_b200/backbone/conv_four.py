@@ -9,10 +9,12 @@ Two execution paths with the same parameters:
   * training / autograd / CPU-constructed checks: the plain module graph (cuDNN + ATen), exactly the
     reference's op sequence;
   * inference on CUDA (eval mode, grad disabled, 1 input channel): `_forward_inference` --
-    block 1 is ONE sm_100a kernel (csrc/conv1.cu: conv + BatchNorm + activation + max-pool, the
-    [N,64,128,157] activation never reaches HBM), blocks 2-4 are cuDNN's fused conv+bias+ReLU on
-    channels-last tensors with BatchNorm folded into the weights (no layout round trips, no separate
-    BN / bias / ReLU passes), and BatchNorm1d is folded into the final Linear.  In the reference's
+    block 1 is ONE sm_100a kernel (csrc/conv1.cu / conv1_tc.cu: conv + BatchNorm + activation + max-pool,
+    the [N,64,128,157] activation never reaches HBM); blocks 2-3 are ONE tcgen05 kernel each
+    (csrc/conv3_tc.cu: TF32 implicit GEMM over shifted shared-memory views + folded BatchNorm + activation
+    + max-pool) when TF32 convolutions are allowed, otherwise -- and block 4 always -- cuDNN's fused
+    conv+bias+ReLU on channels-last tensors with BatchNorm folded into the weights; BatchNorm1d is folded
+    into the final Linear.  In the reference's
     eager sequence those elementwise and layout kernels are 88 % of an evaluation step on B200
     (profiles/r01_bench_launches.csv).
 """
@@ -47,6 +49,7 @@ class Conv64F(nn.Module):
         self.is_flatten, self.is_feature = is_flatten, is_feature
         self.last_pool, self.maxpool_last2 = last_pool, maxpool_last2
         self.stem_tf32 = None  # None: follow torch.backends.cudnn.allow_tf32
+        self.block_tc = None   # tcgen05 kernel for blocks 2-3; None: follow torch.backends.cudnn.allow_tf32
         act = nn.LeakyReLU(negative_slope=negative_slope, inplace=True) if leaky_relu else nn.ReLU(inplace=False)
         trk = use_running_statistics
         self.layer1 = _conv_block(num_channels, 64, act, True, trk)
@@ -89,6 +92,8 @@ class Conv64F(nn.Module):
                 w, b = self._fold(layer[0], layer[1])
                 cache["w%d" % i] = w.contiguous(memory_format=torch.channels_last)
                 cache["b%d" % i] = b.contiguous()
+                if i < 4 and w.is_cuda and tuple(w.shape) == (64, 64, 3, 3):
+                    cache["p%d" % i] = torch.from_numpy(ops.conv3x3_c64_pack_weights(w)).to(w.device)
             bn, lin = self.logits[1], self.logits[2]
             s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
             cache["wl"] = (lin.weight * s.view(1, -1)).contiguous()
@@ -109,10 +114,17 @@ class Conv64F(nn.Module):
         # the exact-fp32 SIMT stem (csrc/conv1.cu, 0.36 ms).  stem_tf32 = True/False forces one of them.
         tf32 = torch.backends.cudnn.allow_tf32 if self.stem_tf32 is None else self.stem_tf32
         h = ops.conv1_bn_act_pool3(x, c["w1"], c["b1"], c["slope"], tf32=tf32)  # [N,64,H/3,W/3] channels_last
-        h = ops.maxpool3_channels_last(self._conv_act(h, c["w2"], c["b2"], c["slope"]))
-        h = self._conv_act(h, c["w3"], c["b3"], c["slope"])
-        if self.maxpool_last2:
-            h = ops.maxpool3_channels_last(h)
+        tc = torch.backends.cudnn.allow_tf32 if self.block_tc is None else self.block_tc
+        if tc and "p2" in c and ops.conv3x3_c64_supported(h):
+            h = ops.conv3x3_c64_bn_act(h, c["p2"], c["b2"], c["slope"], pool=True)
+        else:
+            h = ops.maxpool3_channels_last(self._conv_act(h, c["w2"], c["b2"], c["slope"]))
+        if tc and "p3" in c and ops.conv3x3_c64_supported(h):
+            h = ops.conv3x3_c64_bn_act(h, c["p3"], c["b3"], c["slope"], pool=self.maxpool_last2)
+        else:
+            h = self._conv_act(h, c["w3"], c["b3"], c["slope"])
+            if self.maxpool_last2:
+                h = ops.maxpool3_channels_last(h)
         h = self._conv_act(h, c["w4"], c["b4"], c["slope"])
         if self.last_pool:
             h = ops.maxpool3_channels_last(h)

@@ -1,0 +1,394 @@
+// 64 -> 64 channel 3x3 convolution block of Conv64F on the tensor cores, channels-last:
+// Conv2d(64->64, 3x3, pad 1) + BatchNorm(eval, folded) + ReLU/LeakyReLU (+ MaxPool2d(3,3)) in ONE kernel.  sm_100a.
+//
+// Replaces blocks 2..4 of the reference's Conv64F in eval mode (libfewshot_core/model/backbone/conv_four.py:
+// 67-86,104-113).  The reference runs them as cuDNN TF32 implicit GEMMs followed by separate BatchNorm, ReLU and
+// MaxPool passes; block 2 alone is the largest kernel of an evaluation step on B200 (0.354 ms per 800 clips as a
+// cuDNN conv+bias+ReLU, plus a 447 MB activation round trip to the max-pool).  Precision class: TF32 operands,
+// fp32 accumulation -- what torch.backends.cudnn.allow_tf32 = True (PyTorch's and the reference's default) gives.
+//
+// Formulation ("shifted linear rows").  Think of one image, zero-padded to [H+2, HP = W+2], as a 1-D sequence of
+// pixels.  The conv output at linear position q = y*HP + x needs, for tap (dy,dx), the padded pixel at linear
+// position q + dy*HP + dx -- a CONSTANT offset.  So if a run of padded pixels sits in shared memory as the K-major
+// UMMA operand [pixel][8 channels = 32 bytes] (32-byte swizzle, 8-pixel atoms of 256 bytes back to back), the A
+// operand of tap (dy,dx) for 128 consecutive output positions is the same buffer with its start address advanced
+// by (dy*HP + dx)*32 bytes: the nine taps need no im2col copies at all, and every A tile is one contiguous 4 KB
+// span (33 instead of 32 shared-memory lines when the shift is odd).  Positions with x >= W are junk rows of the GEMM (2 of every HP) and are
+// simply not stored.
+//
+// A tile is R image rows of one image = NM*128 accumulator rows (R*HP <= NM*128; block 2: R = 6, HP = 54, NM = 3).
+// Roles (one persistent CTA per SM, 352 threads):
+//   warps 4-7  producers: cp.async 16-byte copies of the tile's padded pixels, 8 channels (two chunks) per ring
+//              stage, zero-filled outside the image; stages are released to the tensor core with
+//              cp.async.wait_group + fence.proxy.async + mbarrier.arrive.  The ring is rolling: stage kc of the
+//              NEXT tile is loaded as soon as the nine taps of the current tile have consumed stage kc.
+//   warps 8-10 MMA issuers, one per accumulator: per stage 9 taps of tcgen05.mma.kind::tf32 (M = 128, N = 64,
+//              K = 8) into its 64 TMEM columns, double-buffered across tiles; tcgen05.commit frees the stage.
+//   warps 0-3  epilogue: tcgen05.ld 8 channels at a time, + folded shift, activation, then either a direct
+//              channels-last store or the 3x3/3 max-pool through a small shared staging tile.
+// All 64x64x9 folded weights stay resident in shared memory (144 KB, pre-packed and TF32-rounded on the host).
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace afs {
+namespace {
+
+using namespace tc;
+
+constexpr int kC3 = 64;                       // channels in == channels out == UMMA N
+constexpr int kThreads3 = 256 + 32 * 3;        // 4 epilogue + 4 producer warps + up to 3 MMA-issuing warps
+constexpr int kRing3 = 4;                     // operand ring stages (8 input channels each)
+constexpr int kAhead3 = 3;                    // stages a producer keeps in flight before it must signal the oldest
+constexpr uint32_t kTapKcBytes = 2u * kC3 * 16u;          // weights of one (tap, 8-channel group): 2 KB
+constexpr uint32_t kWBytes3 = 9u * 8u * kTapKcBytes;      // 147 456 B
+constexpr int kMaxPix3 = 9;                   // 16-byte copies per producer thread and stage (halo <= 576)
+constexpr int kCg3 = 8;                       // channels per epilogue pass
+constexpr int kStagePitch = 12;               // floats per staged position (8 channels + pad: conflict-free stores)
+
+struct Bars3 {
+  uint64_t full[kRing3], empty[kRing3];
+  uint64_t acc_full[2], acc_empty[2];
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive3(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// K-major SWIZZLE_32B operand descriptor: rows of 32 bytes (8 TF32 values = one MMA K step), 8-row atoms of 256
+// bytes `sbo` apart, LBO unused.  The swizzle (16-byte chunk index ^= address bit 7) is a function of the shared
+// memory address, so a start address advanced by whole rows selects a shifted window of the same buffer; the
+// base-offset field carries the row phase of a start that is not atom-aligned.
+__device__ __forceinline__ uint64_t desc_kmajor_sw32(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
+  uint64_t d = static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_off & 7u) << 49;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+      : "r"(taddr));
+}
+
+struct Conv3Geom {
+  int N, H, W, HP;        // HP = W + 2: padded row pitch
+  int R;                  // image rows per tile
+  int tiles_per_img;
+  int halo;               // padded pixels held per stage: NM*128 + 2*HP + 2, rounded up to a multiple of 8
+  int pool;               // 1: MaxPool2d(3,3) fused
+  int PH, PW;             // pooled extent (pool == 1)
+  float slope;
+};
+
+template <int NM>
+__global__ void __launch_bounds__(kThreads3, 1)
+conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk, const float* __restrict__ shift,
+                      float* __restrict__ out, const Conv3Geom g) {
+  extern __shared__ __align__(16) uint8_t s_dyn_raw[];  // [weights][ring][staging][shift] after 256-byte alignment
+  __shared__ __align__(8) Bars3 bars;
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const uint32_t stage_bytes = static_cast<uint32_t>(g.halo) * 32u;
+  uint8_t* s_dyn = s_dyn_raw + ((256u - (smem_u32(s_dyn_raw) & 255u)) & 255u);  // swizzle atoms are 256 B
+  const uint32_t w_base = smem_u32(s_dyn);
+  const uint32_t ring_base = w_base + kWBytes3;
+  float* s_stage = reinterpret_cast<float*>(s_dyn + kWBytes3 + kRing3 * stage_bytes);
+  float* s_shift = s_stage + NM * 128 * kStagePitch;
+  constexpr uint32_t kTmemCols = NM == 1 ? 128u : (NM == 2 ? 256u : 512u);  // 2 x NM accumulators of 64 columns
+  constexpr uint32_t kIdesc = idesc_tf32(128, kC3);
+
+  {  // resident weights (already in operand layout) and the folded shift
+    const uint4* src = reinterpret_cast<const uint4*>(wpk);
+    uint4* dst = reinterpret_cast<uint4*>(s_dyn);
+    for (int i = tid; i < static_cast<int>(kWBytes3 / 16); i += kThreads3) dst[i] = __ldg(src + i);
+    if (tid < kC3) s_shift[tid] = shift[tid];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kRing3; ++s) {
+      mbar_init(smem_u32(&bars.full[s]), 128);  // every producer thread arrives
+      mbar_init(smem_u32(&bars.empty[s]), NM);  // one tcgen05.commit per MMA-issuing warp
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bars.acc_full[s]), NM);
+      mbar_init(smem_u32(&bars.acc_empty[s]), 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(&s_tmem, kTmemCols);
+  fence_async_smem();  // weights -> visible to the tensor core (async proxy)
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = s_tmem;
+  const int total_tiles = g.N * g.tiles_per_img;
+
+  if (warp >= 4 && warp < 8) {
+    // ======================= producers =======================
+    const int ptid = tid - 128;
+    uint32_t gs = 0;       // stages issued so far (all tiles)
+    uint32_t pending = 0;  // issued, not yet signalled: stages gs - pending .. gs - 1
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n = tile / g.tiles_per_img;
+      const int y0 = (tile - n * g.tiles_per_img) * g.R;
+      // thread pair (2j, 2j+1) copies the two 16-byte halves of one pixel's 8-channel group: a warp reads 16
+      // whole 32-byte sectors and writes 512 contiguous shared-memory bytes per instruction
+      const float* src[kMaxPix3];
+      uint32_t dst[kMaxPix3], nbytes[kMaxPix3];
+      const int half = ptid & 1;
+#pragma unroll
+      for (int i = 0; i < kMaxPix3; ++i) {
+        const int h = (ptid >> 1) + 64 * i;  // padded pixel index inside the tile's run
+        const int hr = h / g.HP, hc = h - hr * g.HP;
+        const int y = y0 - 1 + hr, xx = hc - 1;
+        const bool ok = h < g.halo && hr <= g.R + 1 && y >= 0 && y < g.H && xx >= 0 && xx < g.W;
+        src[i] = (ok ? x + ((static_cast<int64_t>(n) * g.H + y) * g.W + xx) * kC3 : x) + half * 4;
+        nbytes[i] = ok ? 16u : 0u;   // 0 -> the 16 destination bytes are zero-filled (padding)
+        dst[i] = static_cast<uint32_t>(h) * 32u + ((static_cast<uint32_t>(half) ^ ((static_cast<uint32_t>(h) >> 2) & 1u)) << 4);
+      }
+#pragma unroll 1
+      for (int kc = 0; kc < 8; ++kc, ++gs) {
+        const uint32_t st = gs % kRing3, ph = (gs / kRing3) & 1u;
+        if (pending > 0 && !mbar_test(smem_u32(&bars.empty[st]), ph ^ 1u)) {
+          // about to block on a slot the tensor core still reads: hand over everything already in flight first
+          cp_async_wait<0>();
+          fence_async_smem();
+          for (; pending > 0; --pending) mbar_arrive3(smem_u32(&bars.full[(gs - pending) % kRing3]));
+        }
+        mbar_wait(smem_u32(&bars.empty[st]), ph ^ 1u);
+        const uint32_t sb = ring_base + st * stage_bytes;
+#pragma unroll
+        for (int i = 0; i < kMaxPix3; ++i) {
+          if ((ptid >> 1) + 64 * i < g.halo) cp_async16(sb + dst[i], src[i] + kc * 8, nbytes[i]);
+        }
+        cp_async_commit();
+        ++pending;
+        if (pending > static_cast<uint32_t>(kAhead3)) {
+          cp_async_wait<kAhead3>();
+          fence_async_smem();
+          mbar_arrive3(smem_u32(&bars.full[(gs + 1 - pending) % kRing3]));
+          --pending;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_async_smem();
+    for (; pending > 0; --pending) mbar_arrive3(smem_u32(&bars.full[(gs - pending) % kRing3]));
+  } else if (warp >= 8) {
+    // ======================= MMA issuers: warp 8 + m owns accumulator m of every tile =======================
+    // (a single issuing thread spends ~80 cycles per tcgen05.mma on descriptor arithmetic and the election
+    // wrapper, more than the 48 cycles the tensor core needs for M=128, N=64, K=8 from shared memory)
+    const int m = warp - 8;
+    if (m < NM && lane == 0) {
+      uint32_t gs = 0, lt = 0;
+      const uint64_t a_desc0 = desc_kmajor_sw32(ring_base + static_cast<uint32_t>(m) * 128u * 32u, 256u, 0u);
+      const uint64_t b_desc0 = desc_kmajor_noswizzle(w_base, kC3 * 16u, 128u);
+      uint32_t tap_off[9];  // start-address advance of tap (dy,dx) in 16-byte units
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>((tap / 3) * g.HP + tap % 3) * 2u;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
+        mbar_wait(smem_u32(&bars.acc_empty[ab]), aph ^ 1u);  // epilogue has drained this accumulator set
+        fence_after();
+        const uint32_t d_tmem = tmem_base + ab * (NM * kC3) + m * kC3;
+#pragma unroll 1
+        for (int kc = 0; kc < 8; ++kc, ++gs) {
+          const uint32_t st = gs % kRing3, ph = (gs / kRing3) & 1u;
+          mbar_wait(smem_u32(&bars.full[st]), ph);
+          fence_after();
+          const uint64_t da_st = a_desc0 + ((st * stage_bytes) >> 4);
+          const uint64_t db_kc = b_desc0 + static_cast<uint32_t>(kc) * (kTapKcBytes >> 4);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap)
+            mma_tf32(d_tmem, da_st + tap_off[tap], db_kc + static_cast<uint32_t>(tap) * (8u * kTapKcBytes >> 4), kIdesc,
+                     (kc | tap) != 0);
+          commit(smem_u32(&bars.empty[st]));  // stage reusable once these MMAs have read it
+        }
+        commit(smem_u32(&bars.acc_full[ab]));
+      }
+    }
+  } else {
+    // ======================= epilogue (warps 0-3): accumulator row == TMEM lane == tid =======================
+    uint32_t lt = 0;
+    const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int n = tile / g.tiles_per_img;
+      const int y0 = (tile - n * g.tiles_per_img) * g.R;
+      const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
+      mbar_wait(smem_u32(&bars.acc_full[ab]), aph);
+      fence_after();
+      const uint32_t d0 = tmem_base + ab * (NM * kC3) + t_lane;
+#pragma unroll 1
+      for (int cg = 0; cg < kC3 / kCg3; ++cg) {
+        uint32_t v[NM][kCg3];
+#pragma unroll
+        for (int m = 0; m < NM; ++m) tmem_ld8(d0 + m * kC3 + cg * kCg3, v[m]);
+        tmem_wait_ld();
+        if (cg == kC3 / kCg3 - 1) {  // every value of this accumulator set is in registers: hand it back
+          fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive3(smem_u32(&bars.acc_empty[ab]));
+        }
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+          float r[kCg3];
+#pragma unroll
+          for (int j = 0; j < kCg3; ++j) {
+            const float a = __uint_as_float(v[m][j]) + s_shift[cg * kCg3 + j];
+            r[j] = a > 0.f ? a : a * g.slope;
+          }
+          const int q = m * 128 + tid;  // linear position inside the tile
+          if (g.pool) {
+            float4* d = reinterpret_cast<float4*>(s_stage + q * kStagePitch);
+            d[0] = make_float4(r[0], r[1], r[2], r[3]);
+            d[1] = make_float4(r[4], r[5], r[6], r[7]);
+          } else {
+            const int yy = q / g.HP, xx = q - yy * g.HP;
+            if (yy < g.R && y0 + yy < g.H && xx < g.W) {
+              float4* d = reinterpret_cast<float4*>(out + ((static_cast<int64_t>(n) * g.H + y0 + yy) * g.W + xx) * kC3 + cg * kCg3);
+              d[0] = make_float4(r[0], r[1], r[2], r[3]);
+              d[1] = make_float4(r[4], r[5], r[6], r[7]);
+            }
+          }
+        }
+        if (g.pool) {
+          epi_bar();
+          const int prt = g.R / 3;                 // pooled rows of this tile
+          const int npp = prt * g.PW;
+          const int items = npp * 2;               // (4-channel half of the group, pooled pixel): pixel fastest, so
+          for (int it = tid; it < items; it += 128) {  // a quarter-warp reads 8 pixels 3*12 floats apart: no conflicts
+            const int c4 = it >= npp ? 1 : 0, pp = it - c4 * npp;
+            const int pyl = pp / g.PW, px = pp - pyl * g.PW;
+            const int py = y0 / 3 + pyl;
+            if (py < g.PH) {
+              const float* s = s_stage + ((3 * pyl) * g.HP + 3 * px) * kStagePitch + c4 * 4;
+              float4 best = *reinterpret_cast<const float4*>(s);
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                  const float4 t = *reinterpret_cast<const float4*>(s + (i * g.HP + j) * kStagePitch);
+                  best.x = fmaxf(best.x, t.x); best.y = fmaxf(best.y, t.y);
+                  best.z = fmaxf(best.z, t.z); best.w = fmaxf(best.w, t.w);
+                }
+              }
+              *reinterpret_cast<float4*>(out + ((static_cast<int64_t>(n) * g.PH + py) * g.PW + px) * kC3 + cg * kCg3 + c4 * 4) = best;
+            }
+          }
+          epi_bar();
+        }
+      }
+    }
+  }
+
+  fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <int NM>
+int launch_conv3(const float* x, const float* wpk, const float* shift, float* out, Conv3Geom g, cudaStream_t stream) {
+  g.halo = (NM * 128 + 2 * g.HP + 2 + 7) & ~7;
+  const size_t smem = kWBytes3 + kRing3 * (g.halo * 32u) + static_cast<size_t>(NM) * 128 * kStagePitch * 4 + kC3 * 4 + 256;
+  if (smem + 256u > 232448u) return AFS_ERR_UNSUPPORTED;  // 227 KB per CTA, static barriers included
+  AFS_CUDA_TRY(cudaFuncSetAttribute(conv3x3_c64_tc_kernel<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+  const int total = g.N * g.tiles_per_img;
+  const int blocks = total < kNumSMs ? total : kNumSMs;  // persistent: one CTA per SM
+  conv3x3_c64_tc_kernel<NM><<<blocks, kThreads3, smem, stream>>>(x, wpk, shift, out, g);
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
+}
+
+inline float round_tf32_host(float v) {  // cvt.rna.tf32.f32: nearest, ties away from zero
+  uint32_t b;
+  memcpy(&b, &v, 4);
+  if ((b & 0x7f800000u) != 0x7f800000u) b = (b + 0x1000u) & ~0x1fffu;
+  float r;
+  memcpy(&r, &b, 4);
+  return r;
+}
+
+}  // namespace
+}  // namespace afs
+
+extern "C" size_t afs_conv3x3_c64_packed_floats(void) { return afs::kWBytes3 / 4; }
+
+extern "C" int afs_conv3x3_c64_pack_weights(const float* w_folded_host, float* packed_host) {
+  using namespace afs;
+  if (w_folded_host == nullptr || packed_host == nullptr) return AFS_ERR_INVALID_ARG;
+  // packed[tap][kc][chunk][cout][4] <- w[cout][cin = 8 kc + 4 chunk + i][ky][kx], tap = 3 ky + kx
+  for (int tap = 0; tap < 9; ++tap)
+    for (int kc = 0; kc < 8; ++kc)
+      for (int ch = 0; ch < 2; ++ch)
+        for (int co = 0; co < kC3; ++co)
+          for (int i = 0; i < 4; ++i) {
+            const int ci = 8 * kc + 4 * ch + i;
+            packed_host[(((tap * 8 + kc) * 2 + ch) * kC3 + co) * 4 + i] =
+                round_tf32_host(w_folded_host[(co * kC3 + ci) * 9 + tap]);
+          }
+  return AFS_OK;
+}
+
+extern "C" int afs_conv3x3_c64_bn_act_fwd_tf32(const float* x, int32_t N, int32_t H, int32_t Wd, const float* w_packed,
+                                               const float* shift, float negative_slope, int32_t pool3, float* out,
+                                               afs_stream_t stream_) {
+  using namespace afs;
+  if (x == nullptr || w_packed == nullptr || shift == nullptr || out == nullptr || N < 0 || H < 1 || Wd < 1 ||
+      negative_slope < 0.f)
+    return AFS_ERR_INVALID_ARG;
+  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w_packed)) & 15) != 0)
+    return AFS_ERR_INVALID_ARG;
+  if (pool3 && (H < 3 || Wd < 3)) return AFS_ERR_INVALID_ARG;
+  if (Wd > 61) return AFS_ERR_UNSUPPORTED;  // the operand ring of wider rows does not fit next to the weights
+  if (N == 0) return AFS_OK;
+  Conv3Geom g;
+  g.N = N; g.H = H; g.W = Wd; g.HP = Wd + 2; g.pool = pool3 ? 1 : 0; g.slope = negative_slope;
+  g.PH = H / 3; g.PW = Wd / 3;
+  const int rows_needed = pool3 ? 3 * g.PH : H;  // rows below the last complete pooling window are never used
+  // rows per tile: as many as fit 384 accumulator rows (a multiple of 3 when pooling)
+  int R = 384 / g.HP;
+  if (R > rows_needed) R = rows_needed;
+  if (pool3) R -= R % 3;
+  if (R < 1) return AFS_ERR_UNSUPPORTED;  // image rows wider than the tile (W > 126 when pooling)
+  g.R = R;
+  g.tiles_per_img = (rows_needed + R - 1) / R;
+  if (static_cast<int64_t>(N) * g.tiles_per_img > 0x7fffffffLL) return AFS_ERR_UNSUPPORTED;
+  const int NM = (R * g.HP + 127) / 128;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  switch (NM) {
+    case 1: return launch_conv3<1>(x, w_packed, shift, out, g, stream);
+    case 2: return launch_conv3<2>(x, w_packed, shift, out, g, stream);
+    default: return launch_conv3<3>(x, w_packed, shift, out, g, stream);
+  }
+}

@@ -54,7 +54,8 @@ constexpr size_t kSmemFloats = kMaxNnz + 3 * kMaxMels + kNfft + 2 * kTwbdEntries
 constexpr size_t kSmemBytes = kSmemFloats * sizeof(float);
 
 struct Params {
-  const float* wav;
+  const void* wav;     // [B, L] fp32, or int16 PCM when launched with T = int16_t
+  float pcm_scale;     // int16 PCM only: sample = (float)pcm * pcm_scale (1/32768 for full-scale [-1, 1))
   float* out;
   const float* mean;
   const float* stdv;
@@ -73,7 +74,7 @@ struct Params {
 };
 
 struct AugState {
-  float g, sigma;
+  float g, sigma, pcm_scale;
   int k;
   uint32_t c_lo, c_hi, seed_lo, seed_hi;
 };
@@ -82,13 +83,26 @@ __device__ __forceinline__ void group_bar(int grp) {
   asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
 }
 
+// Sample fetch: fp32 waveforms as they are, int16 PCM converted on the fly (exact in fp32 for a
+// power-of-two scale), so 16-bit audio crosses PCIe and HBM at half the bytes.
+__device__ __forceinline__ float ld_sample(const float* p, float) { return __ldg(p); }
+__device__ __forceinline__ float ld_sample(const int16_t* p, float s) {
+  return __fmul_rn(static_cast<float>(__ldg(p)), s);
+}
+__device__ __forceinline__ float2 ld_pair(const float* p, float) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 ld_pair(const int16_t* p, float s) {
+  const short2 v = __ldg(reinterpret_cast<const short2*>(p));
+  return make_float2(__fmul_rn(static_cast<float>(v.x), s), __fmul_rn(static_cast<float>(v.y), s));
+}
+
 // One augmented sample y[idx] = g * x[idx - k] + sigma * n[idx]; n[2i], n[2i+1]
 // are the (cos, sin) Box-Muller pair of the first two words of
 // Philox(counter = (i, 1, clip_lo, clip_hi), key = seed).
-__device__ __forceinline__ float aug_sample(const float* __restrict__ x, int64_t idx, int64_t L,
+template <typename S>
+__device__ __forceinline__ float aug_sample(const S* __restrict__ x, int64_t idx, int64_t L,
                                             const AugState& a) {
   const int64_t src = idx - a.k;
-  float v = (src >= 0 && src < L) ? __fmul_rn(a.g, __ldg(x + src)) : 0.f;
+  float v = (src >= 0 && src < L) ? __fmul_rn(a.g, ld_sample(x + src, a.pcm_scale)) : 0.f;
   if (a.sigma > 0.f) {
     u32x4 c;
     c.x = static_cast<uint32_t>(idx >> 1); c.y = kStreamNoise; c.z = a.c_lo; c.w = a.c_hi;
@@ -104,11 +118,12 @@ __device__ __forceinline__ float aug_sample(const float* __restrict__ x, int64_t
 
 // Both samples of an aligned pair (idx even, idx + 1): they share one Philox block and one Box-Muller draw
 // (cos for the even sample, sin for the odd one), so the pair costs one RNG evaluation instead of two.
-__device__ __forceinline__ float2 aug_pair(const float* __restrict__ x, int64_t idx, int64_t L, const AugState& a) {
+template <typename S>
+__device__ __forceinline__ float2 aug_pair(const S* __restrict__ x, int64_t idx, int64_t L, const AugState& a) {
   const int64_t s0 = idx - a.k, s1 = s0 + 1;
   float2 v;
-  v.x = (s0 >= 0 && s0 < L) ? __fmul_rn(a.g, __ldg(x + s0)) : 0.f;
-  v.y = (s1 >= 0 && s1 < L) ? __fmul_rn(a.g, __ldg(x + s1)) : 0.f;
+  v.x = (s0 >= 0 && s0 < L) ? __fmul_rn(a.g, ld_sample(x + s0, a.pcm_scale)) : 0.f;
+  v.y = (s1 >= 0 && s1 < L) ? __fmul_rn(a.g, ld_sample(x + s1, a.pcm_scale)) : 0.f;
   if (a.sigma > 0.f) {
     u32x4 c;
     c.x = static_cast<uint32_t>(idx >> 1); c.y = kStreamNoise; c.z = a.c_lo; c.w = a.c_hi;
@@ -125,14 +140,14 @@ __device__ __forceinline__ float2 aug_pair(const float* __restrict__ x, int64_t 
 // Raw (augmented, reflect-padded, NOT yet windowed) samples 2n, 2n+1 for n = t + 64 r of the frame that
 // starts at sample s0.  Issued one frame ahead of their use so the global-load latency hides behind the
 // previous frame's FFT.
-template <bool AUG>
-__device__ __forceinline__ void load_frame(const float* __restrict__ x, int64_t s0, int64_t L, int t,
+template <bool AUG, typename S>
+__device__ __forceinline__ void load_frame(const S* __restrict__ x, int64_t s0, int64_t L, int t,
                                            const AugState& aug, float2 (&raw)[8]) {
   const bool interior = (s0 >= 0) && (s0 + kNfft <= L);
-  if (!AUG && interior && ((reinterpret_cast<uintptr_t>(x + s0) & 7) == 0)) {
-    const float2* x2 = reinterpret_cast<const float2*>(x + s0);
+  if (!AUG && interior && ((reinterpret_cast<uintptr_t>(x + s0) & (2 * sizeof(S) - 1)) == 0)) {
+    const S* xb = x + s0 + 2 * t;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) raw[r] = __ldg(x2 + t + 64 * r);
+    for (int r = 0; r < 8; ++r) raw[r] = ld_pair(xb + 128 * r, aug.pcm_scale);
   } else {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -149,14 +164,14 @@ __device__ __forceinline__ void load_frame(const float* __restrict__ x, int64_t 
           raw[r].y = aug_sample(x, i1, L, aug);
         }
       } else {
-        raw[r].x = __ldg(x + i0);
-        raw[r].y = __ldg(x + i1);
+        raw[r].x = ld_sample(x + i0, aug.pcm_scale);
+        raw[r].y = ld_sample(x + i1, aug.pcm_scale);
       }
     }
   }
 }
 
-template <bool AUG>
+template <bool AUG, typename S>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
   float* s_w = smem;
@@ -193,9 +208,10 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
     mel_shift[i] = -mu / sd;
   }
 
-  const float* __restrict__ x = p.wav + static_cast<int64_t>(clip) * p.L;
+  const S* __restrict__ x = static_cast<const S*>(p.wav) + static_cast<int64_t>(clip) * p.L;
 
   AugState aug;
+  aug.pcm_scale = p.pcm_scale;
   if (AUG) {
     const uint64_t cg = p.first_clip + static_cast<uint64_t>(clip);
     aug.c_lo = static_cast<uint32_t>(cg);
@@ -225,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
   const float2* s_win2 = reinterpret_cast<const float2*>(s_win);
 
   float2 raw[8];
-  if (f_begin < f_end) load_frame<AUG>(x, static_cast<int64_t>(t0 + f_begin) * p.hop - p.pad, p.L, t, aug, raw);
+  if (f_begin < f_end) load_frame<AUG, S>(x, static_cast<int64_t>(t0 + f_begin) * p.hop - p.pad, p.L, t, aug, raw);
   __syncthreads();
 
   for (int fl = f_begin; fl < f_end; ++fl) {
@@ -237,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
       z[r].im = raw[r].y * w.y;
     }
     if (fl + 1 < f_end)  // prefetch the next frame while this one is transformed
-      load_frame<AUG>(x, static_cast<int64_t>(t0 + fl + 1) * p.hop - p.pad, p.L, t, aug, raw);
+      load_frame<AUG, S>(x, static_cast<int64_t>(t0 + fl + 1) * p.hop - p.pad, p.L, t, aug, raw);
     const int slot = (fl - f_begin) % kMelBatch;
     phase_a(t, z, tw, bufA);
     group_bar(grp);
@@ -323,8 +339,11 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   if (e == cudaSuccess) e = cudaMemcpy(plan->d_tw1024, tw.data(), kNfft * sizeof(float2), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(plan->d_band, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(plan->d_weights, weights.data(), weights.size() * sizeof(float), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes));
+  const int smem = static_cast<int>(kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaSetDevice(prev);
   if (e != cudaSuccess) {
     afs_logmel_plan_destroy(plan);
@@ -349,11 +368,13 @@ extern "C" int afs_logmel_num_frames(const afs_logmel_plan* plan, int64_t L) {
   return afs::num_frames(plan->cfg, L);
 }
 
-extern "C" int afs_logmel_fwd(const afs_logmel_plan* plan, const float* wav, int32_t B, int64_t L,
-                              const float* mean, const float* std, const afs_aug_cfg* aug,
-                              uint64_t seed, uint64_t first_clip_index, float* out,
-                              afs_stream_t stream_) {
-  using namespace afs;
+namespace afs {
+namespace {
+
+template <typename S>
+int logmel_launch(const afs_logmel_plan* plan, const S* wav, float pcm_scale, int32_t B, int64_t L, const float* mean,
+                  const float* std, const afs_aug_cfg* aug, uint64_t seed, uint64_t first_clip_index, float* out,
+                  afs_stream_t stream_) {
   if (plan == nullptr || wav == nullptr || mean == nullptr || std == nullptr || out == nullptr ||
       B < 0 || L < 1)
     return AFS_ERR_INVALID_ARG;
@@ -367,7 +388,7 @@ extern "C" int afs_logmel_fwd(const afs_logmel_plan* plan, const float* wav, int
   if (B == 0 || T <= 0) return AFS_OK;
 
   Params p;
-  p.wav = wav; p.out = out; p.mean = mean; p.stdv = std;
+  p.wav = wav; p.pcm_scale = pcm_scale; p.out = out; p.mean = mean; p.stdv = std;
   p.window = plan->d_window; p.tw1024 = plan->d_tw1024; p.band = plan->d_band; p.weights = plan->d_weights;
   p.L = L; p.nnz = plan->nnz; p.B = B; p.T = T; p.hop = cfg.hop; p.n_mels = cfg.n_mels; p.pad = pad;
   p.chunks = (T + kFramesPerCta - 1) / kFramesPerCta;
@@ -382,10 +403,27 @@ extern "C" int afs_logmel_fwd(const afs_logmel_plan* plan, const float* wav, int
     p.gain_lo = aug->gain_db_lo; p.gain_hi = aug->gain_db_hi;
     p.noise_lo = aug->noise_std_lo; p.noise_hi = aug->noise_std_hi;
     p.max_shift = aug->max_shift;
-    logmel_kernel<true><<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(p);
+    logmel_kernel<true, S><<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(p);
   } else {
-    logmel_kernel<false><<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(p);
+    logmel_kernel<false, S><<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(p);
   }
   AFS_LAUNCH_CHECK();
   return AFS_OK;
+}
+
+}  // namespace
+}  // namespace afs
+
+extern "C" int afs_logmel_fwd(const afs_logmel_plan* plan, const float* wav, int32_t B, int64_t L,
+                              const float* mean, const float* std, const afs_aug_cfg* aug,
+                              uint64_t seed, uint64_t first_clip_index, float* out,
+                              afs_stream_t stream) {
+  return afs::logmel_launch<float>(plan, wav, 1.f, B, L, mean, std, aug, seed, first_clip_index, out, stream);
+}
+
+extern "C" int afs_logmel_fwd_pcm16(const afs_logmel_plan* plan, const int16_t* wav, float pcm_scale, int32_t B,
+                                    int64_t L, const float* mean, const float* std, const afs_aug_cfg* aug,
+                                    uint64_t seed, uint64_t first_clip_index, float* out,
+                                    afs_stream_t stream) {
+  return afs::logmel_launch<int16_t>(plan, wav, pcm_scale, B, L, mean, std, aug, seed, first_clip_index, out, stream);
 }

@@ -55,17 +55,18 @@ def load_mean_std(path):
 
 
 class LogMelFrontEnd(nn.Module):
-    """wav [B, L] (CUDA fp32) -> [B, 1, n_mels, T].  mean/std: scalars or per-bin [n_mels]."""
+    """wav [B, L] (CUDA fp32, or int16 PCM read as pcm * pcm_scale) -> [B, 1, n_mels, T].
+    mean/std: scalars or per-bin [n_mels]."""
 
     def __init__(self, sample_rate=16000, n_fft=1024, hop_length=512, n_mels=128, f_min=0.0, f_max=None,
                  mean=0.0, std=1.0, mean_std_file=None, center=True, log_mult=10.0, log_eps=LOG_EPS, aug=None,
-                 seed=0):
+                 seed=0, pcm_scale=1.0 / 32768.0):
         super().__init__()
         if mean_std_file is not None:
             mean, std = load_mean_std(mean_std_file)
         self.sample_rate, self.n_fft, self.hop_length, self.n_mels = sample_rate, n_fft, hop_length, n_mels
         self.center, self.log_mult, self.log_eps = center, log_mult, log_eps
-        self.aug, self.seed = aug, seed
+        self.aug, self.seed, self.pcm_scale = aug, seed, pcm_scale
         self._fb = slaney_mel_filterbank(n_fft // 2 + 1, n_mels, sample_rate, f_min, f_max)
         self._window = hann_window(n_fft)
         self.register_buffer("mean", torch.full((n_mels,), 0.0) + torch.as_tensor(mean, dtype=torch.float32).reshape(-1))
@@ -81,4 +82,4 @@ class LogMelFrontEnd(nn.Module):
     def forward(self, wav, first_clip_index=0, out=None):
         aug = self.aug if self.training else None
         return self.plan().forward(wav, self.mean, self.std, aug=aug, seed=self.seed,
-                                   first_clip_index=first_clip_index, out=out)
+                                   first_clip_index=first_clip_index, out=out, pcm_scale=self.pcm_scale)

@@ -63,9 +63,11 @@ class LogMelPlan:
     def num_frames(self, L):
         return int(_lib.lib().afs_logmel_num_frames(self._handle, int(L)))
 
-    def forward(self, wav, mean, std, aug=None, seed=0, first_clip_index=0, out=None):
-        """wav [B, L] fp32 CUDA -> [B, 1, n_mels, T] fp32.  mean/std: [n_mels] CUDA tensors."""
-        _need_cuda(wav, "wav")
+    def forward(self, wav, mean, std, aug=None, seed=0, first_clip_index=0, out=None, pcm_scale=1.0 / 32768.0):
+        """wav [B, L] CUDA, fp32 or int16 PCM (sample = pcm * pcm_scale) -> [B, 1, n_mels, T] fp32.
+        mean/std: [n_mels] CUDA tensors."""
+        _need_cuda(wav, "wav", torch.int16 if isinstance(wav, torch.Tensor) and wav.dtype == torch.int16
+                   else torch.float32)
         _need_cuda(mean, "mean")
         _need_cuda(std, "std")
         if wav.dim() != 2:
@@ -84,6 +86,12 @@ class LogMelPlan:
             aug_ref = C.byref(_lib.AugCfg(float(aug["gain_db"][0]), float(aug["gain_db"][1]),
                                           int(aug.get("max_shift", 0)),
                                           float(aug["noise_std"][0]), float(aug["noise_std"][1])))
+        if wav.dtype == torch.int16:
+            _lib.check(_lib.lib().afs_logmel_fwd_pcm16(self._handle, _ptr(wav), float(pcm_scale), B, L,
+                                                       _ptr(mean.contiguous()), _ptr(std.contiguous()), aug_ref,
+                                                       int(seed), int(first_clip_index), _ptr(out), _stream()),
+                       "afs_logmel_fwd_pcm16")
+            return out
         _lib.check(_lib.lib().afs_logmel_fwd(self._handle, _ptr(wav), B, L, _ptr(mean.contiguous()),
                                              _ptr(std.contiguous()), aug_ref, int(seed), int(first_clip_index),
                                              _ptr(out), _stream()), "afs_logmel_fwd")
@@ -117,6 +125,44 @@ def conv1_bn_act_pool3(x, w_folded, shift, negative_slope=0.0, tf32=False):
     fn = _lib.lib().afs_conv1_bn_act_pool3_fwd_tf32 if tf32 else _lib.lib().afs_conv1_bn_act_pool3_fwd
     _lib.check(fn(_ptr(x), N, H, Wd, w_folded.ctypes.data_as(C.c_void_p), shift.ctypes.data_as(C.c_void_p), Cc,
                   float(negative_slope), _ptr(out), _stream()), "afs_conv1_bn_act_pool3_fwd")
+    return out
+
+
+def conv3x3_c64_pack_weights(w_folded):
+    """BatchNorm-folded [64, 64, 3, 3] weights (any device) -> the packed, TF32-rounded operand buffer of
+    conv3x3_c64_bn_act (a float32 numpy array; upload it once and keep it)."""
+    w = np.ascontiguousarray(w_folded.detach().float().cpu().numpy() if isinstance(w_folded, torch.Tensor)
+                             else w_folded, dtype=np.float32)
+    if w.shape != (64, 64, 3, 3):
+        raise ValueError("weights must be [64, 64, 3, 3]")
+    h = _lib.lib()
+    packed = np.empty((int(h.afs_conv3x3_c64_packed_floats()),), dtype=np.float32)
+    _lib.check(h.afs_conv3x3_c64_pack_weights(w.ctypes.data_as(C.c_void_p), packed.ctypes.data_as(C.c_void_p)),
+               "afs_conv3x3_c64_pack_weights")
+    return packed
+
+
+def conv3x3_c64_supported(x):
+    """Shapes the tensor-core block kernel is built for (others stay on cuDNN)."""
+    return x.dim() == 4 and x.shape[1] == 64 and x.shape[3] <= 61
+
+
+def conv3x3_c64_bn_act(x, w_packed, shift, negative_slope=0.0, pool=False):
+    """Fused eval-mode Conv64F block (64 -> 64, 3x3, pad 1, folded BatchNorm, ReLU/LeakyReLU, optional 3x3/3
+    max-pool) on the tensor cores.  x: channels_last [N, 64, H, W] CUDA fp32; w_packed: CUDA tensor from
+    conv3x3_c64_pack_weights; shift: CUDA [64].  Returns a channels_last tensor."""
+    _need_cuda(x, "x")
+    _need_cuda(w_packed, "w_packed")
+    _need_cuda(shift, "shift")
+    if not conv3x3_c64_supported(x):
+        raise ValueError("x must be [N, 64, H, W] with W <= 61")
+    x = x.contiguous(memory_format=torch.channels_last)
+    N, Cc, H, Wd = x.shape
+    oh, ow = (H // 3, Wd // 3) if pool else (H, Wd)
+    out = torch.empty((N, Cc, oh, ow), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    _lib.check(_lib.lib().afs_conv3x3_c64_bn_act_fwd_tf32(_ptr(x), N, H, Wd, _ptr(w_packed), _ptr(shift.contiguous()),
+                                                          float(negative_slope), 1 if pool else 0, _ptr(out),
+                                                          _stream()), "afs_conv3x3_c64_bn_act_fwd_tf32")
     return out
 
 

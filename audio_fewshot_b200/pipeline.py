@@ -1,7 +1,7 @@
 """Waveform -> logits episodic pipeline: the public call a user of this repo makes.
 
     pipe = EpisodePipeline(frontend, model)          # model: ProtoNet / DN4 / DeepBDC (eval)
-    output, acc = pipe(wav, repeats, support_size)   # wav: [N, L] fp32, pinned host or CUDA
+    output, acc = pipe(wav, repeats, support_size)   # wav: [N, L] fp32 or int16 PCM, pinned host or CUDA
 
 One call = H2D of the waveforms (when they arrive on the host) -> fused log-mel kernel ->
 emb_func (cuDNN) -> head kernel -> vote/accuracy kernel.  Nothing synchronises with the host;
@@ -40,10 +40,10 @@ class EpisodePipeline:
         if not self.use_graph:
             wav_dev = wav.to(dev, non_blocking=True)
             return self._device_forward(wav_dev, repeats, support_size, first_clip_index)
-        key = (tuple(wav.shape), support_size, None if repeats is None else bytes(repeats.cpu().numpy().tobytes()))
+        key = (tuple(wav.shape), wav.dtype, support_size, None if repeats is None else bytes(repeats.cpu().numpy().tobytes()))
         entry = self._graphs.get(key)
         if entry is None:
-            static_in = torch.empty(wav.shape, dtype=torch.float32, device=dev)
+            static_in = torch.empty(wav.shape, dtype=wav.dtype, device=dev)
             static_in.copy_(wav, non_blocking=True)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -73,7 +73,7 @@ class EpisodePipeline:
         i = 0
         for wav in batches:
             if len(slots) < depth:
-                slots.append({"wav": torch.empty(wav.shape, dtype=torch.float32, device=dev), "out": None,
+                slots.append({"wav": torch.empty(wav.shape, dtype=wav.dtype, device=dev), "out": None,
                               "acc": torch.empty((), dtype=torch.float32).pin_memory(),
                               "free": torch.cuda.Event(), "copied": torch.cuda.Event(), "done": torch.cuda.Event()})
             slot = slots[i % depth]

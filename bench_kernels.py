@@ -85,6 +85,24 @@ def main():
     ms, mn = timeit(lambda: ops.maxpool3_channels_last(act), flush=flush)
     report("maxpool3_nhwc_kernel [800,64,42,52]", "clip", 800, 4 * 64 * (42 * 52 + 14 * 17), ms, mn)
 
+    # ---- Conv64F blocks 2 and 3 on the tensor cores (conv + folded BN + ReLU + max-pool) vs cuDNN + our pool
+    for tag, H, Wd in (("block 2 [800,64,42,52]", 42, 52), ("block 3 [800,64,14,17]", 14, 17)):
+        act = torch.randn(800, 64, H, Wd, device=dev).contiguous(memory_format=torch.channels_last)
+        wt = (torch.randn(64, 64, 3, 3, device=dev) * 0.06)
+        wcl = wt.contiguous(memory_format=torch.channels_last)
+        bias = torch.randn(64, device=dev)
+        packed = torch.from_numpy(ops.conv3x3_c64_pack_weights(wt)).to(dev)
+        flops = 2 * 64 * 64 * 9 * H * Wd
+        nbytes = 4 * 64 * (H * Wd + (H // 3) * (Wd // 3))
+        ms, mn = timeit(lambda: ops.conv3x3_c64_bn_act(act, packed, bias, 0.0, pool=True), flush=flush)
+        report("conv3x3_c64_tc_kernel " + tag, "clip", 800, nbytes, ms, mn, flops_per_unit=flops,
+               note="tcgen05 TF32, pool fused; useful flops")
+        torch.backends.cudnn.allow_tf32 = True
+        ms, mn = timeit(lambda: ops.maxpool3_channels_last(
+            torch.cudnn_convolution_relu(act, wcl, bias, (1, 1), (1, 1), (1, 1), 1)), flush=flush)
+        report("cuDNN conv+bias+ReLU (TF32) + maxpool3_nhwc " + tag, "clip", 800, nbytes, ms, mn, flops_per_unit=flops,
+               note="library baseline for the kernel above")
+
     # ---- prototype head: C1 (D=1600, 5w5s15q), C2 (D=12800, 5w1s15q), C4 vectors (D=2080, 5w5s10q)
     for tag, E, W, S, Q, D, mode in (("C1 D=1600 5w5s15q", 256, 5, 5, 15, 1600, "euclidean"),
                                      ("C2 D=12800 5w1s15q", 64, 5, 1, 15, 12800, "euclidean"),

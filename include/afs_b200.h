@@ -96,6 +96,14 @@ int afs_logmel_fwd(const afs_logmel_plan* plan, const float* wav, int32_t B, int
                    const float* mean, const float* std, const afs_aug_cfg* aug,
                    uint64_t seed, uint64_t first_clip_index, float* out, afs_stream_t stream);
 
+/* The same kernel fed with 16-bit PCM (the sample format of the wav files behind the reference's `*_spec`
+ * folders): wav [B, L] int16, sample value = (float)pcm * pcm_scale (1/32768 for full scale in [-1, 1); the
+ * product is exact in fp32 for a power-of-two scale, so the result is bit-identical to afs_logmel_fwd on the
+ * converted fp32 waveform).  Halves the PCIe and HBM bytes of the waveform: 2*L + 4*n_mels*T per clip.   */
+int afs_logmel_fwd_pcm16(const afs_logmel_plan* plan, const int16_t* wav, float pcm_scale, int32_t B, int64_t L,
+                         const float* mean, const float* std, const afs_aug_cfg* aug,
+                         uint64_t seed, uint64_t first_clip_index, float* out, afs_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * (1b) First Conv64F block, inference only: Conv2d(1->C,3x3,pad 1) + BatchNorm2d(eval) +
  * ReLU / LeakyReLU(negative_slope) + MaxPool2d(3,3), fused.  Replaces layer1 of Conv64F
@@ -115,6 +123,20 @@ int afs_conv1_bn_act_pool3_fwd(const float* x, int32_t N, int32_t H, int32_t Wd,
 int afs_conv1_bn_act_pool3_fwd_tf32(const float* x, int32_t N, int32_t H, int32_t Wd,
                                     const float* w_folded_host, const float* shift_host, int32_t C,
                                     float negative_slope, float* out, afs_stream_t stream);
+
+/* (1b'') Conv64F blocks 2..4, inference only: Conv2d(64->64, 3x3, pad 1) + BatchNorm2d(eval) + ReLU / LeakyReLU
+ * (+ MaxPool2d(3,3) when pool3 != 0), fused, channels-last, on the tensor cores (tcgen05 TF32, fp32 accumulate).
+ * Replaces layer2..layer4 of libfewshot_core/model/backbone/conv_four.py:67-86,104-113 in eval mode.
+ * x [N, H, Wd, 64] fp32 NHWC (device); out [N, H, Wd, 64] or, pooled, [N, H/3, Wd/3, 64] NHWC (device).
+ * w_packed (device, afs_conv3x3_c64_packed_floats() floats, 16-byte aligned): the BatchNorm-folded weights in
+ * operand order, produced on the host by afs_conv3x3_c64_pack_weights from w_folded_host [64][64][3][3] (OIHW)
+ * with round-to-nearest TF32; shift [64] (device) = (bias - mean)*gamma/sqrt(var+eps) + beta.
+ * Built for Wd <= 61; AFS_ERR_UNSUPPORTED otherwise (the caller keeps cuDNN for such shapes).               */
+size_t afs_conv3x3_c64_packed_floats(void);
+int afs_conv3x3_c64_pack_weights(const float* w_folded_host, float* packed_host);
+int afs_conv3x3_c64_bn_act_fwd_tf32(const float* x, int32_t N, int32_t H, int32_t Wd, const float* w_packed,
+                                    const float* shift, float negative_slope, int32_t pool3, float* out,
+                                    afs_stream_t stream);
 
 /* (1c) MaxPool2d(3, 3) on channels-last activations: x [N, H, W, C] -> out [N, H/3, W/3, C], fp32,
  * C % 4 == 0, 16-byte aligned.  Replaces the nn.MaxPool2d(3, 3) after each Conv64F block

@@ -113,6 +113,30 @@ def test_logmel_augmentation_matches_oracle(cuda, gain, shift, noise):
         assert len(ks) > 1  # different clips draw different shifts
 
 
+@pytest.mark.parametrize("B,L,hop,aug", [
+    (3, 80000, 512, None),                # aligned short2 loads
+    (2, 4099, 511, None),                 # odd length and hop: scalar int16 loads, reflected edges
+    (4, 16000, 512, dict(gain_db=(-3.0, 3.0), max_shift=300, noise_std=(0.005, 0.02))),
+])
+def test_logmel_pcm16_is_bit_identical_to_converted_fp32(cuda, B, L, hop, aug):
+    """16-bit PCM input (afs_logmel_fwd_pcm16): sample = pcm / 32768 is exact in fp32, so the features must equal
+    bit for bit those of the fp32 entry point on the converted waveform -- and therefore meet the float64 spec."""
+    rng = np.random.default_rng(L + hop)
+    pcm = np.clip(np.round(rng.standard_normal((B, L)) * 0.1 * 32768.0), -32768, 32767).astype(np.int16)
+    pcm[0, :7] = [-32768, 32767, 0, 1, -1, 12345, -12345]
+    x = pcm.astype(np.float32) / np.float32(32768.0)
+    fr = make_frontend(cuda, hop, 128, aug=aug, seed=77)
+    if aug is not None:
+        fr.train()
+    a = fr(torch.from_numpy(pcm).to(cuda), first_clip_index=5)
+    b = fr(torch.from_numpy(x).to(cuda), first_clip_index=5)
+    assert a.dtype == torch.float32 and torch.equal(a, b)
+    if aug is None:
+        assert_db_close(a.cpu().numpy(), fe.logmel_f64(x, hop=hop, mean=MEAN, std=STD))
+    half = make_frontend(cuda, hop, 128, pcm_scale=1.0 / 65536.0)  # another power-of-two scale
+    assert torch.equal(half(torch.from_numpy(pcm).to(cuda)), half(torch.from_numpy(x * np.float32(0.5)).to(cuda)))
+
+
 def test_logmel_rejects_bad_input(cuda):
     from audio_fewshot_b200._lib import AfsError
     fr = make_frontend(cuda)
@@ -120,3 +144,5 @@ def test_logmel_rejects_bad_input(cuda):
         fr(torch.zeros(1, 400, device=cuda))  # reflect padding needs L > n_fft/2
     with pytest.raises(AfsError):
         fr(torch.zeros(1, 4000))  # CPU tensor: no fallback
+    with pytest.raises(TypeError):
+        fr(torch.zeros(1, 4000, device=cuda, dtype=torch.float16))  # fp32 or int16 PCM only

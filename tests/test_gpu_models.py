@@ -92,6 +92,57 @@ def test_conv1_tensor_core_stem_matches_fp32_stem_at_tf32_tolerance(cuda):
         assert (tc - exact).abs().max().item() <= 2e-3 * exact.abs().max().item()  # TF32 operands: ~1e-3 relative
 
 
+@pytest.mark.parametrize("N,H,Wd,slope,pool", [
+    (5, 42, 52, 0.0, True),     # Conv64F block 2: 6 rows per tile, three 128-row accumulators
+    (3, 14, 17, 0.0, True),     # block 3: two rows of the image fall below the last pooling window
+    (2, 14, 17, 0.2, False),    # un-pooled, LeakyReLU, ragged last tile
+    (7, 4, 5, 0.0, False),      # block 4 of the DN4 backbone: one tiny tile per image
+    (2, 4, 5, 0.0, True),
+    (2, 10, 61, 0.1, False),    # widest supported row (HP = 63): 5 rows per tile, ring at the shared-memory limit
+    (300, 42, 52, 0.0, True),   # more tiles than SMs: persistent loop, ring wrap-around, both accumulator sets
+])
+def test_conv3x3_block_tensor_core_kernel(cuda, N, H, Wd, slope, pool):
+    """csrc/conv3_tc.cu (tcgen05 TF32 implicit GEMM + folded BN + activation + max-pool) against the fp64 op
+    sequence conv2d -> leaky_relu -> max_pool2d.  Tolerance: TF32 operands (weights rounded to nearest,
+    activations truncated by the MMA like cuDNN's TF32 convolutions), K = 576 -> <= 2e-3 of the output range."""
+    from audio_fewshot_b200 import ops
+    rng = np.random.default_rng(N * 1000 + H * 10 + Wd)
+    x = torch.from_numpy(rng.standard_normal((N, 64, H, Wd)).astype(np.float32)).to(cuda)
+    x = x.contiguous(memory_format=torch.channels_last)
+    w = torch.from_numpy((rng.standard_normal((64, 64, 3, 3)) * 0.06).astype(np.float32)).to(cuda)
+    w[5] *= -1.0
+    b = torch.from_numpy(rng.standard_normal(64).astype(np.float32)).to(cuda)
+    packed = torch.from_numpy(ops.conv3x3_c64_pack_weights(w)).to(cuda)
+    got = ops.conv3x3_c64_bn_act(x, packed, b, slope, pool=pool)
+    want = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1), slope)
+    if pool:
+        want = torch.nn.functional.max_pool2d(want, 3, 3)
+    assert got.shape == want.shape
+    assert got.is_contiguous(memory_format=torch.channels_last) or got.shape[2] * got.shape[3] == 1
+    err = (got.double() - want).abs().max().item()
+    assert err <= 2e-3 * want.abs().max().item(), err
+    # the packed weights are exactly the round-to-nearest TF32 values, so with TF32-exact activations the kernel
+    # must agree with an fp32-accumulated convolution to fp32 rounding
+    xq = (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    wq = ((w.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    got_q = ops.conv3x3_c64_bn_act(xq, packed, b, slope, pool=pool)
+    want_q = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(xq.double(), wq.double(), b.double(), padding=1), slope)
+    if pool:
+        want_q = torch.nn.functional.max_pool2d(want_q, 3, 3)
+    assert (got_q.double() - want_q).abs().max().item() <= 2e-5 * want_q.abs().max().item()
+
+
+def test_conv64f_tensor_core_blocks_match_fp32_path(cuda):
+    """Whole Conv64F inference path with the tcgen05 stem and blocks (TF32) against the exact-fp32 path."""
+    net = _net(cuda, "conv64f_flat")
+    x = torch.from_numpy((np.random.default_rng(6).standard_normal((24, 1, 128, 157)) * 0.7).astype(np.float32)).to(cuda)
+    with torch.no_grad():
+        exact = net(x)
+        net.stem_tf32, net.block_tc = True, True
+        fast = net(x)
+    assert (fast - exact).abs().max().item() <= 5e-3 * exact.abs().max().item()
+
+
 def test_maxpool3_channels_last_matches_torch(cuda):
     from audio_fewshot_b200 import ops
     for shape in [(5, 64, 42, 52), (3, 64, 14, 17), (2, 8, 3, 3), (1, 64, 4, 5)]:

@@ -1,0 +1,13 @@
+"""One launch of the block-2 shape for ncu (development helper)."""
+import sys
+import torch
+sys.path.insert(0, ".")
+from audio_fewshot_b200 import ops
+dev = torch.device("cuda", 0)
+x = torch.randn(800, 64, 42, 52, device=dev).contiguous(memory_format=torch.channels_last)
+w = torch.randn(64, 64, 3, 3, device=dev) * 0.06
+b = torch.randn(64, device=dev)
+packed = torch.from_numpy(ops.conv3x3_c64_pack_weights(w)).to(dev)
+for _ in range(2):
+    ops.conv3x3_c64_bn_act(x, packed, b, 0.0, pool=True)
+torch.cuda.synchronize()
