@@ -5,10 +5,79 @@ Architecture and state_dict layout of libfewshot_core/model/backbone/resnet_12.p
 reference's regulariser for training (resnet_12.py:83-99); in eval it is the identity.
 Here it is implemented with device-agnostic torch ops (the reference's version calls
 .cuda() unconditionally, dropblock.py:28-29).  Convolutions stay on cuDNN.
+
+Inference path (eval mode, grad disabled, CUDA): BatchNorms are folded into the convolution weights, tensors stay
+channels-last, the bias + LeakyReLU after conv1/conv2 is one in-place sm_100a kernel and the block tail
+(bn3 -> += residual -> LeakyReLU -> MaxPool2d) is ONE kernel (csrc/pool.cu: add_bias_act_pool) that reads the two
+convolution outputs once and writes the pooled map -- instead of the module graph's BatchNorm, add, activation
+and pooling passes over the un-pooled activation.  Training / autograd keeps the reference's op sequence.
 """
 import torch
 import torch.nn.functional as F
 from torch import nn
+
+from .. import ops
+
+
+def fold_conv_bn(conv, bn):
+    """Eval-mode BatchNorm folded into the preceding bias-free convolution -> (weight channels_last, bias)."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    w = (conv.weight * scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+    b = bn.bias - bn.running_mean * scale
+    if conv.bias is not None:
+        b = b + conv.bias * scale
+    return w, b.contiguous()
+
+
+class FoldedTrunkMixin:
+    """Shared by ResNet and ResNetBdc: the folded channels-last evaluation of layer1..layer4."""
+
+    fast_eval = True
+
+    def _inference_ok(self, x):
+        return (self.fast_eval and not self.training and not torch.is_grad_enabled() and x.is_cuda
+                and x.dim() == 4 and x.dtype == torch.float32)
+
+    def _trunk_state_key(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _folded_trunk(self):
+        key = self._trunk_state_key()
+        cache = getattr(self, "_trunk_cache", None)
+        if cache is not None and cache["key"] == key:
+            return cache["blocks"]
+        blocks = []
+        with torch.no_grad():
+            for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+                blk = layer[0]
+                w1, b1 = fold_conv_bn(blk.conv1, blk.bn1)
+                w2, b2 = fold_conv_bn(blk.conv2, blk.bn2)
+                w3, b3 = fold_conv_bn(blk.conv3, blk.bn3)
+                wd = None
+                if blk.downsample is not None:
+                    wd, bd = fold_conv_bn(blk.downsample[0], blk.downsample[1])
+                    b3 = (b3 + bd).contiguous()
+                blocks.append((w1, b1, w2, b2, w3, b3, wd, float(blk.relu.negative_slope),
+                               int(blk.stride) if blk.use_pool else 1))
+        self._trunk_cache = {"key": key, "blocks": blocks}
+        return blocks
+
+    def _trunk_inference(self, x):
+        x = x.contiguous(memory_format=torch.channels_last)
+        if x.shape[1] == 1:
+            # a 1-channel tensor is both NCHW- and NHWC-contiguous; give it unambiguous channels-last strides so
+            # cuDNN's first convolution writes channels-last output (PyTorch picks the format from the strides)
+            n, c, h, w = x.shape
+            x = x.as_strided((n, c, h, w), (h * w, 1, w, 1))
+        for layer, (w1, b1, w2, b2, w3, b3, wd, slope, k) in zip((self.layer1, self.layer2, self.layer3, self.layer4),
+                                                                  self._folded_trunk()):
+            layer[0].num_batches_tracked += 1  # the reference counts every forward (resnet_12.py:73)
+            o = ops.add_bias_act_pool(F.conv2d(x, w1, padding=1), None, b1, slope, 1, inplace=True)
+            o = ops.add_bias_act_pool(F.conv2d(o, w2, padding=1), None, b2, slope, 1, inplace=True)
+            o = F.conv2d(o, w3, padding=1)
+            r = x if wd is None else F.conv2d(x, wd)
+            x = ops.add_bias_act_pool(o, r, b3, slope, k)
+        return x
 
 
 def drop_block(x, gamma, block_size, training):
@@ -86,7 +155,7 @@ def init_resnet(module):
             nn.init.constant_(m.bias, 0)
 
 
-class ResNet(nn.Module):
+class ResNet(FoldedTrunkMixin, nn.Module):
     def __init__(self, planes=(64, 160, 320, 640), keep_prob=1.0, avg_pool=True, drop_rate=0.1,
                  dropblock_size=5, is_flatten=True, maxpool_last2=True, num_channels=3):
         super().__init__()
@@ -104,11 +173,14 @@ class ResNet(nn.Module):
         init_resnet(self)
 
     def forward(self, x):
-        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        if self._inference_ok(x):
+            x = self._trunk_inference(x)
+        else:
+            x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         if self.keep_avg_pool:
             x = self.avgpool(x)
         if self.is_flatten:
-            x = x.view(x.size(0), -1)
+            x = x.contiguous().view(x.size(0), -1)  # NCHW flatten order (resnet_12.py:285)
         return x
 
 

@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from .resnet_12 import BasicBlock, init_resnet, make_stage
+from .resnet_12 import BasicBlock, FoldedTrunkMixin, fold_conv_bn, init_resnet, make_stage
 
 
 class BdcPool(nn.Module):
@@ -37,11 +37,18 @@ class BdcPool(nn.Module):
 
     def forward(self, x):
         if self.dr is not None and self.dr != self.input_dim:
-            x = self.conv_dr_block(x)
+            if (not self.training and not torch.is_grad_enabled() and x.is_cuda
+                    and x.is_contiguous(memory_format=torch.channels_last) and self.dr % 4 == 0):
+                # inference: 1x1 conv with the BatchNorm folded in, bias + activation in one in-place kernel
+                w, b = fold_conv_bn(self.conv_dr_block[0], self.conv_dr_block[1])
+                slope = float(getattr(self.act, "negative_slope", 0.0))
+                x = ops.add_bias_act_pool(torch.nn.functional.conv2d(x, w), None, b, slope, 1, inplace=True)
+            else:
+                x = self.conv_dr_block(x)
         return ops.bdc_pool(x, self.temperature, triu=self.is_vec)
 
 
-class ResNetBdc(nn.Module):
+class ResNetBdc(FoldedTrunkMixin, nn.Module):
     def __init__(self, keep_prob=1.0, avg_pool=False, drop_rate=0.0, dropblock_size=5, num_classes=-1,
                  use_se=False, reduce_dim=640, num_channels=3):
         super().__init__()
@@ -62,7 +69,10 @@ class ResNetBdc(nn.Module):
             self.classifier = nn.Linear(640, num_classes)
 
     def forward(self, x, is_feat=False):
-        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        if self._inference_ok(x):
+            x = self._trunk_inference(x)
+        else:
+            x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.bdc_pool(x)
 
 

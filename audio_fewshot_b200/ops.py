@@ -180,6 +180,33 @@ def maxpool3_channels_last(x):
     return out
 
 
+def add_bias_act_pool(a, b=None, bias=None, negative_slope=0.0, k=1, inplace=False):
+    """MaxPool2d(k)(LeakyReLU(a + b + bias[c])) on channels_last [N, C, H, W] CUDA tensors (b, bias optional;
+    k in {1, 2, 3}).  inplace=True (k == 1 only) writes into `a`."""
+    _need_cuda(a, "a")
+    if a.dim() != 4 or a.shape[1] % 4 != 0:
+        raise ValueError("a must be [N, C, H, W] with C % 4 == 0")
+    if not a.is_contiguous(memory_format=torch.channels_last):
+        a = a.contiguous(memory_format=torch.channels_last)  # a copy: "in place" then means into that copy
+    if b is not None:
+        _need_cuda(b, "b")
+        if b.shape != a.shape:
+            raise ValueError("a and b must have the same shape")
+        b = b.contiguous(memory_format=torch.channels_last)
+    if bias is not None:
+        _need_cuda(bias, "bias")
+        bias = bias.contiguous()
+    N, Cc, H, Wd = a.shape
+    if inplace and k != 1:
+        raise ValueError("in-place only without pooling")
+    out = a if inplace else torch.empty((N, Cc, H // k, Wd // k), dtype=torch.float32, device=a.device,
+                                        memory_format=torch.channels_last)
+    _lib.check(_lib.lib().afs_add_bias_act_pool_nhwc_fwd(_ptr(a), _ptr(b), _ptr(bias), N, H, Wd, Cc,
+                                                         float(negative_slope), int(k), _ptr(out), _stream()),
+               "afs_add_bias_act_pool_nhwc_fwd")
+    return out
+
+
 # --------------------------------------------------------------------------- heads
 def _proto_call(feat, cls_row, E, W, S, mode, want_pred):
     _need_cuda(feat, "feat")

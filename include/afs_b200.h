@@ -144,6 +144,15 @@ int afs_conv3x3_c64_bn_act_fwd_tf32(const float* x, int32_t N, int32_t H, int32_
 int afs_maxpool3_nhwc_fwd(const float* x, int32_t N, int32_t H, int32_t W, int32_t C, float* out,
                           afs_stream_t stream);
 
+/* (1d) Tail of a ResNet-12 BasicBlock on the inference path, channels-last, BatchNorms folded into the
+ * convolutions: out = MaxPool2d(k)( LeakyReLU_slope( a + b + bias[c] ) ), k in {1,2,3} (floor mode).
+ * a, b [N, H, W, C] (b nullable), bias [C] (nullable), out [N, H/k, W/k, C]; fp32, C % 4 == 0, 16-byte aligned.
+ * out may alias a when k == 1 (in-place bias + activation after a folded convolution).  Replaces
+ * bn -> += residual -> relu -> maxpool of libfewshot_core/model/backbone/resnet_12.py:79-101 in eval mode. */
+int afs_add_bias_act_pool_nhwc_fwd(const float* a, const float* b, const float* bias, int32_t N, int32_t H,
+                                   int32_t W, int32_t C, float negative_slope, int32_t k, float* out,
+                                   afs_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Episode row table shared by the heads (replaces the host slicing of
  * AbstractModel.split_by_episode, libfewshot_core/model/abstract_model.py:176-332).

@@ -143,6 +143,46 @@ def test_conv64f_tensor_core_blocks_match_fp32_path(cuda):
     assert (fast - exact).abs().max().item() <= 5e-3 * exact.abs().max().item()
 
 
+@pytest.mark.parametrize("name", ["resnet12", "resnet12bdc"])
+def test_resnet12_inference_path_equals_module_graph(cuda, name):
+    """Folded channels-last trunk (cuDNN convolutions + add_bias_act_pool kernels) against the plain module graph."""
+    from audio_fewshot_b200 import ops
+    net = _net(cuda, name)
+    x = torch.from_numpy((np.random.default_rng(9).standard_normal((5, 1, 128, 157)) * 0.7).astype(np.float32)).to(cuda)
+    n0 = ops.launch_count()
+    with torch.no_grad():
+        fast = net(x)
+    assert ops.launch_count() >= n0 + 12  # 3 kernels per BasicBlock
+    net.fast_eval = False
+    with torch.no_grad():
+        slow = net(x)
+    assert fast.shape == slow.shape
+    assert (fast - slow).abs().max().item() <= 1e-4 * slow.abs().max().item()
+
+
+def test_add_bias_act_pool_kernel(cuda):
+    from audio_fewshot_b200 import ops
+    F = torch.nn.functional
+    for (shape, k, slope, with_b, with_bias) in [((3, 64, 128, 157), 2, 0.1, True, True), ((2, 160, 64, 78), 2, 0.1, True, True),
+                                                 ((2, 640, 16, 19), 1, 0.1, True, True), ((2, 8, 7, 9), 3, 0.0, False, True),
+                                                 ((1, 4, 2, 2), 2, 0.3, True, False), ((2, 64, 5, 6), 1, 0.0, False, False)]:
+        a = torch.randn(shape, device=cuda).contiguous(memory_format=torch.channels_last)
+        b = torch.randn(shape, device=cuda).contiguous(memory_format=torch.channels_last) if with_b else None
+        bias = torch.randn(shape[1], device=cuda) if with_bias else None
+        want = a if b is None else a + b
+        if bias is not None:
+            want = want + bias.view(1, -1, 1, 1)
+        want = F.leaky_relu(want, slope)
+        if k > 1:
+            want = F.max_pool2d(want, k, k)
+        got = ops.add_bias_act_pool(a, b, bias, slope, k)
+        assert got.shape == want.shape and torch.allclose(got, want, atol=1e-6, rtol=1e-6)
+        if k == 1:
+            a2 = a.clone(memory_format=torch.channels_last)
+            r = ops.add_bias_act_pool(a2, b, bias, slope, 1, inplace=True)
+            assert r.data_ptr() == a2.data_ptr() and torch.allclose(a2, want, atol=1e-6, rtol=1e-6)
+
+
 def test_maxpool3_channels_last_matches_torch(cuda):
     from audio_fewshot_b200 import ops
     for shape in [(5, 64, 42, 52), (3, 64, 14, 17), (2, 8, 3, 3), (1, 64, 4, 5)]:
