@@ -89,6 +89,12 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw32(uint32_t saddr, uint32_t sb
   d |= static_cast<uint64_t>(6) << 61;
   return d;
 }
+// One lane polls the mbarrier, the warp then reconverges: 32 lanes spinning on try_wait are 32 shared-memory
+// accesses per probe, which the profiler shows as bank-conflict wavefronts competing with the tensor core's reads.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
@@ -179,13 +185,15 @@ conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk
 #pragma unroll 1
       for (int kc = 0; kc < 8; ++kc, ++gs) {
         const uint32_t st = gs % kRing3, ph = (gs / kRing3) & 1u;
-        if (pending > 0 && !mbar_test(smem_u32(&bars.empty[st]), ph ^ 1u)) {
+        uint32_t ready = lane == 0 ? (mbar_test(smem_u32(&bars.empty[st]), ph ^ 1u) ? 1u : 0u) : 0u;
+        ready = __shfl_sync(0xffffffffu, ready, 0);
+        if (pending > 0 && !ready) {
           // about to block on a slot the tensor core still reads: hand over everything already in flight first
           cp_async_wait<0>();
           fence_async_smem();
           for (; pending > 0; --pending) mbar_arrive3(smem_u32(&bars.full[(gs - pending) % kRing3]));
         }
-        mbar_wait(smem_u32(&bars.empty[st]), ph ^ 1u);
+        if (!ready) mbar_wait_warp(smem_u32(&bars.empty[st]), ph ^ 1u, lane);
         const uint32_t sb = ring_base + st * stage_bytes;
 #pragma unroll
         for (int i = 0; i < kMaxPix3; ++i) {
@@ -245,7 +253,7 @@ conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk
       const int n = tile / g.tiles_per_img;
       const int y0 = (tile - n * g.tiles_per_img) * g.R;
       const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
-      mbar_wait(smem_u32(&bars.acc_full[ab]), aph);
+      mbar_wait_warp(smem_u32(&bars.acc_full[ab]), aph, lane);
       fence_after();
       const uint32_t d0 = tmem_base + ab * (NM * kC3) + t_lane;
 #pragma unroll 1

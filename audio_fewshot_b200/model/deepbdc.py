@@ -64,7 +64,7 @@ class DeepBDC(MetricModel):
         output = ops.proto_logits(feat, tab.cls_row, tab.E, tab.W, tab.S, self._mode())
         target = tab.q_target_long
         loss = self.loss_func(output, target)
-        acc = accuracy_percent(output, target)
+        acc = accuracy_percent(output, target, as_tensor=getattr(self, "acc_on_device", False))
         return output, acc, loss
 
     def get_uncertainty_threshold(self, policy="mean", normalize=False):

@@ -36,5 +36,5 @@ class DN4(MetricModel):
         output, _, _ = ops.dn4_scores(feat, tab.cls_row, tab.E, tab.W, tab.S, self.n_k)
         target = tab.q_target_long
         loss = self.loss_func(output, target)
-        acc = accuracy_percent(output, target)
+        acc = accuracy_percent(output, target, as_tensor=getattr(self, "acc_on_device", False))
         return output, acc, loss

@@ -158,5 +158,5 @@ class MAML(MetaModel):
         output = self._adapt_all(image, tab, sup_idx, qry_idx)
         target = tab.q_target_long
         loss = self.loss_func(output, target)
-        acc = accuracy_percent(output, target)
+        acc = accuracy_percent(output, target, as_tensor=getattr(self, "acc_on_device", False))
         return output, acc, loss

@@ -34,5 +34,5 @@ class MetaBaseline(MetricModel):
         output = ops.proto_logits(emb, tab.cls_row, tab.E, tab.W, tab.S, "cos_sim") * self.temp
         target = tab.q_target_long
         loss = self.loss_func(output, target)
-        acc = accuracy_percent(output, target)
+        acc = accuracy_percent(output, target, as_tensor=getattr(self, "acc_on_device", False))
         return output, acc, loss

@@ -13,9 +13,10 @@ from .. import ops
 from .abstract_model import MetricModel
 
 
-def accuracy_percent(output, target):
+def accuracy_percent(output, target, as_tensor=False):
     """utils.accuracy (libfewshot_core/utils/utils.py:84-121), top-1: percent as a Python float,
-    summed over ranks when torch.distributed is initialised."""
+    summed over ranks when torch.distributed is initialised.  as_tensor=True keeps the value on the
+    device (a 1-element tensor, no host sync) -- what a CUDA-graph-captured train step needs."""
     import torch.distributed as dist
 
     with torch.no_grad():
@@ -24,7 +25,8 @@ def accuracy_percent(output, target):
         if dist.is_available() and dist.is_initialized():
             dist.all_reduce(correct, op=dist.ReduceOp.SUM)
             n *= dist.get_world_size()
-        return correct.mul_(100.0 / n).item()
+        correct.mul_(100.0 / n)
+        return correct if as_tensor else correct.item()
 
 
 class ProtoNet(MetricModel):
@@ -50,5 +52,5 @@ class ProtoNet(MetricModel):
         output = ops.proto_logits(emb, tab.cls_row, tab.E, tab.W, tab.S, self.distance)
         target = tab.q_target_long
         loss = self.loss_func(output, target)
-        acc = accuracy_percent(output, target)
+        acc = accuracy_percent(output, target, as_tensor=getattr(self, "acc_on_device", False))
         return output, acc, loss

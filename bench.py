@@ -346,8 +346,9 @@ def run_b200(args, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "episodes_per_step_per_gpu": E, "clips_per_step_per_gpu": n_clips,
                    "way": W, "shot": S, "query": Q, "clip_samples": L, "n_fft": 1024, "hop": HOP, "n_mels": N_MELS,
-                   "backbone": "Conv64F eval path: fused conv1+BN+ReLU+pool kernel (fp32), cuDNN conv+bias+ReLU for "
-                               "blocks 2-4 (TF32 allowed, the reference's PyTorch default)",
+                   "backbone": "Conv64F eval path: tcgen05 TF32 kernels for block 1 (conv+BN+ReLU+pool) and blocks 2-3 "
+                               "(implicit GEMM+BN+ReLU+pool), cuDNN conv+bias+ReLU for block 4 (TF32 allowed, the "
+                               "reference's PyTorch default)",
                    "e2e_path": "EpisodePipeline.stream: H2D on a copy stream overlapped with compute, 2 buffers",
                    "l2_policy": "inputs larger than L2: %d MB of waveform per step, two rotating batches"
                                 % (wav_bytes // 2 ** 20),

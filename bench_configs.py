@@ -124,8 +124,15 @@ def main():
             opt.step()
 
         ms = timeit(step, max(3, args.steps // 4), 2)
-        emit("C5", "MAML/Conv64F 5w5s10q train step (5 inner steps, second order) + Adam", E, ms,
+        emit("C5", "MAML/Conv64F 5w5s10q train step (5 inner steps, second order) + Adam, eager launches", E, ms,
              "150 images per step; autograd through cuDNN (SURVEY a20)", 0)
+
+        from audio_fewshot_b200.graph_step import GraphedTrainStep
+        opt2 = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+        gstep = GraphedTrainStep(m, opt2, batches[0].shape, target=target)
+        ms = timeit(lambda i: gstep(batches[i % 2]), args.steps, 3)
+        emit("C5", "MAML/Conv64F 5w5s10q train step as ONE CUDA graph (GraphedTrainStep)", E, ms,
+             "same kernels and order as the eager step; launch path only", 0)
 
 
 if __name__ == "__main__":

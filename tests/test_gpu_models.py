@@ -474,3 +474,49 @@ def test_metabaseline_forward_and_cosine_backward_match_autograd_of_oracle(cuda)
     with torch.no_grad():
         out2, acc2 = m([torch.randn(n2, D), torch.zeros(n2), torch.from_numpy(rep), E * W * S])
     assert out2.shape == (int(rep.sum()), W) and 0.0 <= acc2.item() <= 100.0
+
+
+def test_graphed_train_step_matches_eager_maml(cuda):
+    """GraphedTrainStep (one CUDA graph for set_forward_loss + backward + Adam) reproduces the eager MAML step:
+    same loss sequence and the same parameters after three steps (Dropout disabled so both see the same masks)."""
+    import copy
+    from audio_fewshot_b200 import model as arch
+    from audio_fewshot_b200.graph_step import GraphedTrainStep
+    torch.manual_seed(3)
+    emb = arch.Conv64F(is_flatten=True, num_channels=1)
+    emb.logits[0].p = 0.0
+    kw = dict(way_num=3, shot_num=2, query_num=3, test_way=3, test_shot=2, test_query=3, device=cuda)
+    m1 = arch.MAML(inner_param={"lr": 0.01, "train_iter": 2, "test_iter": 2}, feat_dim=1600, emb_func=emb, **kw).to(cuda).train()
+    m2 = copy.deepcopy(m1)
+    E, W, S, Q = 2, 3, 2, 3
+    n = E * W * (S + Q)
+    target = torch.arange(W).repeat_interleave(S + Q).repeat(E)
+    batches = [torch.randn(n, 1, 128, 157, device=cuda) * 0.7 for _ in range(3)]
+    o1 = torch.optim.Adam(m1.parameters(), lr=1e-3)
+    o2 = torch.optim.Adam(m2.parameters(), lr=1e-3, capturable=True)
+    with pytest.raises(ValueError):
+        GraphedTrainStep(m2, torch.optim.Adam(m2.parameters(), lr=1e-3), batches[0].shape, target=target)
+    ref_state = copy.deepcopy(m2.state_dict())
+    step = GraphedTrainStep(m2, o2, batches[0].shape, target=target, warmup=1)
+    # the warm-up and the capture ran optimizer steps on zeros: restart both from the same point
+    m2.load_state_dict(ref_state)
+    for st in o2.state.values():
+        for k, v in st.items():
+            if torch.is_tensor(v):
+                v.zero_()
+    losses1, losses2 = [], []
+    for b in batches:
+        o1.zero_grad(set_to_none=True)
+        out, acc, loss = m1([b, target])
+        loss.backward()
+        o1.step()
+        losses1.append(float(loss))
+        out2, acc2, loss2 = step(b)
+        losses2.append(float(loss2))
+        # an untrained net scores near chance with near-tied logits: allow one query to flip (cuDNN may pick
+        # different TF32/fp32 algorithms under capture)
+        assert acc2.numel() == 1 and abs(float(acc2) - acc) <= 100.0 / (E * W * Q) + 1e-3
+    assert np.allclose(losses1, losses2, rtol=2e-3, atol=2e-4), (losses1, losses2)
+    for (k, a), (_, b2) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        if a.dtype.is_floating_point and "running" not in k:
+            assert (a - b2).abs().max().item() <= 3.5e-3, k  # three Adam steps of lr 1e-3 move a weight <= 3e-3
