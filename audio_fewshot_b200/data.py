@@ -12,11 +12,15 @@ not in the snapshot; what it must deliver is fixed by its call si
     clips are chopped into fixed windows and majority-voted, utils.py:436-446); `support_size` = E*W*S;
   * statistics come from `mean_std_file` = (2,1,1) [mean, std] (test.py:398-399).
 
-Three sources share one sampler:
+Four sources share one sampler:
   SyntheticWaveformEpisodes   seeded class-tone waveforms [rows, L] for the fused log-mel front-end
   SyntheticSpectrogramEpisodes  seeded [rows,1,128,157] images (front-end already applied / bypassed)
   SpectrogramFolderEpisodes   `<root>/<class>/*.npy` log-mel arrays [128, T] (the `*_spec` folders of
                               config/headers/data.yaml:1) with a class split (Auxiliary/KOS_paper_splits.npy)
+
+  WaveformFolderEpisodes      `<root>/<class>/*.wav` 16-bit PCM clips, served as int16 [rows, L] windows for
+                              afs_logmel_fwd_pcm16 (the step the reference did offline to build its `*_spec`
+                              folders), with the same support/query window protocol
 
 Everything random is keyed by the GLOBAL episode index, so a run is invariant to the world size.
 """
@@ -174,6 +178,76 @@ class SpectrogramFolderEpisodes(_EpisodeLoader):
         return self._finish(np.concatenate(rows, axis=0), np.asarray(target), np.asarray(repeats))
 
 
+def read_wav_pcm16(path):
+    """Mono int16 samples and the sample rate of a 16-bit PCM .wav file (multi-channel files: first channel)."""
+    import wave
+
+    with wave.open(path, "rb") as w:
+        if w.getsampwidth() != 2:
+            raise ValueError("%s: only 16-bit PCM wav files are supported (sample width %d)" % (path, w.getsampwidth()))
+        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+        if w.getnchannels() > 1:
+            pcm = pcm.reshape(-1, w.getnchannels())[:, 0]
+        return np.ascontiguousarray(pcm), w.getframerate()
+
+
+def window_waveform(pcm, n_samples):
+    """[T] -> [k, n_samples]: consecutive windows, the last one right-aligned (zero-padded when the clip is
+    shorter than one window) -- window_spectrogram's protocol in the sample domain."""
+    T = pcm.shape[0]
+    if T <= n_samples:
+        out = np.zeros((1, n_samples), dtype=pcm.dtype)
+        out[0, :T] = pcm
+        return out
+    k = -(-T // n_samples)
+    starts = [min(i * n_samples, T - n_samples) for i in range(k)]
+    return np.stack([pcm[s:s + n_samples] for s in starts])
+
+
+class WaveformFolderEpisodes(_EpisodeLoader):
+    """`root/<class>/*.wav` 16-bit PCM clips -> `image` = int16 waveform windows [rows, n_samples] for the fused
+    log-mel front-end (LogMelFrontEnd accepts int16 and converts on load: pcm / 32768).  Supports use their first
+    window; queries are chopped into all their windows and `repeats` records how many."""
+
+    def __init__(self, sampler, root, classes, way, shot, query, n_samples=80000, sample_rate=16000, pin=True):
+        super().__init__(sampler, way, shot, query, pin)
+        self.n_samples, self.sample_rate = int(n_samples), int(sample_rate)
+        self.files = {}
+        for c in classes:
+            d = os.path.join(root, str(c))
+            fs = sorted(f for f in os.listdir(d) if f.lower().endswith(".wav")) if os.path.isdir(d) else []
+            if len(fs) >= shot + query:
+                self.files[str(c)] = [os.path.join(d, f) for f in fs]
+        self.classes = sorted(self.files)
+        if len(self.classes) < way:
+            raise ValueError("only %d classes with >= %d clips under %s" % (len(self.classes), shot + query, root))
+        self.class_id = {c: i for i, c in enumerate(self.classes)}
+
+    def _load(self, path):
+        pcm, sr = read_wav_pcm16(path)
+        if sr != self.sample_rate:
+            raise ValueError("%s: sample rate %d, expected %d (resample offline)" % (path, sr, self.sample_rate))
+        return pcm
+
+    def batch(self, b):
+        E, W, S, Q = self.sampler.episode_size, self.way, self.shot, self.query
+        rows, target, repeats = [], [], []
+        for e in range(E):
+            r = self.sampler.rng(b, e)
+            for c in r.choice(len(self.classes), size=W, replace=False):
+                name = self.classes[int(c)]
+                picks = r.choice(len(self.files[name]), size=S + Q, replace=False)
+                for i, p in enumerate(picks):
+                    win = window_waveform(self._load(self.files[name][int(p)]), self.n_samples)
+                    if i < S:
+                        win = win[:1]
+                    else:
+                        repeats.append(win.shape[0])
+                    rows.append(win)
+                    target.extend([self.class_id[name]] * win.shape[0])
+        return self._finish(np.concatenate(rows, axis=0), np.asarray(target), np.asarray(repeats))
+
+
 def load_class_split(path, mode):
     """Auxiliary/KOS_paper_splits.npy: object array [train, val, test] of class-name lists."""
     arr = np.load(path, allow_pickle=True)
@@ -205,7 +279,12 @@ def get_dataloader(config, mode, model_type=None, distribute=False, modality="au
             classes = (load_class_split(config["class_per_split"], mode) if config.get("class_per_split")
                        else sorted(os.listdir(root)))
             mean, std = get_mean_std(config) if config.get("mean_std_file") else (0.0, 1.0)
-            loaders.append(SpectrogramFolderEpisodes(sampler, root, classes, way, shot, query, mean, std))
+            if config.get("data_format") == "wav":  # raw 16-bit clips: the log-mel front-end runs on the GPU
+                loaders.append(WaveformFolderEpisodes(sampler, root, classes, way, shot, query,
+                                                      n_samples=int(config.get("audio_samples", 80000)),
+                                                      sample_rate=int(config.get("sample_rate", 16000))))
+            else:
+                loaders.append(SpectrogramFolderEpisodes(sampler, root, classes, way, shot, query, mean, std))
         elif config.get("synthetic_waveform"):
             loaders.append(SyntheticWaveformEpisodes(sampler, way, shot, query,
                                                      n_samples=int(config.get("audio_samples", 80000))))

@@ -110,3 +110,39 @@ def test_synthetic_waveform_loader_matches_bench_recipe():
     assert wav.shape == (2 * 5 * 3, 4000) and support_size == 10 and repeats.tolist() == [1] * 20
     spec = np.abs(np.fft.rfft(wav[3 * 2].numpy()))  # class 2 -> 600 Hz tone
     assert abs(np.argmax(spec[10:]) + 10 - 600 * 4000 / 16000) <= 1
+
+
+def test_wav_folder_loader_serves_pcm16_windows(tmp_path):
+    """`data_format: wav` -> int16 [rows, L] windows (first window for supports, all windows + repeats for queries)
+    that LogMelFrontEnd consumes directly (afs_logmel_fwd_pcm16)."""
+    import wave
+    from audio_fewshot_b200.data import get_dataloader, read_wav_pcm16, window_waveform
+    rng = np.random.default_rng(3)
+    names = ["dog", "cat", "owl", "bat", "fox"]
+    written = {}
+    for c in names:
+        os.makedirs(tmp_path / "wav" / c)
+        for i in range(3):
+            n = int(rng.integers(2000, 9000))
+            pcm = rng.integers(-20000, 20000, size=n).astype("<i2")
+            path = str(tmp_path / "wav" / c / ("%d.wav" % i))
+            with wave.open(path, "wb") as w:
+                w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+                w.writeframes(pcm.tobytes())
+            written[path] = pcm
+    p0 = sorted(written)[0]
+    got, sr = read_wav_pcm16(p0)
+    assert sr == 16000 and got.dtype == np.int16 and np.array_equal(got, written[p0])
+    cfg = dict(way_num=5, shot_num=1, query_num=2, test_way=5, test_shot=1, test_query=2, train_episode=2,
+               test_episode=2, episode_size=1, data_root=str(tmp_path / "wav"), data_format="wav", audio_samples=4000)
+    (loader,) = get_dataloader(cfg, "test")
+    wav, target, repeats, support_size = next(iter(loader))
+    assert wav.dtype == torch.int16 and wav.shape == (5 + int(repeats.sum()), 4000)
+    assert support_size == 5 and repeats.numel() == 10 and repeats.max() >= 2 and target.shape[0] == wav.shape[0]
+    w = window_waveform(np.arange(9000, dtype=np.int16), 4000)
+    assert w.shape == (3, 4000) and w[2, -1] == 8999 and w[1, 0] == 4000
+    assert window_waveform(np.ones(100, np.int16), 4000).shape == (1, 4000)
+    with wave.open(str(tmp_path / "bad.wav"), "wb") as w8:
+        w8.setnchannels(1); w8.setsampwidth(1); w8.setframerate(16000); w8.writeframes(b"\x00" * 10)
+    with pytest.raises(ValueError):
+        read_wav_pcm16(str(tmp_path / "bad.wav"))
