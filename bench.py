@@ -7,14 +7,15 @@ Workload (BASELINE.json `metric`; SURVEY.md 8d, config C1 = config/proto_5shot_i
 Conv64F, 5w5s15q = 100 clips per episode, each clip 5 s @ 16 kHz (L = 80 000) -> log-mel [1,128,157]
 (n_fft 1024, hop 512, 128 slaney mels, KOS_0.5_alpha mean/std).  One "step" = one pass of the hot path
 over `--episodes-per-step` episodes per rank:
-    fused log-mel kernel -> Conv64F (fused conv1 kernel + cuDNN blocks 2-4) -> prototype head kernel ->
-    vote/accuracy kernel.
+    fused log-mel kernel -> Conv64F (tcgen05 block-1 and block-2/3 kernels, cuDNN block 4) -> prototype head
+    kernel -> vote/accuracy kernel.
 Episodes are independent, so ranks never exchange data inside a step ("weak" scaling: per-GPU work is
 fixed).  Synthetic seeded waveforms, weights derived from parameter names (oracle.cases.perturb_bn_).
 
 `value`  : device-resident inputs (two rotating batches, each larger than L2).
 `e2e`    : the public call EpisodePipeline.stream(pinned host batches) -- every step's H2D of the waveforms
            and D2H of the logits + accuracy inside the timed region (copies overlap compute).
+`e2e_pcm16`: the same call with the host waveforms as 16-bit PCM (extra key; `e2e` is the fp32-host figure).
 `roofline`: the fused log-mel kernel (our dominant kernel), algorithmic bytes 4*L + 4*128*T per clip over
            its CUDA-event duration measured inside the timed region, against MEASURED_PEAKS.json.
 `cpu_baseline` / `--impl reference`: the oracle port of the reference path (torch.stft front-end spec ->
@@ -51,7 +52,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--episodes-per-step", type=int, default=8, help="episodes per rank per step")
+    ap.add_argument("--episodes-per-step", type=int, default=32, help="episodes per rank per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bound of the cpu_baseline sample")
     return ap.parse_args()
@@ -336,7 +337,8 @@ def run_b200(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "logmel_traffic.json")  # written from an ncu --set full capture
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))  # captured at `clips_per_launch` clips; DRAM bytes scale with the clip count
+            traffic = tj["dram_bytes_per_launch"] / tj["clips_per_launch"] * n_clips
         except Exception:
             traffic = None
 
