@@ -516,7 +516,10 @@ def test_graphed_train_step_matches_eager_maml(cuda):
         # an untrained net scores near chance with near-tied logits: allow one query to flip (cuDNN may pick
         # different TF32/fp32 algorithms under capture)
         assert acc2.numel() == 1 and abs(float(acc2) - acc) <= 100.0 / (E * W * Q) + 1e-3
-    assert np.allclose(losses1, losses2, rtol=2e-3, atol=2e-4), (losses1, losses2)
+    # step 1 sees identical weights; afterwards Adam's first updates are ~lr*sign(g), which amplifies the
+    # run-to-run rounding differences of cuDNN's backward kernels, so later losses are compared more loosely
+    for l1, l2, tol in zip(losses1, losses2, (1e-4, 2e-3, 3e-2)):
+        assert abs(l1 - l2) <= tol * abs(l1), (losses1, losses2)
     for (k, a), (_, b2) in zip(m1.state_dict().items(), m2.state_dict().items()):
         if a.dtype.is_floating_point and "running" not in k:
             assert (a - b2).abs().max().item() <= 3.5e-3, k  # three Adam steps of lr 1e-3 move a weight <= 3e-3
