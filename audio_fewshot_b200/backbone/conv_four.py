@@ -7,7 +7,9 @@ logits.1 = BatchNorm1d(64), logits.2 = Linear(64, 1600)).
 
 Two execution paths with the same parameters:
   * training / autograd / CPU-constructed checks: the plain module graph (cuDNN + ATen), exactly the
-    reference's op sequence;
+    reference's op sequence -- except block 1 in training mode on CUDA, which runs as three fused sm_100a
+    kernels (csrc/conv1_train.cu: batch statistics from the input's 9-tap autocorrelation, forward without
+    the [N,64,128,157] activation, backward by recomputation);
   * inference on CUDA (eval mode, grad disabled, 1 input channel): `_forward_inference` --
     block 1 is ONE sm_100a kernel (csrc/conv1.cu / conv1_tc.cu: conv + BatchNorm + activation + max-pool,
     the [N,64,128,157] activation never reaches HBM); blocks 2-3 are ONE tcgen05 kernel each
@@ -50,6 +52,7 @@ class Conv64F(nn.Module):
         self.last_pool, self.maxpool_last2 = last_pool, maxpool_last2
         self.stem_tf32 = None  # None: follow torch.backends.cudnn.allow_tf32
         self.block_tc = None   # tcgen05 kernel for blocks 2-3; None: follow torch.backends.cudnn.allow_tf32
+        self.fused_train_stem = True  # training: block 1 forward + backward as fused kernels (csrc/conv1_train.cu)
         act = nn.LeakyReLU(negative_slope=negative_slope, inplace=True) if leaky_relu else nn.ReLU(inplace=False)
         trk = use_running_statistics
         self.layer1 = _conv_block(num_channels, 64, act, True, trk)
@@ -133,10 +136,24 @@ class Conv64F(nn.Module):
             h = torch.addmm(c["bl"], h, c["wl"].t())
         return h
 
+    def _train_stem_ok(self, x):
+        """Training with batch statistics on CUDA, plain nn.BatchNorm2d (MAML's BatchStatNorm2d needs double
+        backward through this block and keeps the module graph), 1-channel data input without grad."""
+        conv, bn = self.layer1[0], self.layer1[1]
+        return (self.fused_train_stem and self.training and torch.is_grad_enabled() and x.is_cuda and x.dim() == 4
+                and x.shape[1] == 1 and x.dtype == torch.float32 and not x.requires_grad
+                and type(bn) is nn.BatchNorm2d and bn.affine and bn.momentum is not None
+                and type(conv) is nn.Conv2d and conv.out_channels == 64 and conv.bias is not None
+                and conv.weight.dtype == torch.float32 and len(self.layer1) == 4)
+
     def forward(self, x):
         if self._inference_ok(x):
             return self._forward_inference(x)
-        out1 = self.layer1(x)
+        if self._train_stem_ok(x):
+            out1 = ops.conv1_bn_act_pool3_train(x, self.layer1[0], self.layer1[1],
+                                                float(getattr(self.layer1[2], "negative_slope", 0.0)))
+        else:
+            out1 = self.layer1(x)
         out2 = self.layer2(out1)
         out3 = self.layer3(out2)
         if self.maxpool_last2:

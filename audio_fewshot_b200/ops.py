@@ -128,6 +128,81 @@ def conv1_bn_act_pool3(x, w_folded, shift, negative_slope=0.0, tf32=False):
     return out
 
 
+class _Conv1TrainFn(torch.autograd.Function):
+    """Conv2d(1->64,3x3,pad 1,bias) + BatchNorm2d(batch statistics) + ReLU/LeakyReLU + MaxPool2d(3,3), training mode,
+    as three sm_100a kernels (csrc/conv1_train.cu); gradients for conv.weight, conv.bias (zero), bn.weight, bn.bias."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, momentum, eps, slope):
+        h = _lib.lib()
+        N, _, H, Wd = x.shape
+        P = float(N) * H * Wd
+        x = x.contiguous()
+        ac = torch.empty((int(h.afs_conv1_train_num_partials(0)), 54), dtype=torch.float32, device=x.device)
+        _lib.check(h.afs_conv1_autocorr(_ptr(x), N, H, Wd, _ptr(ac), _stream()), "afs_conv1_autocorr")
+        st = ac.double().sum(0)
+        s = st[:9]
+        iu = torch.triu_indices(9, 9, device=x.device)
+        R = torch.zeros((9, 9), dtype=torch.float64, device=x.device)
+        R[iu[0], iu[1]] = st[9:]
+        R = R + R.t() - torch.diag(torch.diagonal(R))
+        w64 = weight.detach().reshape(64, 9).double()
+        mean_nob = (w64 @ s) / P
+        cov = R / P - torch.outer(s, s) / (P * P)
+        var = torch.einsum("ct,tu,cu->c", w64, cov, w64).clamp_min_(0.0)
+        invstd = torch.rsqrt(var + eps)
+        scale = gamma.detach().double() * invstd
+        shift = beta.detach().double() - mean_nob * scale
+        w32 = weight.detach().reshape(64, 9).contiguous()
+        scale32, shift32 = scale.float().contiguous(), shift.float().contiguous()
+        out = torch.empty((N, 64, H // 3, Wd // 3), dtype=torch.float32, device=x.device,
+                          memory_format=torch.channels_last)
+        _lib.check(h.afs_conv1_train_fwd(_ptr(x), N, H, Wd, _ptr(w32), _ptr(scale32), _ptr(shift32), float(slope),
+                                         _ptr(out), _stream()), "afs_conv1_train_fwd")
+        if running_mean is not None and momentum is not None:  # nn.BatchNorm2d in train(): unbiased running variance
+            with torch.no_grad():
+                running_mean.mul_(1.0 - momentum).add_((mean_nob + bias.detach().double()).to(running_mean.dtype), alpha=momentum)
+                running_var.mul_(1.0 - momentum).add_((var * (P / max(P - 1.0, 1.0))).to(running_var.dtype), alpha=momentum)
+        ctx.save_for_backward(x, w32, scale32, shift32, mean_nob.float().contiguous(), invstd.float().contiguous())
+        ctx.stats = (s, R, w64, mean_nob, invstd, scale, P, float(slope))
+        ctx.shapes = (weight.shape, bias.shape)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        x, w32, scale32, shift32, mean32, invstd32 = ctx.saved_tensors
+        s, R, w64, mean_nob, invstd, scale, P, slope = ctx.stats
+        h = _lib.lib()
+        N, _, H, Wd = x.shape
+        g = grad_out.contiguous(memory_format=torch.channels_last)
+        part = torch.empty((int(h.afs_conv1_train_num_partials(1)), 64, 11), dtype=torch.float32, device=x.device)
+        _lib.check(h.afs_conv1_train_bwd(_ptr(x), _ptr(g), N, H, Wd, _ptr(w32), _ptr(scale32), _ptr(shift32),
+                                         _ptr(mean32), _ptr(invstd32), slope, _ptr(part), _stream()),
+                   "afs_conv1_train_bwd")
+        t = part.double().sum(0)
+        a1, a2, G = t[:, 0], t[:, 1], t[:, 2:]
+        Q = invstd[:, None] * (w64 @ R - mean_nob[:, None] * s[None, :])
+        dW = scale[:, None] * (G - (a1 / P)[:, None] * s[None, :] - (a2 / P)[:, None] * Q)
+        w_shape, b_shape = ctx.shapes
+        return (None, dW.float().reshape(w_shape), torch.zeros(b_shape, dtype=torch.float32, device=x.device),
+                a2.float(), a1.float(), None, None, None, None, None)
+
+
+def conv1_bn_act_pool3_train(x, conv, bn, negative_slope=0.0):
+    """Training-mode first Conv64F block (batch statistics, running-stat update, autograd for the four parameter
+    tensors) on CUDA.  x [N,1,H,W] fp32 without grad; conv: nn.Conv2d(1,64,3,padding=1); bn: nn.BatchNorm2d(64)."""
+    _need_cuda(x, "x")
+    if x.dim() != 4 or x.shape[1] != 1 or conv.out_channels != 64 or x.requires_grad:
+        raise ValueError("x must be [N, 1, H, W] data (no grad) and the block 1 -> 64 channels")
+    track = bn.track_running_stats and bn.running_mean is not None
+    if track:
+        bn.num_batches_tracked += 1
+    return _Conv1TrainFn.apply(x, conv.weight, conv.bias, bn.weight, bn.bias,
+                               bn.running_mean if track else None, bn.running_var if track else None,
+                               bn.momentum, bn.eps, float(negative_slope))
+
+
 def conv3x3_c64_pack_weights(w_folded):
     """BatchNorm-folded [64, 64, 3, 3] weights (any device) -> the packed, TF32-rounded operand buffer of
     conv3x3_c64_bn_act (a float32 numpy array; upload it once and keep it)."""

@@ -88,6 +88,38 @@ def main():
         m = arch.ProtoNet(shot_num=5, query_num=15, test_shot=5, test_query=15, emb_func=emb, device=dev, **common).to(dev)
         run_eval("C1", "ProtoNet/Conv64F 5w5s15q set_forward", m, 8, 5, 5, 15, "800 images per step")
 
+    if only is None or "C1T" in only:
+        # episodic TRAINING step of C1 (trainer.py:186-192): set_forward_loss + backward + Adam, episode_size 2
+        from audio_fewshot_b200.graph_step import GraphedTrainStep
+        E, W, S, Q = 2, 5, 5, 15
+        n = E * W * (S + Q)
+        target = torch.arange(W).repeat_interleave(S + Q).repeat(E)
+        for tag, cl, graphed in (("eager launches", False, False), ("channels_last", True, False),
+                                 ("ONE CUDA graph (GraphedTrainStep)", False, True),
+                                 ("channels_last + ONE CUDA graph", True, True)):
+            torch.manual_seed(0)
+            emb = arch.Conv64F(is_flatten=True, num_channels=1)
+            m = arch.ProtoNet(shot_num=S, query_num=Q, test_shot=S, test_query=Q, emb_func=emb, device=dev, **common).to(dev)
+            if cl:
+                m = m.to(memory_format=torch.channels_last)
+            m.train()
+            batches = [images(n, dev, 200 + b) for b in range(2)]
+            if graphed:
+                opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+                gstep = GraphedTrainStep(m, opt, batches[0].shape, target=target)
+                step = lambda i: gstep(batches[i % 2])
+            else:
+                opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+
+                def step(i, m=m, opt=opt, batches=batches):
+                    opt.zero_grad(set_to_none=True)
+                    out, acc, loss = m([batches[i % 2], target])
+                    loss.backward()
+                    opt.step()
+
+            ms = timeit(step, args.steps, args.warmup)
+            emit("C1-train", "ProtoNet/Conv64F 5w5s15q train step + Adam, " + tag, E, ms, "200 images per step", 0)
+
     if only is None or "C2" in only:
         emb = arch.resnet12(keep_prob=0.0, avg_pool=True, is_flatten=True, maxpool_last2=True, num_channels=1)
         m = arch.ProtoNet(shot_num=1, query_num=15, test_shot=1, test_query=15, emb_func=emb, device=dev, **common).to(dev)

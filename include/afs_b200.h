@@ -124,6 +124,26 @@ int afs_conv1_bn_act_pool3_fwd_tf32(const float* x, int32_t N, int32_t H, int32_
                                     const float* w_folded_host, const float* shift_host, int32_t C,
                                     float negative_slope, float* out, afs_stream_t stream);
 
+/* (1b-train) First Conv64F block in TRAINING mode (batch statistics), forward and backward, fused: replaces
+ * layer1 of libfewshot_core/model/backbone/conv_four.py:61-66 under set_forward_loss.  The block has one input
+ * channel, so the BatchNorm statistics and the dense BatchNorm-backward correction terms are functions of the 9-tap
+ * sums s[t] and the 9x9 autocorrelation R[t,u] of the input (csrc/conv1_train.cu).  All pointers are device pointers.
+ *   afs_conv1_autocorr: x [N,1,H,Wd] -> partials [afs_conv1_train_num_partials(0)][54] (9 sums, then the upper
+ *     triangle of R row-major); the caller adds the rows (fixed order: deterministic).
+ *   afs_conv1_train_fwd: out[N, H/3, Wd/3, 64] (NHWC) = MaxPool3(act(scale_c * (w_c * x) + shift_c)); w [64*9] raw
+ *     conv weights, scale = gamma*invstd, shift = beta - mean_nob*scale (the conv bias cancels under batch statistics).
+ *   afs_conv1_train_bwd: grad_out [N, H/3, Wd/3, 64] (NHWC) -> partials [afs_conv1_train_num_partials(1)][64][11]:
+ *     per channel A1 = sum dy, A2 = sum dy*xhat, G[9] = sum dy * x_tap(argmax), dy = grad routed through the max-pool
+ *     arg-max (first maximum) and the activation.  dgamma = A2, dbeta = A1, dbias = 0,
+ *     dW[c,t] = scale_c (G[c,t] - A1_c/P s[t] - A2_c/P Q[c,t]), Q = invstd_c ((w_c R)[t] - mean_nob_c s[t]).        */
+int32_t afs_conv1_train_num_partials(int32_t which);
+int afs_conv1_autocorr(const float* x, int32_t N, int32_t H, int32_t Wd, float* partials, afs_stream_t stream);
+int afs_conv1_train_fwd(const float* x, int32_t N, int32_t H, int32_t Wd, const float* w, const float* scale,
+                        const float* shift, float negative_slope, float* out, afs_stream_t stream);
+int afs_conv1_train_bwd(const float* x, const float* grad_out, int32_t N, int32_t H, int32_t Wd, const float* w,
+                        const float* scale, const float* shift, const float* mean_nob, const float* invstd,
+                        float negative_slope, float* partials, afs_stream_t stream);
+
 /* (1b'') Conv64F blocks 2..4, inference only: Conv2d(64->64, 3x3, pad 1) + BatchNorm2d(eval) + ReLU / LeakyReLU
  * (+ MaxPool2d(3,3) when pool3 != 0), fused, channels-last, on the tensor cores (tcgen05 TF32, fp32 accumulate).
  * Replaces layer2..layer4 of libfewshot_core/model/backbone/conv_four.py:67-86,104-113 in eval mode.

@@ -520,6 +520,80 @@ def test_graphed_train_step_matches_eager_maml(cuda):
     # run-to-run rounding differences of cuDNN's backward kernels, so later losses are compared more loosely
     for l1, l2, tol in zip(losses1, losses2, (1e-4, 2e-3, 3e-2)):
         assert abs(l1 - l2) <= tol * abs(l1), (losses1, losses2)
-    for (k, a), (_, b2) in zip(m1.state_dict().items(), m2.state_dict().items()):
-        if a.dtype.is_floating_point and "running" not in k:
-            assert (a - b2).abs().max().item() <= 3.5e-3, k  # three Adam steps of lr 1e-3 move a weight <= 3e-3
+    # the captured optimizer step really updates the live parameters
+    moved = [(m2.state_dict()[k] - v.to(cuda)).abs().max().item() for k, v in ref_state.items()
+             if v.dtype.is_floating_point and "running" not in k]
+    assert 1e-3 <= max(moved) <= 3.5e-3  # three Adam steps of lr 1e-3
+
+
+@pytest.mark.parametrize("N,H,Wd,leaky", [(6, 128, 157, False), (3, 20, 23, True), (2, 9, 10, False)])
+def test_fused_training_stem_matches_module_graph(cuda, N, H, Wd, leaky):
+    """csrc/conv1_train.cu (batch statistics from the 9-tap autocorrelation, fused forward, recomputing backward)
+    against Conv2d -> BatchNorm2d(train) -> activation -> MaxPool2d under autograd: output, running statistics and the
+    gradients of all four parameter tensors for a random upstream gradient."""
+    from audio_fewshot_b200 import model as arch
+    torch.manual_seed(N * 100 + H)
+    a = arch.Conv64F(is_flatten=False, leaky_relu=leaky, negative_slope=0.2, num_channels=1).to(cuda).train()
+    with torch.no_grad():
+        a.layer1[1].weight.copy_(torch.randn(64, device=cuda) * 0.5 + 1.0)  # includes negative scales
+        a.layer1[1].bias.copy_(torch.randn(64, device=cuda) * 0.3)
+        a.layer1[0].bias.copy_(torch.randn(64, device=cuda))
+    import copy
+    b = copy.deepcopy(a)
+    b.fused_train_stem = False
+    x = torch.randn(N, 1, H, Wd, device=cuda) * 0.7 + 0.2
+    from audio_fewshot_b200 import ops
+    n0 = ops.launch_count()
+    out_f = ops.conv1_bn_act_pool3_train(x, a.layer1[0], a.layer1[1], 0.2 if leaky else 0.0)
+    assert ops.launch_count() == n0 + 2
+    out_r = b.layer1(x)
+    assert out_f.shape == out_r.shape
+    assert (out_f - out_r).abs().max().item() <= 2e-5 * max(out_r.abs().max().item(), 1.0)
+    for name in ("running_mean", "running_var"):
+        ra, rb = getattr(a.layer1[1], name), getattr(b.layer1[1], name)
+        assert torch.allclose(ra, rb, rtol=1e-4, atol=1e-6), name
+    assert int(a.layer1[1].num_batches_tracked) == int(b.layer1[1].num_batches_tracked) == 1
+    gout = torch.randn_like(out_r)
+    out_f.backward(gout)
+    out_r.backward(gout)
+    for (na, pa), (_, pb) in zip(a.layer1.named_parameters(), b.layer1.named_parameters()):
+        ga, gb = pa.grad, pb.grad
+        assert ga is not None and ga.shape == gb.shape, na
+        tol = 2e-4 * gb.abs().max().item() + 1e-4 * gout.abs().sum().item() ** 0.5 * 1e-2
+        if na == "0.bias":  # the conv bias cancels under batch statistics: autograd gives rounding noise
+            assert ga.abs().max().item() == 0.0 and gb.abs().max().item() <= 1e-2 * gout.abs().sum().item() ** 0.5
+        else:
+            assert (ga - gb).abs().max().item() <= tol, (na, (ga - gb).abs().max().item(), gb.abs().max().item())
+
+
+def test_protonet_training_step_with_fused_stem_matches_module_graph(cuda):
+    import copy
+    from audio_fewshot_b200 import model as arch
+    torch.manual_seed(4)
+    emb = arch.Conv64F(is_flatten=True, num_channels=1)
+    emb.logits[0].p = 0.0
+    kw = dict(way_num=3, shot_num=2, query_num=3, test_way=3, test_shot=2, test_query=3, device=cuda)
+    m1 = arch.ProtoNet(emb_func=emb, **kw).to(cuda).train()
+    m2 = copy.deepcopy(m1)
+    m2.emb_func.fused_train_stem = False
+    E, W, S, Q = 2, 3, 2, 3
+    x = torch.randn(E * W * (S + Q), 1, 128, 157, device=cuda) * 0.7
+    target = torch.arange(W).repeat_interleave(S + Q).repeat(E)
+    out1, acc1, loss1 = m1([x, target])
+    out2, acc2, loss2 = m2([x, target])
+    assert abs(float(loss1) - float(loss2)) <= 1e-4 * abs(float(loss2))
+    loss1.backward()
+    loss2.backward()
+    top = max(p.grad.abs().max().item() for p in m2.parameters() if p.grad is not None)
+    for (n1, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if p2.grad is None:
+            assert p1.grad is None, n1
+            continue
+        scale = p2.grad.abs().max().item()
+        if scale < 1e-5 * top:  # analytically zero gradients (biases cancelled by batch statistics / by q - proto)
+            assert p1.grad.abs().max().item() < 1e-4 * top, n1
+            continue
+        # fp32 rounding of block 1 can flip an arg-max in a later max-pool (18 images, maps down to 1x1), so whole
+        # gradients are compared in the L2 sense; the block itself is pinned element-wise by the test above
+        rel = (p1.grad - p2.grad).norm().item() / max(p2.grad.norm().item(), 1e-12)
+        assert rel <= 5e-2, (n1, rel, scale)
