@@ -27,7 +27,11 @@
 //   warps 0-3  epilogue: tcgen05.ld 8 channels at a time, + folded shift, activation, then either a direct
 //              channels-last store or the 3x3/3 max-pool through a small shared staging tile.
 // All 64x64x9 folded weights stay resident in shared memory (144 KB, pre-packed and TF32-rounded on the host).
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -114,6 +118,147 @@ struct Conv3Geom {
   float slope;
 };
 
+// ---- pieces shared by the one-CTA and the CTA-pair kernel --------------------------------------------------------
+
+// One tile's copy plan of a producer thread: thread pair (2j, 2j+1) copies the two 16-byte halves of one pixel's
+// 8-channel group, so a warp reads 16 whole 32-byte sectors and writes 512 contiguous shared-memory bytes per
+// instruction.  dst already carries the 32-byte swizzle (16-byte chunk index ^= bit 2 of the pixel index).
+struct ProducerPlan {
+  const float* src[kMaxPix3];
+  uint32_t dst[kMaxPix3], nbytes[kMaxPix3];
+
+  __device__ __forceinline__ void setup(const float* x, const Conv3Geom& g, int ptid, int n, int y0) {
+    const int half = ptid & 1;
+#pragma unroll
+    for (int i = 0; i < kMaxPix3; ++i) {
+      const int h = (ptid >> 1) + 64 * i;  // padded pixel index inside the tile's run
+      const int hr = h / g.HP, hc = h - hr * g.HP;
+      const int y = y0 - 1 + hr, xx = hc - 1;
+      const bool ok = h < g.halo && hr <= g.R + 1 && y >= 0 && y < g.H && xx >= 0 && xx < g.W;
+      src[i] = (ok ? x + ((static_cast<int64_t>(n) * g.H + y) * g.W + xx) * kC3 : x) + half * 4;
+      nbytes[i] = ok ? 16u : 0u;   // 0 -> the 16 destination bytes are zero-filled (padding)
+      dst[i] = static_cast<uint32_t>(h) * 32u + ((static_cast<uint32_t>(half) ^ ((static_cast<uint32_t>(h) >> 2) & 1u)) << 4);
+    }
+  }
+  __device__ __forceinline__ void issue(uint32_t stage_addr, int kc, int ptid, int halo) const {
+#pragma unroll
+    for (int i = 0; i < kMaxPix3; ++i) {
+      if ((ptid >> 1) + 64 * i < halo) cp_async16(stage_addr + dst[i], src[i] + kc * 8, nbytes[i]);
+    }
+    cp_async_commit();
+  }
+};
+
+// Producer loop over this CTA's tiles.  RING stages, at most AHEAD of them in flight before the oldest is handed
+// over; a thread that is about to block on a slot the tensor core still reads first hands over everything it has in
+// flight.  next_tile(j) returns the j-th tile of this CTA or -1.
+template <int RING, int AHEAD, class NextTile>
+__device__ __forceinline__ void producer_loop(const float* x, const Conv3Geom& g, int ptid, int lane, uint32_t ring_base,
+                                              uint32_t stage_bytes, uint64_t* full, uint64_t* empty, NextTile next_tile) {
+  uint32_t gs = 0;       // stages issued so far (all tiles)
+  uint32_t pending = 0;  // issued, not yet signalled: stages gs - pending .. gs - 1
+  for (int j = 0;; ++j) {
+    const int tile = next_tile(j);
+    if (tile < 0) break;
+    const int n = tile / g.tiles_per_img;
+    const int y0 = (tile - n * g.tiles_per_img) * g.R;
+    ProducerPlan plan;
+    plan.setup(x, g, ptid, n, y0);
+#pragma unroll 1
+    for (int kc = 0; kc < 8; ++kc, ++gs) {
+      const uint32_t st = gs % RING, ph = (gs / RING) & 1u;
+      uint32_t ready = lane == 0 ? (mbar_test(smem_u32(&empty[st]), ph ^ 1u) ? 1u : 0u) : 0u;
+      ready = __shfl_sync(0xffffffffu, ready, 0);
+      if (pending > 0 && !ready) {
+        cp_async_wait<0>();
+        fence_async_smem();
+        for (; pending > 0; --pending) mbar_arrive3(smem_u32(&full[(gs - pending) % RING]));
+      }
+      if (!ready) mbar_wait_warp(smem_u32(&empty[st]), ph ^ 1u, lane);
+      plan.issue(ring_base + st * stage_bytes, kc, ptid, g.halo);
+      ++pending;
+      if (pending > static_cast<uint32_t>(AHEAD)) {
+        cp_async_wait<AHEAD>();
+        fence_async_smem();
+        mbar_arrive3(smem_u32(&full[(gs + 1 - pending) % RING]));
+        --pending;
+      }
+    }
+  }
+  cp_async_wait<0>();
+  fence_async_smem();
+  for (; pending > 0; --pending) mbar_arrive3(smem_u32(&full[(gs - pending) % RING]));
+}
+
+// Epilogue of one tile by the four epilogue warps (accumulator row == TMEM lane == tid): tcgen05.ld 8 channels at a
+// time, + folded shift, activation, then a direct channels-last store or the 3x3/3 max-pool through the staging tile.
+// release() is called once per warp as soon as the accumulator set has been read completely.
+template <int NM, class Release>
+__device__ __forceinline__ void epilogue_tile(const Conv3Geom& g, int n, int y0, bool store, uint32_t d0, float* s_stage,
+                                              const float* s_shift, float* __restrict__ out, int tid, Release release) {
+#pragma unroll 1
+  for (int cg = 0; cg < kC3 / kCg3; ++cg) {
+    uint32_t v[NM][kCg3];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) tmem_ld8(d0 + m * kC3 + cg * kCg3, v[m]);
+    tmem_wait_ld();
+    if (cg == kC3 / kCg3 - 1) {  // every value of this accumulator set is in registers: hand it back
+      fence_before();
+      __syncwarp();
+      release();
+    }
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      float r[kCg3];
+#pragma unroll
+      for (int j = 0; j < kCg3; ++j) {
+        const float a = __uint_as_float(v[m][j]) + s_shift[cg * kCg3 + j];
+        r[j] = a > 0.f ? a : a * g.slope;
+      }
+      const int q = m * 128 + tid;  // linear position inside the tile
+      if (g.pool) {
+        float4* d = reinterpret_cast<float4*>(s_stage + q * kStagePitch);
+        d[0] = make_float4(r[0], r[1], r[2], r[3]);
+        d[1] = make_float4(r[4], r[5], r[6], r[7]);
+      } else {
+        const int yy = q / g.HP, xx = q - yy * g.HP;
+        if (store && yy < g.R && y0 + yy < g.H && xx < g.W) {
+          float4* d = reinterpret_cast<float4*>(out + ((static_cast<int64_t>(n) * g.H + y0 + yy) * g.W + xx) * kC3 + cg * kCg3);
+          d[0] = make_float4(r[0], r[1], r[2], r[3]);
+          d[1] = make_float4(r[4], r[5], r[6], r[7]);
+        }
+      }
+    }
+    if (g.pool) {
+      epi_bar();
+      const int prt = g.R / 3;                 // pooled rows of this tile
+      const int npp = prt * g.PW;
+      const int items = npp * 2;               // (4-channel half of the group, pooled pixel): pixel fastest, so
+      for (int it = tid; it < items; it += 128) {  // a quarter-warp reads 8 pixels 3*12 floats apart: no conflicts
+        const int c4 = it >= npp ? 1 : 0, pp = it - c4 * npp;
+        const int pyl = pp / g.PW, px = pp - pyl * g.PW;
+        const int py = y0 / 3 + pyl;
+        if (store && py < g.PH) {
+          const float* s = s_stage + ((3 * pyl) * g.HP + 3 * px) * kStagePitch + c4 * 4;
+          float4 best = *reinterpret_cast<const float4*>(s);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const float4 t = *reinterpret_cast<const float4*>(s + (i * g.HP + j) * kStagePitch);
+              best.x = fmaxf(best.x, t.x); best.y = fmaxf(best.y, t.y);
+              best.z = fmaxf(best.z, t.z); best.w = fmaxf(best.w, t.w);
+            }
+          }
+          *reinterpret_cast<float4*>(out + ((static_cast<int64_t>(n) * g.PH + py) * g.PW + px) * kC3 + cg * kCg3 + c4 * 4) = best;
+        }
+      }
+      epi_bar();
+    }
+  }
+}
+
+// ---- one CTA per SM ------------------------------------------------------------------------------------------------
 template <int NM>
 __global__ void __launch_bounds__(kThreads3, 1)
 conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk, const float* __restrict__ shift,
@@ -158,60 +303,14 @@ conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk
   fence_after();
   const uint32_t tmem_base = s_tmem;
   const int total_tiles = g.N * g.tiles_per_img;
+  auto next_tile = [&](int j) {
+    const int64_t t = blockIdx.x + static_cast<int64_t>(j) * gridDim.x;
+    return t < total_tiles ? static_cast<int>(t) : -1;
+  };
 
   if (warp >= 4 && warp < 8) {
     // ======================= producers =======================
-    const int ptid = tid - 128;
-    uint32_t gs = 0;       // stages issued so far (all tiles)
-    uint32_t pending = 0;  // issued, not yet signalled: stages gs - pending .. gs - 1
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n = tile / g.tiles_per_img;
-      const int y0 = (tile - n * g.tiles_per_img) * g.R;
-      // thread pair (2j, 2j+1) copies the two 16-byte halves of one pixel's 8-channel group: a warp reads 16
-      // whole 32-byte sectors and writes 512 contiguous shared-memory bytes per instruction
-      const float* src[kMaxPix3];
-      uint32_t dst[kMaxPix3], nbytes[kMaxPix3];
-      const int half = ptid & 1;
-#pragma unroll
-      for (int i = 0; i < kMaxPix3; ++i) {
-        const int h = (ptid >> 1) + 64 * i;  // padded pixel index inside the tile's run
-        const int hr = h / g.HP, hc = h - hr * g.HP;
-        const int y = y0 - 1 + hr, xx = hc - 1;
-        const bool ok = h < g.halo && hr <= g.R + 1 && y >= 0 && y < g.H && xx >= 0 && xx < g.W;
-        src[i] = (ok ? x + ((static_cast<int64_t>(n) * g.H + y) * g.W + xx) * kC3 : x) + half * 4;
-        nbytes[i] = ok ? 16u : 0u;   // 0 -> the 16 destination bytes are zero-filled (padding)
-        dst[i] = static_cast<uint32_t>(h) * 32u + ((static_cast<uint32_t>(half) ^ ((static_cast<uint32_t>(h) >> 2) & 1u)) << 4);
-      }
-#pragma unroll 1
-      for (int kc = 0; kc < 8; ++kc, ++gs) {
-        const uint32_t st = gs % kRing3, ph = (gs / kRing3) & 1u;
-        uint32_t ready = lane == 0 ? (mbar_test(smem_u32(&bars.empty[st]), ph ^ 1u) ? 1u : 0u) : 0u;
-        ready = __shfl_sync(0xffffffffu, ready, 0);
-        if (pending > 0 && !ready) {
-          // about to block on a slot the tensor core still reads: hand over everything already in flight first
-          cp_async_wait<0>();
-          fence_async_smem();
-          for (; pending > 0; --pending) mbar_arrive3(smem_u32(&bars.full[(gs - pending) % kRing3]));
-        }
-        if (!ready) mbar_wait_warp(smem_u32(&bars.empty[st]), ph ^ 1u, lane);
-        const uint32_t sb = ring_base + st * stage_bytes;
-#pragma unroll
-        for (int i = 0; i < kMaxPix3; ++i) {
-          if ((ptid >> 1) + 64 * i < g.halo) cp_async16(sb + dst[i], src[i] + kc * 8, nbytes[i]);
-        }
-        cp_async_commit();
-        ++pending;
-        if (pending > static_cast<uint32_t>(kAhead3)) {
-          cp_async_wait<kAhead3>();
-          fence_async_smem();
-          mbar_arrive3(smem_u32(&bars.full[(gs + 1 - pending) % kRing3]));
-          --pending;
-        }
-      }
-    }
-    cp_async_wait<0>();
-    fence_async_smem();
-    for (; pending > 0; --pending) mbar_arrive3(smem_u32(&bars.full[(gs - pending) % kRing3]));
+    producer_loop<kRing3, kAhead3>(x, g, tid - 128, lane, ring_base, stage_bytes, bars.full, bars.empty, next_tile);
   } else if (warp >= 8) {
     // ======================= MMA issuers: warp 8 + m owns accumulator m of every tile =======================
     // (a single issuing thread spends ~80 cycles per tcgen05.mma on descriptor arithmetic and the election
@@ -224,7 +323,7 @@ conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk
       uint32_t tap_off[9];  // start-address advance of tap (dy,dx) in 16-byte units
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>((tap / 3) * g.HP + tap % 3) * 2u;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int j = 0; next_tile(j) >= 0; ++j, ++lt) {
         const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
         mbar_wait(smem_u32(&bars.acc_empty[ab]), aph ^ 1u);  // epilogue has drained this accumulator set
         fence_after();
@@ -246,82 +345,255 @@ conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk
       }
     }
   } else {
-    // ======================= epilogue (warps 0-3): accumulator row == TMEM lane == tid =======================
+    // ======================= epilogue (warps 0-3) =======================
     uint32_t lt = 0;
     const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int j = 0;; ++j, ++lt) {
+      const int tile = next_tile(j);
+      if (tile < 0) break;
       const int n = tile / g.tiles_per_img;
       const int y0 = (tile - n * g.tiles_per_img) * g.R;
       const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
       mbar_wait_warp(smem_u32(&bars.acc_full[ab]), aph, lane);
       fence_after();
-      const uint32_t d0 = tmem_base + ab * (NM * kC3) + t_lane;
-#pragma unroll 1
-      for (int cg = 0; cg < kC3 / kCg3; ++cg) {
-        uint32_t v[NM][kCg3];
-#pragma unroll
-        for (int m = 0; m < NM; ++m) tmem_ld8(d0 + m * kC3 + cg * kCg3, v[m]);
-        tmem_wait_ld();
-        if (cg == kC3 / kCg3 - 1) {  // every value of this accumulator set is in registers: hand it back
-          fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive3(smem_u32(&bars.acc_empty[ab]));
-        }
-#pragma unroll
-        for (int m = 0; m < NM; ++m) {
-          float r[kCg3];
-#pragma unroll
-          for (int j = 0; j < kCg3; ++j) {
-            const float a = __uint_as_float(v[m][j]) + s_shift[cg * kCg3 + j];
-            r[j] = a > 0.f ? a : a * g.slope;
-          }
-          const int q = m * 128 + tid;  // linear position inside the tile
-          if (g.pool) {
-            float4* d = reinterpret_cast<float4*>(s_stage + q * kStagePitch);
-            d[0] = make_float4(r[0], r[1], r[2], r[3]);
-            d[1] = make_float4(r[4], r[5], r[6], r[7]);
-          } else {
-            const int yy = q / g.HP, xx = q - yy * g.HP;
-            if (yy < g.R && y0 + yy < g.H && xx < g.W) {
-              float4* d = reinterpret_cast<float4*>(out + ((static_cast<int64_t>(n) * g.H + y0 + yy) * g.W + xx) * kC3 + cg * kCg3);
-              d[0] = make_float4(r[0], r[1], r[2], r[3]);
-              d[1] = make_float4(r[4], r[5], r[6], r[7]);
-            }
-          }
-        }
-        if (g.pool) {
-          epi_bar();
-          const int prt = g.R / 3;                 // pooled rows of this tile
-          const int npp = prt * g.PW;
-          const int items = npp * 2;               // (4-channel half of the group, pooled pixel): pixel fastest, so
-          for (int it = tid; it < items; it += 128) {  // a quarter-warp reads 8 pixels 3*12 floats apart: no conflicts
-            const int c4 = it >= npp ? 1 : 0, pp = it - c4 * npp;
-            const int pyl = pp / g.PW, px = pp - pyl * g.PW;
-            const int py = y0 / 3 + pyl;
-            if (py < g.PH) {
-              const float* s = s_stage + ((3 * pyl) * g.HP + 3 * px) * kStagePitch + c4 * 4;
-              float4 best = *reinterpret_cast<const float4*>(s);
-#pragma unroll
-              for (int i = 0; i < 3; ++i) {
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                  const float4 t = *reinterpret_cast<const float4*>(s + (i * g.HP + j) * kStagePitch);
-                  best.x = fmaxf(best.x, t.x); best.y = fmaxf(best.y, t.y);
-                  best.z = fmaxf(best.z, t.z); best.w = fmaxf(best.w, t.w);
-                }
-              }
-              *reinterpret_cast<float4*>(out + ((static_cast<int64_t>(n) * g.PH + py) * g.PW + px) * kC3 + cg * kCg3 + c4 * 4) = best;
-            }
-          }
-          epi_bar();
-        }
-      }
+      epilogue_tile<NM>(g, n, y0, true, tmem_base + ab * (NM * kC3) + t_lane, s_stage, s_shift, out, tid, [&]() {
+        if (lane == 0) mbar_arrive3(smem_u32(&bars.acc_empty[ab]));
+      });
     }
   }
 
   fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---- CTA pair (cta_group::2) ---------------------------------------------------------------------------------------
+// Two CTAs of a cluster (the two SMs of a TPC) run one M = 256 MMA per step: each supplies the 128 activation rows
+// of ITS tile and only HALF of the weights (32 of the 64 output channels); the tensor cores exchange the halves.
+// Per MMA a CTA now reads 4 KB of A + 1 KB of B from shared memory instead of 4 + 2 KB -- the operand-read pipe is
+// what bounds this kernel -- and the resident weights shrink to 72 KB, which pays for an 8-stage ring.
+// The leader (cluster rank 0) issues every MMA; its "stage full" barriers collect the local producers plus one
+// remote arrival relayed from the peer's producers, its "accumulator empty" barriers the epilogue warps of both
+// CTAs; tcgen05.commit multicasts "stage empty" / "accumulator full" to both CTAs.
+constexpr int kRingP = 8;
+constexpr int kAheadP = 4;
+constexpr uint32_t kTapKcBytesP = 2u * (kC3 / 2) * 16u;   // one (tap, 8-channel group) of one CTA's half: 1 KB
+constexpr uint32_t kWBytesP = 9u * 8u * kTapKcBytesP;      // 73 728 B per CTA
+
+struct BarsP {
+  uint64_t full[kRingP], empty[kRingP];
+  uint64_t acc_full[2], acc_empty[2];
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
+  const uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void commit_pair(uint32_t bar) {  // arrives on the same barrier of both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+
+template <int NM>
+__global__ void __launch_bounds__(kThreads3, 1)
+conv3x3_c64_tc_pair_kernel(const float* __restrict__ x, const float* __restrict__ wpk_pair,
+                           const float* __restrict__ shift, float* __restrict__ out, const Conv3Geom g) {
+  extern __shared__ __align__(16) uint8_t s_dyn_raw[];  // [weight half][ring][staging][shift] after 256-byte alignment
+  __shared__ __align__(8) BarsP bars;
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t stage_bytes = static_cast<uint32_t>(g.halo) * 32u;
+  uint8_t* s_dyn = s_dyn_raw + ((256u - (smem_u32(s_dyn_raw) & 255u)) & 255u);
+  const uint32_t w_base = smem_u32(s_dyn);
+  const uint32_t ring_base = w_base + kWBytesP;
+  float* s_stage = reinterpret_cast<float*>(s_dyn + kWBytesP + kRingP * stage_bytes);
+  float* s_shift = s_stage + NM * 128 * kStagePitch;
+  constexpr uint32_t kTmemCols = NM == 1 ? 128u : (NM == 2 ? 256u : 512u);
+  constexpr uint32_t kIdesc = idesc_tf32(256, kC3);
+
+  {  // this CTA's half of the weights: output channels [32 rank, 32 rank + 32)
+    const uint4* src = reinterpret_cast<const uint4*>(wpk_pair) + static_cast<size_t>(rank) * (kWBytesP / 16);
+    uint4* dst = reinterpret_cast<uint4*>(s_dyn);
+    for (int i = tid; i < static_cast<int>(kWBytesP / 16); i += kThreads3) dst[i] = __ldg(src + i);
+    if (tid < kC3) s_shift[tid] = shift[tid];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kRingP; ++s) {
+      mbar_init(smem_u32(&bars.full[s]), leader ? 129 : 128);  // local producers (+ the peer's relay on the leader)
+      mbar_init(smem_u32(&bars.empty[s]), NM);                 // multicast commits of the NM issuing warps
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bars.acc_full[s]), NM);
+      mbar_init(smem_u32(&bars.acc_empty[s]), 8);              // epilogue warps of both CTAs (used on the leader)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers, weights and TMEM exist before anyone signals across the pair
+  fence_after();
+  const uint32_t tmem_base = s_tmem;
+  const int total_tiles = g.N * g.tiles_per_img;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  // step j of the pair covers tiles 2*(pair + j*npairs) + {0, 1}; an odd tail tile is paired with a recomputation
+  // of itself whose stores are suppressed
+  auto pair_base = [&](int j) { return 2 * (static_cast<int64_t>(pair) + static_cast<int64_t>(j) * npairs); };
+  auto next_tile = [&](int j) {
+    const int64_t b = pair_base(j);
+    if (b >= total_tiles) return -1;
+    const int64_t t = b + rank;
+    return static_cast<int>(t < total_tiles ? t : total_tiles - 1);
+  };
+
+  if (warp >= 4 && warp < 8) {
+    // ======================= producers (both CTAs fill their own ring) =======================
+    producer_loop<kRingP, kAheadP>(x, g, tid - 128, lane, ring_base, stage_bytes, bars.full, bars.empty, next_tile);
+  } else if (warp >= 8) {
+    const int m = warp - 8;
+    if (leader) {
+      // ======================= MMA issuers (leader only) =======================
+      if (m < NM && lane == 0) {
+        uint32_t gs = 0, lt = 0;
+        const uint64_t a_desc0 = desc_kmajor_sw32(ring_base + static_cast<uint32_t>(m) * 128u * 32u, 256u, 0u);
+        const uint64_t b_desc0 = desc_kmajor_noswizzle(w_base, (kC3 / 2) * 16u, 128u);
+        uint32_t tap_off[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>((tap / 3) * g.HP + tap % 3) * 2u;
+        for (int j = 0; next_tile(j) >= 0; ++j, ++lt) {
+          const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
+          mbar_wait_cluster(smem_u32(&bars.acc_empty[ab]), aph ^ 1u);  // both CTAs' epilogues have drained it
+          fence_after();
+          const uint32_t d_tmem = tmem_base + ab * (NM * kC3) + m * kC3;
+#pragma unroll 1
+          for (int kc = 0; kc < 8; ++kc, ++gs) {
+            const uint32_t st = gs % kRingP, ph = (gs / kRingP) & 1u;
+            mbar_wait_cluster(smem_u32(&bars.full[st]), ph);  // both CTAs' slices of this stage have landed
+            fence_after();
+            const uint64_t da_st = a_desc0 + ((st * stage_bytes) >> 4);
+            const uint64_t db_kc = b_desc0 + static_cast<uint32_t>(kc) * (kTapKcBytesP >> 4);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap)
+              mma_tf32_pair(d_tmem, da_st + tap_off[tap], db_kc + static_cast<uint32_t>(tap) * (8u * kTapKcBytesP >> 4),
+                            kIdesc, (kc | tap) != 0);
+            commit_pair(smem_u32(&bars.empty[st]));
+          }
+          commit_pair(smem_u32(&bars.acc_full[ab]));
+        }
+      }
+    } else if (m == 0 && lane == 0) {
+      // ======================= relay (peer only): "my slice of stage st is full" -> leader's barrier ==============
+      uint32_t gs = 0;
+      for (int j = 0; next_tile(j) >= 0; ++j) {
+        for (int kc = 0; kc < 8; ++kc, ++gs) {
+          const uint32_t st = gs % kRingP, ph = (gs / kRingP) & 1u;
+          mbar_wait(smem_u32(&bars.full[st]), ph);
+          mbar_arrive_cluster(map_to_cta(smem_u32(&bars.full[st]), 0));
+        }
+      }
+    }
+  } else {
+    // ======================= epilogue (warps 0-3 of both CTAs, each on its own tile) =======================
+    uint32_t lt = 0;
+    const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+    for (int j = 0;; ++j, ++lt) {
+      const int tile = next_tile(j);
+      if (tile < 0) break;
+      const bool store = pair_base(j) + rank < total_tiles;
+      const int n = tile / g.tiles_per_img;
+      const int y0 = (tile - n * g.tiles_per_img) * g.R;
+      const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
+      mbar_wait_warp(smem_u32(&bars.acc_full[ab]), aph, lane);
+      fence_after();
+      epilogue_tile<NM>(g, n, y0, store, tmem_base + ab * (NM * kC3) + t_lane, s_stage, s_shift, out, tid, [&]() {
+        if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&bars.acc_empty[ab]), 0));
+      });
+    }
+  }
+
+  fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be signalling this CTA's barriers / the leader reading this CTA's ring
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+}
+
+template <int NM>
+int launch_conv3_pair(const float* x, const float* wpk_pair, const float* shift, float* out, Conv3Geom g,
+                      cudaStream_t stream) {
+  g.halo = (NM * 128 + 2 * g.HP + 2 + 7) & ~7;
+  const size_t smem = kWBytesP + kRingP * (g.halo * 32u) + static_cast<size_t>(NM) * 128 * kStagePitch * 4 + kC3 * 4 + 256;
+  if (smem + 256u > 232448u) return AFS_ERR_UNSUPPORTED;
+  AFS_CUDA_TRY(cudaFuncSetAttribute(conv3x3_c64_tc_pair_kernel<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+  const int total = g.N * g.tiles_per_img;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kNumSMs, 1, 1);
+  cfg.blockDim = dim3(kThreads3, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent: as many CTA pairs as can be co-resident (a pair that had to wait for a free TPC would run its
+  // whole share of the tiles after everyone else has finished)
+  static int max_pairs[4] = {0, 0, 0, 0};
+  if (max_pairs[NM] == 0) {
+    int n = 0;
+    AFS_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, conv3x3_c64_tc_pair_kernel<NM>, &cfg));
+    max_pairs[NM] = n > 0 ? n : 1;
+    if (getenv("AFS_DEBUG") != nullptr) fprintf(stderr, "conv3 pair kernel NM=%d: %d co-resident CTA pairs\n", NM, n);
+  }
+  int pairs = (total + 1) / 2;
+  if (pairs > max_pairs[NM]) pairs = max_pairs[NM];
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  AFS_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_c64_tc_pair_kernel<NM>, x, wpk_pair, shift, out, g));
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
 }
 
 template <int NM>
@@ -338,6 +610,12 @@ int launch_conv3(const float* x, const float* wpk, const float* shift, float* ou
   return AFS_OK;
 }
 
+// 0: one CTA per SM (default).  1: CTA pairs (cta_group::2).  Initialised from AFS_CONV3_PAIR.
+std::atomic<int> g_pair_mode{[] {
+  const char* e = getenv("AFS_CONV3_PAIR");
+  return (e != nullptr && e[0] == '1') ? 1 : 0;
+}()};
+
 inline float round_tf32_host(float v) {  // cvt.rna.tf32.f32: nearest, ties away from zero
   uint32_t b;
   memcpy(&b, &v, 4);
@@ -350,7 +628,12 @@ inline float round_tf32_host(float v) {  // cvt.rna.tf32.f32: nearest, ties away
 }  // namespace
 }  // namespace afs
 
-extern "C" size_t afs_conv3x3_c64_packed_floats(void) { return afs::kWBytes3 / 4; }
+extern "C" int afs_conv3x3_c64_set_pair_mode(int32_t on) {
+  afs::g_pair_mode.store(on ? 1 : 0, std::memory_order_relaxed);
+  return AFS_OK;
+}
+
+extern "C" size_t afs_conv3x3_c64_packed_floats(void) { return 2 * (afs::kWBytes3 / 4); }
 
 extern "C" int afs_conv3x3_c64_pack_weights(const float* w_folded_host, float* packed_host) {
   using namespace afs;
@@ -362,8 +645,10 @@ extern "C" int afs_conv3x3_c64_pack_weights(const float* w_folded_host, float* p
         for (int co = 0; co < kC3; ++co)
           for (int i = 0; i < 4; ++i) {
             const int ci = 8 * kc + 4 * ch + i;
-            packed_host[(((tap * 8 + kc) * 2 + ch) * kC3 + co) * 4 + i] =
-                round_tf32_host(w_folded_host[(co * kC3 + ci) * 9 + tap]);
+            const float v = round_tf32_host(w_folded_host[(co * kC3 + ci) * 9 + tap]);
+            packed_host[(((tap * 8 + kc) * 2 + ch) * kC3 + co) * 4 + i] = v;
+            // second copy for the CTA-pair kernel: [rank = co / 32][tap][kc][chunk][co % 32][4]
+            packed_host[kWBytes3 / 4 + ((((co / 32) * 9 + tap) * 8 + kc) * 2 + ch) * (kC3 / 2) * 4 + (co % 32) * 4 + i] = v;
           }
   return AFS_OK;
 }
@@ -394,6 +679,14 @@ extern "C" int afs_conv3x3_c64_bn_act_fwd_tf32(const float* x, int32_t N, int32_
   if (static_cast<int64_t>(N) * g.tiles_per_img > 0x7fffffffLL) return AFS_ERR_UNSUPPORTED;
   const int NM = (R * g.HP + 127) / 128;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (g_pair_mode.load(std::memory_order_relaxed) != 0 && static_cast<int64_t>(N) * g.tiles_per_img >= 2) {
+    const float* w_pair = w_packed + kWBytes3 / 4;
+    switch (NM) {
+      case 1: return launch_conv3_pair<1>(x, w_pair, shift, out, g, stream);
+      case 2: return launch_conv3_pair<2>(x, w_pair, shift, out, g, stream);
+      default: return launch_conv3_pair<3>(x, w_pair, shift, out, g, stream);
+    }
+  }
   switch (NM) {
     case 1: return launch_conv3<1>(x, w_packed, shift, out, g, stream);
     case 2: return launch_conv3<2>(x, w_packed, shift, out, g, stream);

@@ -217,6 +217,12 @@ def conv3x3_c64_pack_weights(w_folded):
     return packed
 
 
+def conv3x3_c64_set_pair_mode(on):
+    """Process-wide switch between the one-CTA-per-SM kernel (default) and the CTA-pair (cta_group::2) variant of
+    conv3x3_c64_bn_act; results are bit-identical."""
+    _lib.check(_lib.lib().afs_conv3x3_c64_set_pair_mode(1 if on else 0), "afs_conv3x3_c64_set_pair_mode")
+
+
 def conv3x3_c64_supported(x):
     """Shapes the tensor-core block kernel is built for (others stay on cuDNN)."""
     return x.dim() == 4 and x.shape[1] == 64 and x.shape[3] <= 61

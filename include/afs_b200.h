@@ -149,10 +149,14 @@ int afs_conv1_train_bwd(const float* x, const float* grad_out, int32_t N, int32_
  * Replaces layer2..layer4 of libfewshot_core/model/backbone/conv_four.py:67-86,104-113 in eval mode.
  * x [N, H, Wd, 64] fp32 NHWC (device); out [N, H, Wd, 64] or, pooled, [N, H/3, Wd/3, 64] NHWC (device).
  * w_packed (device, afs_conv3x3_c64_packed_floats() floats, 16-byte aligned): the BatchNorm-folded weights in
- * operand order, produced on the host by afs_conv3x3_c64_pack_weights from w_folded_host [64][64][3][3] (OIHW)
+ * operand order (once for the one-CTA kernel, once split in halves for the CTA-pair kernel), produced on the host by afs_conv3x3_c64_pack_weights from w_folded_host [64][64][3][3] (OIHW)
  * with round-to-nearest TF32; shift [64] (device) = (bias - mean)*gamma/sqrt(var+eps) + beta.
  * Built for Wd <= 61; AFS_ERR_UNSUPPORTED otherwise (the caller keeps cuDNN for such shapes).               */
 size_t afs_conv3x3_c64_packed_floats(void);
+/* Kernel variant switch (process-wide; default 0, or 1 when AFS_CONV3_PAIR=1 is in the environment): 1 runs the block
+ * on CTA pairs (thread-block clusters of 2, tcgen05 cta_group::2: each CTA keeps half of the weights).  Results are
+ * bit-identical; on B200 the pair variant is not faster, it is kept as the measured alternative.   */
+int afs_conv3x3_c64_set_pair_mode(int32_t on);
 int afs_conv3x3_c64_pack_weights(const float* w_folded_host, float* packed_host);
 int afs_conv3x3_c64_bn_act_fwd_tf32(const float* x, int32_t N, int32_t H, int32_t Wd, const float* w_packed,
                                     const float* shift, float negative_slope, int32_t pool3, float* out,

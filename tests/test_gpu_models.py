@@ -132,6 +132,29 @@ def test_conv3x3_block_tensor_core_kernel(cuda, N, H, Wd, slope, pool):
     assert (got_q.double() - want_q).abs().max().item() <= 2e-5 * want_q.abs().max().item()
 
 
+@pytest.mark.parametrize("N,H,Wd,pool", [(5, 42, 52, True), (3, 14, 17, True), (3, 14, 17, False), (149, 42, 52, True),
+                                         (1, 4, 5, False)])
+def test_conv3x3_block_cta_pair_variant_is_bit_identical(cuda, N, H, Wd, pool):
+    """The cta_group::2 kernel (thread-block clusters of 2, half of the weights per CTA, remote mbarrier arrivals,
+    multicast commits) accumulates the same MMAs in the same order: outputs must equal the one-CTA kernel's bit for
+    bit, including an odd number of tiles (the tail tile is paired with a store-suppressed recomputation)."""
+    from audio_fewshot_b200 import ops
+    rng = np.random.default_rng(N + H)
+    x = torch.from_numpy(rng.standard_normal((N, 64, H, Wd)).astype(np.float32)).to(cuda)
+    x = x.contiguous(memory_format=torch.channels_last)
+    w = torch.from_numpy((rng.standard_normal((64, 64, 3, 3)) * 0.06).astype(np.float32)).to(cuda)
+    b = torch.from_numpy(rng.standard_normal(64).astype(np.float32)).to(cuda)
+    packed = torch.from_numpy(ops.conv3x3_c64_pack_weights(w)).to(cuda)
+    one = ops.conv3x3_c64_bn_act(x, packed, b, 0.1, pool=pool)
+    try:
+        ops.conv3x3_c64_set_pair_mode(True)
+        two = ops.conv3x3_c64_bn_act(x, packed, b, 0.1, pool=pool)
+        torch.cuda.synchronize()
+    finally:
+        ops.conv3x3_c64_set_pair_mode(False)
+    assert torch.equal(one, two)
+
+
 def test_conv64f_tensor_core_blocks_match_fp32_path(cuda):
     """Whole Conv64F inference path with the tcgen05 stem and blocks (TF32) against the exact-fp32 path."""
     net = _net(cuda, "conv64f_flat")
