@@ -45,7 +45,7 @@ constexpr int kThreads = 256;
 constexpr int kGroups = kThreads / kGroup;
 constexpr int kFramesPerCta = 32;
 constexpr int kFramesPerGroup = kFramesPerCta / kGroups;
-constexpr int kMaxNnz = 2048;
+constexpr int kMaxNnz = 3072;  // floats of the ELL weight table (128 slaney mels: 1 440)
 constexpr int kTileStride = kFramesPerCta + 1;
 constexpr int kGroupFloats = kBufA + kBufB + kMelBatch * kPStride;
 
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
         const int m = mel_id[i];
         if (m >= 0) {
           float acc[kMelBatch];
-          mel_dot_batch(bufP, s_w + s_band[2 * kMaxMels + m], s_band[m], s_band[kMaxMels + m], acc);
+          mel_dot_batch(bufP, s_w + s_band[2 * kMaxMels + m], kEllStride, s_band[m], s_band[kMaxMels + m], acc);
 #pragma unroll
           for (int f = 0; f < kMelBatch; ++f)
             if (f <= slot) s_tile[m * kTileStride + fl0 + f] = norm_db(acc[f], p.log_eps, mel_scale[i], mel_shift[i]);
@@ -310,7 +310,7 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
 
   std::vector<int> band;
   std::vector<float> weights;
-  pack_mel_bands(fb_host, cfg->n_mels, band, weights);
+  pack_mel_ell(fb_host, cfg->n_mels, band, weights);
   if (weights.size() > static_cast<size_t>(kMaxNnz)) return AFS_ERR_UNSUPPORTED;
   if (weights.empty()) weights.push_back(0.f);
 

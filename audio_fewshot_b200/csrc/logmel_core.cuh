@@ -186,6 +186,10 @@ AFS_HD void phase_c(int t, const float* bufB, float* bufA) {
   }
 }
 
+// Power bin k is stored at pskew(k) = k + k/32: the mel projection reads bins lo_m + i with a different lo_m per
+// lane, and for the upper filters the lo_m are ~8-12 bins apart, which without the skew puts 3-4 lanes on one bank.
+AFS_HD int pskew(int k) { return k + (k >> 5); }
+
 // Phase D. thread u handles k = u + 64 m (m = 0..3) and its mirror 512 - k;
 // thread 0 also writes the self-paired bin 256.  Power spectrum into buffer B.
 AFS_HD void phase_d(int u, const float2* twbd, const float* bufA, float* power) {
@@ -206,12 +210,12 @@ AFS_HD void phase_d(int u, const float2* twbd, const float* bufA, float* power) 
     const cpx t2 = cmul(o2, td);
     const float xr = er + t2.re, xi = ei + t2.im;
     const float yr = er - t2.re, yi = ei - t2.im;
-    power[k] = 0.25f * (xr * xr + xi * xi);
-    power[kHalf - k] = 0.25f * (yr * yr + yi * yi);
+    power[pskew(k)] = 0.25f * (xr * xr + xi * xi);
+    power[pskew(kHalf - k)] = 0.25f * (yr * yr + yi * yi);
   }
   if (u == 0) {
     const float ar = re[256], ai = im[256];
-    power[256] = ar * ar + ai * ai;
+    power[pskew(256)] = ar * ar + ai * ai;
   }
 }
 
@@ -222,24 +226,26 @@ AFS_HD int64_t reflect_index(int64_t idx, int64_t L) {
   return idx;
 }
 
-// Banded mel projection of one filter: sum_i w[off+i] * P[lo+i].
-AFS_HD float mel_dot(const float* power, const float* weights, int lo, int len) {
+// Banded mel projection of one filter: sum_i w[i * wstride] * P[lo+i] (P in the skewed layout).
+AFS_HD float mel_dot(const float* power, const float* weights, int wstride, int lo, int len) {
   float acc = 0.f;
-  for (int i = 0; i < len; ++i) acc += weights[i] * power[lo + i];
+  for (int i = 0; i < len; ++i) acc += weights[i * wstride] * power[pskew(lo + i)];
   return acc;
 }
 
 // The same projection for kMelBatch frames at once (their power spectra kPStride floats apart): one
 // weight load feeds kMelBatch FMAs.  Summation order per frame is identical to mel_dot.
 constexpr int kMelBatch = 4;
-constexpr int kPStride = 516;  // 513 power bins, padded to a multiple of 4 floats
-AFS_HD void mel_dot_batch(const float* power, const float* weights, int lo, int len, float (&acc)[kMelBatch]) {
+constexpr int kPStride = 532;  // 513 power bins + 16 of skew, padded to a multiple of 4 floats
+AFS_HD void mel_dot_batch(const float* power, const float* weights, int wstride, int lo, int len,
+                          float (&acc)[kMelBatch]) {
 #pragma unroll
   for (int f = 0; f < kMelBatch; ++f) acc[f] = 0.f;
   for (int i = 0; i < len; ++i) {
-    const float w = weights[i];
+    const float w = weights[i * wstride];
+    const int k = pskew(lo + i);
 #pragma unroll
-    for (int f = 0; f < kMelBatch; ++f) acc[f] += w * power[f * kPStride + lo + i];
+    for (int f = 0; f < kMelBatch; ++f) acc[f] += w * power[f * kPStride + k];
   }
 }
 
@@ -279,6 +285,43 @@ inline int pack_mel_bands(const float* fb, int n_mels, IntVec& band, FloatVec& w
     band[kMaxMels + m] = len;
     band[2 * kMaxMels + m] = static_cast<int>(weights.size());
     for (int i = 0; i < len; ++i) weights.push_back(fb[static_cast<size_t>(lo + i) * n_mels + m]);
+  }
+  return static_cast<int>(weights.size());
+}
+
+// The kernel's weight table (ELL layout): thread t of a 64-thread frame group owns filter t (pass 0) and filter
+// n_mels-1-t when that is >= 64 (pass 1).  The 32 lanes of a warp read weight i of their filter in the same
+// instruction, so the table is stored [warp-pass][i][lane] (zero padded to the longest filter of the warp-pass):
+// every weight load is one conflict-free wavefront.  band[m] = first bin, band[kMaxMels+m] = span length,
+// band[2*kMaxMels+m] = index of the filter's weight 0; consecutive weights are kEllStride apart.
+constexpr int kEllStride = 32;
+template <typename IntVec, typename FloatVec>
+inline int pack_mel_ell(const float* fb, int n_mels, IntVec& band, FloatVec& weights) {
+  IntVec b0;
+  FloatVec w0;
+  pack_mel_bands(fb, n_mels, b0, w0);
+  band.assign(3 * kMaxMels, 0);
+  weights.clear();
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int warp = 0; warp < kGroup / 32; ++warp) {
+      int filt[32], maxlen = 0;
+      for (int lane = 0; lane < 32; ++lane) {
+        const int t = warp * 32 + lane;
+        int m = pass == 0 ? (t < n_mels ? t : -1) : (n_mels - 1 - t >= kGroup ? n_mels - 1 - t : -1);
+        filt[lane] = m;
+        if (m >= 0 && b0[kMaxMels + m] > maxlen) maxlen = b0[kMaxMels + m];
+      }
+      const int base = static_cast<int>(weights.size());
+      weights.resize(weights.size() + static_cast<size_t>(maxlen) * kEllStride, 0.f);
+      for (int lane = 0; lane < 32; ++lane) {
+        const int m = filt[lane];
+        if (m < 0) continue;
+        band[m] = b0[m];
+        band[kMaxMels + m] = b0[kMaxMels + m];
+        band[2 * kMaxMels + m] = base + lane;
+        for (int i = 0; i < b0[kMaxMels + m]; ++i) weights[base + i * kEllStride + lane] = w0[b0[2 * kMaxMels + m] + i];
+      }
+    }
   }
   return static_cast<int>(weights.size());
 }

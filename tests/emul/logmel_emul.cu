@@ -51,7 +51,7 @@ extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, con
     const int slot = f % kMelBatch;
     float* power = bufP.data() + slot * kPStride;
     for (int t = 0; t < kGroup; ++t) phase_d(t, twbd.data(), bufA.data(), power);
-    if (power_out) for (int k = 0; k < kBins; ++k) power_out[static_cast<size_t>(f) * kBins + k] = power[k];
+    if (power_out) for (int k = 0; k < kBins; ++k) power_out[static_cast<size_t>(f) * kBins + k] = power[pskew(k)];
     if (slot != kMelBatch - 1 && f + 1 != T) continue;
     for (int t = 0; t < kGroup; ++t) {  // batched mel projection, as the kernel's epilogue
       int mel_id[2];
@@ -61,7 +61,7 @@ extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, con
         const int m = mel_id[i];
         if (m < 0) continue;
         float acc[kMelBatch];
-        mel_dot_batch(bufP.data(), weights.data() + band[2 * kMaxMels + m], band[m], band[kMaxMels + m], acc);
+        mel_dot_batch(bufP.data(), weights.data() + band[2 * kMaxMels + m], 1, band[m], band[kMaxMels + m], acc);
         const float scale = log_mult * 0.30102999566398120f / stdv[m];
         const float shift = -mean[m] / stdv[m];
         for (int b = 0; b <= slot; ++b)
