@@ -84,7 +84,46 @@ def make_augment():
     print("augment.npz", os.path.getsize(os.path.join(OUT, "augment.npz")))
 
 
+def tta_cases():
+    """Seeded (query-row mask, windows per query, flagged queries, images) cases for the TTA helpers."""
+    rng = np.random.default_rng(77)
+    out = []
+    for _ in range(6):
+        nq = int(rng.integers(1, 8))
+        r = rng.integers(1, 4, size=nq)
+        s = []
+        for j in range(nq):
+            s += [False] * int(rng.integers(0, 3)) + [True] * int(r[j])
+        s = np.array(s + [False] * int(rng.integers(0, 4)), dtype=bool)
+        q = rng.random(nq) < 0.4
+        imgs = rng.standard_normal((len(s), 1, 4, 5)).astype(np.float32)
+        out.append((s, r.astype(np.int64), q, imgs))
+    return out
+
+
+def make_tta():
+    """map_q_to_s_runs / augment_images_with_mask of the real reference (test.py:33-152) on seeded cases, with a
+    call-counting augmentation so the call ORDER is pinned too."""
+    import_reference()
+    import libfewshot_core.test as rt
+    out = {}
+    for i, (s, r, q, imgs) in enumerate(tta_cases()):
+        out["%d/s" % i], out["%d/r" % i], out["%d/q" % i], out["%d/img" % i] = s, r, q, imgs
+        out["%d/mapped" % i] = rt.map_q_to_s_runs(s, r, q)
+        calls = [0]
+
+        def fn(x):
+            calls[0] += 1
+            return x * 2 + calls[0]
+
+        out["%d/aug" % i] = rt.augment_images_with_mask(torch.from_numpy(imgs), torch.from_numpy(r), s, q, fn, 3).numpy()
+    np.savez_compressed(os.path.join(OUT, "tta.npz"), **out)
+    print("tta.npz", os.path.getsize(os.path.join(OUT, "tta.npz")))
+
+
 def main():
+    if "--tta" in sys.argv:
+        return make_tta()
     if "--maml" in sys.argv:
         return make_maml()
     if "--augment" in sys.argv:

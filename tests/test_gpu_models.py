@@ -620,3 +620,35 @@ def test_protonet_training_step_with_fused_stem_matches_module_graph(cuda):
         # gradients are compared in the L2 sense; the block itself is pinned element-wise by the test above
         rel = (p1.grad - p2.grad).norm().item() / max(p2.grad.norm().item(), 1e-12)
         assert rel <= 5e-2, (n1, rel, scale)
+
+
+def test_energy_gated_tta_step(cuda, tmp_path, monkeypatch):
+    """tta.energy_tta_step (reference test.py:380-414) around DeepBDC: with an identity augmentation and one window per
+    query the re-vote over k identical copies cannot change a prediction (with several windows a tied vote may: the
+    CUDA torch.mode tie rule depends on the slice length), so the accuracy must be unchanged and the new repeats must
+    describe the enlarged batch; with ragged windows and the real noise suppression the step runs end to end."""
+    from audio_fewshot_b200 import model as arch
+    from audio_fewshot_b200 import tta
+    monkeypatch.chdir(tmp_path)  # the reference appends to ./test_uncertainty.npy (deepbdc.py:326-351)
+    torch.manual_seed(0)
+    emb = arch.resnet12Bdc(reduce_dim=64, num_channels=1)
+    m = arch.DeepBDC(way_num=3, shot_num=2, query_num=4, test_way=3, test_shot=2, test_query=4, emb_func=emb,
+                     device=cuda).to(cuda).eval()
+    E, W, S, Q = 1, 3, 2, 4
+    rng = np.random.default_rng(0)
+    ones = torch.ones(E * W * Q, dtype=torch.long)
+    x1 = torch.randn(E * W * (S + Q), 1, 128, 157) * 0.7
+    repeats = torch.from_numpy(rng.integers(1, 3, size=E * W * Q)).long()
+    n = E * W * S + int(repeats.sum())
+    x = torch.randn(n, 1, 128, 157) * 0.7
+    with torch.no_grad():
+        acc, info = tta.energy_tta_step(m, [x1, None, ones, E * W * S], num_augmentations=3, mean=-15.0, std=26.0,
+                                        suppression_strength=0.0, noise_percentile=20.0)
+        assert info["n_flagged"] == int(0.2 * E * W * Q) >= 1
+        assert abs(float(acc) - float(info["acc_before"])) < 1e-4
+        rep2 = info["repeats_after"]
+        flagged = np.flatnonzero(info["ood_query_mask"])
+        assert all(int(rep2[i]) == 3 for i in flagged) and int(rep2.sum()) == E * W * Q + 2 * len(flagged)
+        acc2, _ = tta.energy_tta_step(m, [x, None, repeats, E * W * S], num_augmentations=2, mean=-15.0, std=26.0)
+        assert 0.0 <= float(acc2) <= 100.0
+    assert (tmp_path / "test_uncertainty.npy").exists()

@@ -109,3 +109,39 @@ def test_world_size_2_gloo(tmp_path):
     assert all(p.returncode == 0 for p in procs), outs
     m, h = [float(v) for v in outs[0][0].split()[1:3]]
     assert m == pytest.approx(55.0) and h > 0
+
+
+def test_tta_helpers_match_reference_golden(golden):
+    """tta.map_q_to_s_runs / augment_images_with_mask against outputs of the reference's own functions
+    (libfewshot_core/test.py:33-152; tests/golden/tta.npz from `python -m oracle.make_golden --tta`): same rows, same
+    order, same number and order of augmentation calls."""
+    from audio_fewshot_b200 import tta
+    g = golden("tta.npz")
+    n_cases = len({k.split("/")[0] for k in g.files})
+    assert n_cases == 6
+    for i in range(n_cases):
+        s, r, q, img = g["%d/s" % i], g["%d/r" % i], g["%d/q" % i], g["%d/img" % i]
+        assert np.array_equal(tta.map_q_to_s_runs(s, r, q), g["%d/mapped" % i])
+        calls = [0]
+
+        def fn(x):
+            calls[0] += 1
+            return x * 2 + calls[0]
+
+        got = tta.augment_images_with_mask(torch.from_numpy(img), torch.from_numpy(r), s, q, fn, 3)
+        assert np.array_equal(got.numpy(), g["%d/aug" % i])
+        rep = tta.updated_repeats(torch.from_numpy(r), q, 3)
+        assert int(rep.sum()) + int((~s).sum()) == got.shape[0]  # repeats describe exactly the rows that exist
+    with pytest.raises(ValueError):
+        tta.map_q_to_s_runs([True, True], [1], [True])
+
+
+def test_tta_helpers_match_live_reference(reference):
+    import libfewshot_core.test as rt
+    from audio_fewshot_b200 import tta
+    from oracle.make_golden import tta_cases
+    for s, r, q, img in tta_cases():
+        assert np.array_equal(tta.map_q_to_s_runs(s, r, q), rt.map_q_to_s_runs(s, r, q))
+        a = rt.augment_images_with_mask(torch.from_numpy(img), torch.from_numpy(r), s, q, lambda x: x + 1, 2)
+        b = tta.augment_images_with_mask(torch.from_numpy(img), torch.from_numpy(r), s, q, lambda x: x + 1, 2)
+        assert torch.equal(a, b)
