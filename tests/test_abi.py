@@ -61,3 +61,30 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
                 assert "/root/reference" not in src, f
+
+
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """include/afs_b200.h must be usable from a C host (no C++ or torch types in any signature): a C99 translation
+    unit that includes it, takes the address of every declared entry point and calls the GPU-free ones compiles with
+    gcc, links against libafs_b200.so and runs."""
+    from audio_fewshot_b200 import build
+    lib = build.build()
+    names = declared_symbols()
+    src = tmp_path / "host.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "afs_b200.h"\n'
+        "typedef void (*fn_t)(void);\n"
+        "int main(void) {\n"
+        "  fn_t fns[] = {%s};\n"
+        "  size_t n = sizeof(fns) / sizeof(fns[0]);\n"
+        "  for (size_t i = 0; i < n; ++i) if (fns[i] == 0) return 2;\n"
+        "  if (afs_abi_version() != AFS_ABI_VERSION) return 3;\n"
+        "  if (afs_proto_fwd(0, 0, 0, 0, 0, 5, 5, 1600, 0, 0, 0, 0, 0, 0) != AFS_ERR_INVALID_ARG) return 4;\n"
+        '  printf("%%s %%zu\\n", afs_status_string(AFS_ERR_WORKSPACE), n);\n'
+        "  return 0;\n}\n" % ", ".join("(fn_t)%s" % n for n in names))
+    exe = tmp_path / "host"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), lib, "-Wl,-rpath," + os.path.dirname(lib)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out
+    assert out.stdout.split() == ["workspace", "too", "small", str(len(names))]
