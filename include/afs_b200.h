@@ -51,9 +51,9 @@ uint64_t afs_launch_count(void);
  * (1) Fused waveform -> normalised log-mel front-end.
  *
  * Replaces the (absent) offline feature extraction that
- * produced the reference's `*_spec` folders (config/headers/data.yaml:1) and
+ * produced the reference's `<set>_spec` folders (config/headers/data.yaml:1) and
  * the `(x-mean)/std` step of libfewshot_core/audio_augmentations.py:36-53
- * with statistics from Auxiliary/*_Mean_Std.npy (libfewshot_core/test.py:398-399).
+ * with statistics from Auxiliary/<set>_Mean_Std.npy (libfewshot_core/test.py:398-399).
  * Canonical spec (oracle/frontend.py): reflect-pad n_fft/2, frame, window,
  * |rFFT|^2, mel projection, log_mult*log10(. + log_eps), (. - mean[m])/std[m].
  * Output layout [B, 1, n_mels, T] fp32 contiguous, T = 1 + L/hop (center) --
@@ -91,12 +91,12 @@ int afs_logmel_plan_destroy(afs_logmel_plan* plan);
 int afs_logmel_num_frames(const afs_logmel_plan* plan, int64_t L);
 
 /* wav [B, L] fp32; mean/std [n_mels] fp32 (per-bin; broadcast the scalar of
- * Auxiliary/*_Mean_Std.npy into it); aug nullable; out [B, 1, n_mels, T].  */
+ * Auxiliary/<set>_Mean_Std.npy into it); aug nullable; out [B, 1, n_mels, T].  */
 int afs_logmel_fwd(const afs_logmel_plan* plan, const float* wav, int32_t B, int64_t L,
                    const float* mean, const float* std, const afs_aug_cfg* aug,
                    uint64_t seed, uint64_t first_clip_index, float* out, afs_stream_t stream);
 
-/* The same kernel fed with 16-bit PCM (the sample format of the wav files behind the reference's `*_spec`
+/* The same kernel fed with 16-bit PCM (the sample format of the wav files behind the reference's `<set>_spec`
  * folders): wav [B, L] int16, sample value = (float)pcm * pcm_scale (1/32768 for full scale in [-1, 1); the
  * product is exact in fp32 for a power-of-two scale, so the result is bit-identical to afs_logmel_fwd on the
  * converted fp32 waveform).  Halves the PCIe and HBM bytes of the waveform: 2*L + 4*n_mels*T per clip.   */
@@ -301,7 +301,7 @@ int afs_energy_score(const float* logits, int32_t W, const int32_t* q_start, int
  * augmentations it dispatches to (:56-528) between denormalize_spectrogram (:16-33) and
  * normalize_spectrogram (:36-53).  in/out: `planes` contiguous [H, W] fp32 planes (every
  * (batch, channel) pair of the reference's [B,C,H,W] / [C,H,W] / [H,W] inputs); mean/std: the
- * scalar pair of Auxiliary/*_Mean_Std.npy.  The random parameters are drawn by the host (the
+ * scalar pair of Auxiliary/<set>_Mean_Std.npy.  The random parameters are drawn by the host (the
  * reference draws them with Python's `random`) and arrive in `cfg`:
  *   CUTOUT                 n_rect rectangles rect[k] = {top, left, height, width}, value `fill`
  *   LINEAR_FILTER          filter_curve [H] (device): per-frequency gain
