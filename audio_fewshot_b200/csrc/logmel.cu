@@ -49,7 +49,7 @@ constexpr int kMaxNnz = 3072;  // floats of the ELL weight table (128 slaney mel
 constexpr int kTileStride = kFramesPerCta + 1;
 constexpr int kGroupFloats = kBufA + kBufB + kMelBatch * kPStride;
 
-constexpr size_t kSmemFloats = kMaxNnz + 3 * kMaxMels + kNfft + 2 * kTwbdEntries + kGroups * kGroupFloats +
+constexpr size_t kSmemFloats = kMaxNnz + 3 * kMaxMels + kGroups * kGroupFloats +
                                kMaxMels * kTileStride;
 constexpr size_t kSmemBytes = kSmemFloats * sizeof(float);
 
@@ -176,9 +176,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
   float* s_w = smem;
   int* s_band = reinterpret_cast<int*>(s_w + kMaxNnz);
-  float* s_win = reinterpret_cast<float*>(s_band + 3 * kMaxMels);
-  float2* s_twbd = reinterpret_cast<float2*>(s_win + kNfft);
-  float* s_grp = reinterpret_cast<float*>(s_twbd + kTwbdEntries);
+  float* s_grp = reinterpret_cast<float*>(s_band + 3 * kMaxMels);
   float* s_tile = s_grp + kGroups * kGroupFloats;
 
   const int tid = threadIdx.x;
@@ -189,8 +187,6 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
 
   for (int i = tid; i < p.nnz; i += kThreads) s_w[i] = p.weights[i];
   for (int i = tid; i < 3 * kMaxMels; i += kThreads) s_band[i] = p.band[i];
-  for (int i = tid; i < kNfft; i += kThreads) s_win[i] = p.window[i];
-  for (int i = tid; i < kTwbdEntries; i += kThreads) s_twbd[i] = twbd_entry(i, p.tw1024);
 
   ThreadTw tw;
   load_thread_tw(tw, t, p.tw1024);
@@ -238,7 +234,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
   const int nfr = min(kFramesPerCta, p.T - t0);
   const int f_begin = grp * kFramesPerGroup;
   const int f_end = min(f_begin + kFramesPerGroup, nfr);
-  const float2* s_win2 = reinterpret_cast<const float2*>(s_win);
+  // this thread's 16 window coefficients stay in registers for every frame (the shared-memory pipe is the limiter)
+  float2 win[8];
+  {
+    const float2* w2 = reinterpret_cast<const float2*>(p.window);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) win[r] = __ldg(w2 + t + 64 * r);
+  }
 
   float2 raw[8];
   if (f_begin < f_end) load_frame<AUG, S>(x, static_cast<int64_t>(t0 + f_begin) * p.hop - p.pad, p.L, t, aug, raw);
@@ -248,20 +250,19 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
     cpx z[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const float2 w = s_win2[t + 64 * r];
-      z[r].re = raw[r].x * w.x;
-      z[r].im = raw[r].y * w.y;
+      z[r].re = raw[r].x * win[r].x;
+      z[r].im = raw[r].y * win[r].y;
     }
     if (fl + 1 < f_end)  // prefetch the next frame while this one is transformed
       load_frame<AUG, S>(x, static_cast<int64_t>(t0 + fl + 1) * p.hop - p.pad, p.L, t, aug, raw);
     const int slot = (fl - f_begin) % kMelBatch;
     phase_a(t, z, tw, bufA);
     group_bar(grp);
-    phase_b(t, s_twbd, bufA, bufB);
+    phase_b(t, tw, bufA, bufB);
     group_bar(grp);
     phase_c(t, bufB, bufA);
     group_bar(grp);
-    phase_d(t, s_twbd, bufA, bufP + slot * kPStride);
+    phase_d(t, tw, bufA, bufP + slot * kPStride);
     group_bar(grp);
     if (slot == kMelBatch - 1 || fl + 1 == f_end) {
       const int fl0 = fl - slot;  // first frame of this batch

@@ -97,28 +97,32 @@ AFS_HD int e2_slot(int q, int j0, int p0) {
   return q + 8 * (((j0 & 3) + (p0 & 3)) & 3) + 32 * ((j0 >> 2) + 2 * (p0 >> 2) + 4 * (j0 & 3));
 }
 
-// Per-thread phase-A twiddles, held in registers for the whole kernel.
+// Per-thread twiddle BASES, held in registers for the whole kernel; the powers each phase needs are rebuilt per
+// frame with complex multiplications (the FMA pipe has headroom, the shared-memory pipe is the kernel's limiter):
+//   a  = W_512^j          phase A uses a^q,  q = 1..7
+//   b  = W_64^(t >> 3)    phase B uses b^p0, p0 = 1..7
+//   d  = W_1024^t         phase D uses d * W_16^m, m = 0..3
 struct ThreadTw {
-  cpx a[8];  // phase A: W_512^{j q}, q = 0..7 (a[0] unused)
+  cpx a, b, d;
 };
 
-// Twiddles of phases B and D live in a table shared by all frame groups of a CTA, laid out
-// [index][thread] so that the 64 threads of a group read consecutive float2's:
-//   twbd[(p0 - 1) * 64 + t] = W_64^{(t >> 3) p0},  p0 = 1..7      (phase B)
-//   twbd[(7 + m) * 64 + t]  = W_1024^{t + 64 m},   m = 0..3       (phase D)
-constexpr int kTwbdEntries = 11 * kGroup;  // float2 entries
+// w^1 .. w^7 with 6 complex multiplications of depth <= 3 (a few ulp of error, far below the FFT's own rounding)
+AFS_HD void powers7(cpx w, cpx (&p)[8]) {
+  p[1] = w;
+  p[2] = cmul(w, w);
+  p[3] = cmul(p[2], w);
+  p[4] = cmul(p[2], p[2]);
+  p[5] = cmul(p[4], w);
+  p[6] = cmul(p[4], p[2]);
+  p[7] = cmul(p[4], p[3]);
+}
 
 // tw1024[k] = (cos(2 pi k/1024), -sin(2 pi k/1024)), k in [0, 1024)
 AFS_HD void load_thread_tw(ThreadTw& tw, int t, const float2* tw1024) {
-  for (int q = 0; q < 8; ++q) {
-    const float2 wa = tw1024[(2 * t * q) & 1023];
-    tw.a[q].re = wa.x; tw.a[q].im = wa.y;
-  }
-}
-
-AFS_HD float2 twbd_entry(int idx, const float2* tw1024) {
-  const int row = idx / kGroup, t = idx - row * kGroup;
-  return row < 7 ? tw1024[(16 * (t >> 3) * (row + 1)) & 1023] : tw1024[t + 64 * (row - 7)];
+  const float2 wa = tw1024[(2 * t) & 1023], wb = tw1024[(16 * (t >> 3)) & 1023], wd = tw1024[t];
+  tw.a.re = wa.x; tw.a.im = wa.y;
+  tw.b.re = wb.x; tw.b.im = wb.y;
+  tw.d.re = wd.x; tw.d.im = wd.y;
 }
 
 // Phase A. in: z[r] = windowed (x[2n], x[2n+1]), n = j + 64 r.  out: exchange 1.
@@ -128,16 +132,18 @@ AFS_HD void phase_a(int j, cpx (&z)[8], const ThreadTw& tw, float* bufA) {
   float* im = bufA + 8 * kE1Stride;
   re[j] = z[0].re;
   im[j] = z[0].im;
+  cpx pw[8];
+  powers7(tw.a, pw);
 #pragma unroll
   for (int q = 1; q < 8; ++q) {
-    const cpx v = cmul(z[q], tw.a[q]);
+    const cpx v = cmul(z[q], pw[q]);
     re[q * kE1Stride + j] = v.re;
     im[q * kE1Stride + j] = v.im;
   }
 }
 
 // Phase B. thread t = q + 8*j0.
-AFS_HD void phase_b(int t, const float2* twbd, const float* bufA, float* bufB) {
+AFS_HD void phase_b(int t, const ThreadTw& tw, const float* bufA, float* bufB) {
   const int q = t & 7, j0 = t >> 3;
   const float* re = bufA;
   const float* im = bufA + 8 * kE1Stride;
@@ -150,14 +156,12 @@ AFS_HD void phase_b(int t, const float2* twbd, const float* bufA, float* bufB) {
   dft8(v);
   float* ore = bufB;
   float* oim = bufB + kHalf;
+  cpx pw[8];
+  powers7(tw.b, pw);
 #pragma unroll
   for (int p0 = 0; p0 < 8; ++p0) {
     cpx w = v[0];
-    if (p0 > 0) {
-      const float2 f = twbd[(p0 - 1) * kGroup + t];
-      cpx tb; tb.re = f.x; tb.im = f.y;
-      w = cmul(v[p0], tb);
-    }
+    if (p0 > 0) w = cmul(v[p0], pw[p0]);
     const int s = e2_slot(q, j0, p0);
     ore[s] = w.re;
     oim[s] = w.im;
@@ -192,7 +196,10 @@ AFS_HD int pskew(int k) { return k + (k >> 5); }
 
 // Phase D. thread u handles k = u + 64 m (m = 0..3) and its mirror 512 - k;
 // thread 0 also writes the self-paired bin 256.  Power spectrum into buffer B.
-AFS_HD void phase_d(int u, const float2* twbd, const float* bufA, float* power) {
+AFS_HD void phase_d(int u, const ThreadTw& tw, const float* bufA, float* power) {
+  // W_16^m = exp(-2 pi i m / 16), m = 0..3
+  const float w16re[4] = {1.0f, 0.92387953251128673848f, 0.70710678118654752440f, 0.38268343236508978178f};
+  const float w16im[4] = {0.0f, -0.38268343236508978178f, -0.70710678118654752440f, -0.92387953251128673848f};
   const float* re = bufA;
   const float* im = bufA + kHalf;
 #pragma unroll
@@ -205,8 +212,11 @@ AFS_HD void phase_d(int u, const float2* twbd, const float* bufA, float* power) 
     const float er = ar + br, ei = ai - bi;
     const float orr = ai + bi, oi = br - ar;
     cpx o2; o2.re = orr; o2.im = oi;
-    const float2 f = twbd[(7 + m) * kGroup + u];
-    cpx td; td.re = f.x; td.im = f.y;
+    cpx td = tw.d;  // W_1024^(u + 64 m) = W_1024^u * W_16^m
+    if (m > 0) {
+      cpx c; c.re = w16re[m]; c.im = w16im[m];
+      td = cmul(tw.d, c);
+    }
     const cpx t2 = cmul(o2, td);
     const float xr = er + t2.re, xi = ei + t2.im;
     const float yr = er - t2.re, yi = ei - t2.im;

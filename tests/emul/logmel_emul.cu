@@ -28,8 +28,6 @@ extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, con
   const int pad = center ? kNfft / 2 : 0;
   const int T = center ? static_cast<int>(1 + L / hop) : static_cast<int>(1 + (L - kNfft) / hop);
   std::vector<float> bufA(kBufA), bufB(kBufB), bufP(kMelBatch * kPStride, 0.f);
-  std::vector<float2> twbd(kTwbdEntries);
-  for (int i = 0; i < kTwbdEntries; ++i) twbd[i] = twbd_entry(i, tw.data());
   std::vector<ThreadTw> tws(kGroup);
   for (int t = 0; t < kGroup; ++t) load_thread_tw(tws[t], t, tw.data());
   for (int f = 0; f < T; ++f) {
@@ -46,11 +44,11 @@ extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, con
       }
       phase_a(t, z, tws[t], bufA.data());
     }
-    for (int t = 0; t < kGroup; ++t) phase_b(t, twbd.data(), bufA.data(), bufB.data());
+    for (int t = 0; t < kGroup; ++t) phase_b(t, tws[t], bufA.data(), bufB.data());
     for (int t = 0; t < kGroup; ++t) phase_c(t, bufB.data(), bufA.data());
     const int slot = f % kMelBatch;
     float* power = bufP.data() + slot * kPStride;
-    for (int t = 0; t < kGroup; ++t) phase_d(t, twbd.data(), bufA.data(), power);
+    for (int t = 0; t < kGroup; ++t) phase_d(t, tws[t], bufA.data(), power);
     if (power_out) for (int k = 0; k < kBins; ++k) power_out[static_cast<size_t>(f) * kBins + k] = power[pskew(k)];
     if (slot != kMelBatch - 1 && f + 1 != T) continue;
     for (int t = 0; t < kGroup; ++t) {  // batched mel projection, as the kernel's epilogue
