@@ -140,17 +140,18 @@ __device__ __forceinline__ float2 aug_pair(const S* __restrict__ x, int64_t idx,
 // Raw (augmented, reflect-padded, NOT yet windowed) samples 2n, 2n+1 for n = t + 64 r of the frame that
 // starts at sample s0.  Issued one frame ahead of their use so the global-load latency hides behind the
 // previous frame's FFT.
-template <bool AUG, typename S>
+// R0 = 0 loads the whole frame, R0 = 4 only its second half (see the hop == n_fft/2 reuse in the kernel).
+template <bool AUG, typename S, int R0>
 __device__ __forceinline__ void load_frame(const S* __restrict__ x, int64_t s0, int64_t L, int t,
                                            const AugState& aug, float2 (&raw)[8]) {
   const bool interior = (s0 >= 0) && (s0 + kNfft <= L);
   if (!AUG && interior && ((reinterpret_cast<uintptr_t>(x + s0) & (2 * sizeof(S) - 1)) == 0)) {
     const S* xb = x + s0 + 2 * t;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) raw[r] = ld_pair(xb + 128 * r, aug.pcm_scale);
+    for (int r = R0; r < 8; ++r) raw[r] = ld_pair(xb + 128 * r, aug.pcm_scale);
   } else {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = R0; r < 8; ++r) {
       int64_t i0 = s0 + 2 * (t + 64 * r), i1 = i0 + 1;
       if (!interior) {
         i0 = reflect_index(i0, L);
@@ -243,7 +244,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
   }
 
   float2 raw[8];
-  if (f_begin < f_end) load_frame<AUG, S>(x, static_cast<int64_t>(t0 + f_begin) * p.hop - p.pad, p.L, t, aug, raw);
+  if (f_begin < f_end) load_frame<AUG, S, 0>(x, static_cast<int64_t>(t0 + f_begin) * p.hop - p.pad, p.L, t, aug, raw);
+  const bool half_overlap = p.hop * 2 == kNfft;  // consecutive frames share half of their (padded, augmented) samples
   __syncthreads();
 
   for (int fl = f_begin; fl < f_end; ++fl) {
@@ -253,8 +255,16 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
       z[r].re = raw[r].x * win[r].x;
       z[r].im = raw[r].y * win[r].y;
     }
-    if (fl + 1 < f_end)  // prefetch the next frame while this one is transformed
-      load_frame<AUG, S>(x, static_cast<int64_t>(t0 + fl + 1) * p.hop - p.pad, p.L, t, aug, raw);
+    if (fl + 1 < f_end) {  // prefetch the next frame while this one is transformed
+      const int64_t s_next = static_cast<int64_t>(t0 + fl + 1) * p.hop - p.pad;
+      if (half_overlap) {  // its first half is this frame's second half: sample index s_next + 2(t+64r) = s0 + 2(t+64(r+4))
+#pragma unroll
+        for (int r = 0; r < 4; ++r) raw[r] = raw[r + 4];
+        load_frame<AUG, S, 4>(x, s_next, p.L, t, aug, raw);
+      } else {
+        load_frame<AUG, S, 0>(x, s_next, p.L, t, aug, raw);
+      }
+    }
     const int slot = (fl - f_begin) % kMelBatch;
     phase_a(t, z, tw, bufA);
     group_bar(grp);
