@@ -263,6 +263,106 @@ conv1_train_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g,
   }
 }
 
+// ------------------------------------------------------------------------------------------------ finalisers
+// One CTA of 64 threads (thread = channel) turns the autocorrelation partials into everything the forward and the
+// backward kernels need, in fp64: s[9], R[9][9] (kept for the backward), mean_nob, invstd, scale, shift, and the
+// running-statistics update of nn.BatchNorm2d.  stats layout (doubles): [0,9) s, [9,90) R row-major.
+__global__ void __launch_bounds__(64)
+conv1_train_stats_kernel(const float* __restrict__ partials, int n_part, double P, const float* __restrict__ w,
+                         const float* __restrict__ bias, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, double eps, double momentum, float* running_mean,
+                         float* running_var, double* __restrict__ stats, float* __restrict__ mean_nob,
+                         float* __restrict__ invstd, float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ double s_st[kAcStats];
+  __shared__ double s_R[81];
+  const int c = threadIdx.x;
+  if (c < kAcStats) {
+    double v = 0.0;
+    for (int i = 0; i < n_part; ++i) v += static_cast<double>(partials[static_cast<int64_t>(i) * kAcStats + c]);
+    s_st[c] = v;
+  }
+  __syncthreads();
+  if (c == 0) {
+    int k = 9;
+    for (int t = 0; t < 9; ++t)
+      for (int u = t; u < 9; ++u) {
+        s_R[t * 9 + u] = s_st[k];
+        s_R[u * 9 + t] = s_st[k];
+        ++k;
+      }
+  }
+  __syncthreads();
+  if (c < 9) stats[c] = s_st[c];
+  for (int i = c; i < 81; i += 64) stats[9 + i] = s_R[i];
+  double wc[9], m = 0.0;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    wc[t] = static_cast<double>(w[c * 9 + t]);
+    m += wc[t] * s_st[t];
+  }
+  m /= P;  // mean of the conv output without its bias
+  double var = 0.0;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int u = 0; u < 9; ++u) var += wc[t] * wc[u] * (s_R[t * 9 + u] / P - s_st[t] * s_st[u] / (P * P));
+  if (var < 0.0) var = 0.0;
+  const double is = 1.0 / sqrt(var + eps);
+  const double sc = static_cast<double>(gamma[c]) * is;
+  mean_nob[c] = static_cast<float>(m);
+  invstd[c] = static_cast<float>(is);
+  scale[c] = static_cast<float>(sc);
+  shift[c] = static_cast<float>(static_cast<double>(beta[c]) - m * sc);
+  if (running_mean != nullptr) {  // nn.BatchNorm2d in train(): unbiased running variance
+    running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * (m + static_cast<double>(bias[c])));
+    running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * var * (P / (P > 1.0 ? P - 1.0 : 1.0)));
+  }
+}
+
+// Backward partials [n_part][64][11] -> dW [64][9], dgamma, dbeta (fp64 accumulation, fixed order).
+__global__ void __launch_bounds__(64)
+conv1_train_grads_kernel(const float* __restrict__ partials, int n_part, double P, const double* __restrict__ stats,
+                         const float* __restrict__ w, const float* __restrict__ gamma, double eps,
+                         float* __restrict__ dW, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = threadIdx.x;
+  double t[kBwdStats];
+#pragma unroll
+  for (int i = 0; i < kBwdStats; ++i) t[i] = 0.0;
+  for (int p = 0; p < n_part; ++p) {
+    const float* row = partials + (static_cast<int64_t>(p) * kCT + c) * kBwdStats;
+#pragma unroll
+    for (int i = 0; i < kBwdStats; ++i) t[i] += static_cast<double>(row[i]);
+  }
+  const double* s = stats;
+  const double* R = stats + 9;
+  double wc[9], m = 0.0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    wc[k] = static_cast<double>(w[c * 9 + k]);
+    m += wc[k] * s[k];
+  }
+  m /= P;
+  double var = 0.0;
+#pragma unroll
+  for (int a = 0; a < 9; ++a)
+#pragma unroll
+    for (int b = 0; b < 9; ++b) var += wc[a] * wc[b] * (R[a * 9 + b] / P - s[a] * s[b] / (P * P));
+  if (var < 0.0) var = 0.0;
+  const double is = 1.0 / sqrt(var + eps);
+  const double sc = static_cast<double>(gamma[c]) * is;
+  const double a1 = t[0], a2 = t[1];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    double wr = 0.0;
+#pragma unroll
+    for (int u = 0; u < 9; ++u) wr += wc[u] * R[u * 9 + k];
+    const double q = is * (wr - m * s[k]);
+    dW[c * 9 + k] = static_cast<float>(sc * (t[2 + k] - (a1 / P) * s[k] - (a2 / P) * q));
+  }
+  dgamma[c] = static_cast<float>(a2);
+  dbeta[c] = static_cast<float>(a1);
+}
+
 }  // namespace
 }  // namespace afs
 
@@ -278,6 +378,37 @@ extern "C" int afs_conv1_autocorr(const float* x, int32_t N, int32_t H, int32_t 
   const int64_t total = static_cast<int64_t>(N) * H * Wd;
   const int blocks = afs_conv1_train_num_partials(0);
   conv1_autocorr_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(x, total, H, Wd, partials);
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
+}
+
+extern "C" int afs_conv1_train_stats(const float* ac_partials, int32_t N, int32_t H, int32_t Wd, const float* w,
+                                     const float* bias, const float* gamma, const float* beta, double eps,
+                                     double momentum, float* running_mean, float* running_var, double* stats,
+                                     float* mean_nob, float* invstd, float* scale, float* shift, afs_stream_t stream_) {
+  using namespace afs;
+  if (ac_partials == nullptr || w == nullptr || bias == nullptr || gamma == nullptr || beta == nullptr ||
+      stats == nullptr || mean_nob == nullptr || invstd == nullptr || scale == nullptr || shift == nullptr || N < 1 ||
+      H < 1 || Wd < 1 || (running_mean == nullptr) != (running_var == nullptr))
+    return AFS_ERR_INVALID_ARG;
+  const double P = static_cast<double>(N) * H * Wd;
+  conv1_train_stats_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream_)>>>(
+      ac_partials, afs_conv1_train_num_partials(0), P, w, bias, gamma, beta, eps, momentum, running_mean, running_var,
+      stats, mean_nob, invstd, scale, shift);
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
+}
+
+extern "C" int afs_conv1_train_grads(const float* bwd_partials, int32_t N, int32_t H, int32_t Wd, const double* stats,
+                                     const float* w, const float* gamma, double eps, float* dW, float* dgamma,
+                                     float* dbeta, afs_stream_t stream_) {
+  using namespace afs;
+  if (bwd_partials == nullptr || stats == nullptr || w == nullptr || gamma == nullptr || dW == nullptr ||
+      dgamma == nullptr || dbeta == nullptr || N < 1 || H < 1 || Wd < 1)
+    return AFS_ERR_INVALID_ARG;
+  const double P = static_cast<double>(N) * H * Wd;
+  conv1_train_grads_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream_)>>>(
+      bwd_partials, afs_conv1_train_num_partials(1), P, stats, w, gamma, eps, dW, dgamma, dbeta);
   AFS_LAUNCH_CHECK();
   return AFS_OK;
 }

@@ -130,63 +130,55 @@ def conv1_bn_act_pool3(x, w_folded, shift, negative_slope=0.0, tf32=False):
 
 class _Conv1TrainFn(torch.autograd.Function):
     """Conv2d(1->64,3x3,pad 1,bias) + BatchNorm2d(batch statistics) + ReLU/LeakyReLU + MaxPool2d(3,3), training mode,
-    as three sm_100a kernels (csrc/conv1_train.cu); gradients for conv.weight, conv.bias (zero), bn.weight, bn.bias."""
+    as five sm_100a kernels (csrc/conv1_train.cu: autocorrelation, statistics, forward; backward, gradients); gradients
+    for conv.weight, conv.bias (zero), bn.weight, bn.bias."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, momentum, eps, slope):
         h = _lib.lib()
         N, _, H, Wd = x.shape
-        P = float(N) * H * Wd
         x = x.contiguous()
-        ac = torch.empty((int(h.afs_conv1_train_num_partials(0)), 54), dtype=torch.float32, device=x.device)
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        ac = torch.empty((int(h.afs_conv1_train_num_partials(0)), 54), **f32)
         _lib.check(h.afs_conv1_autocorr(_ptr(x), N, H, Wd, _ptr(ac), _stream()), "afs_conv1_autocorr")
-        st = ac.double().sum(0)
-        s = st[:9]
-        iu = torch.triu_indices(9, 9, device=x.device)
-        R = torch.zeros((9, 9), dtype=torch.float64, device=x.device)
-        R[iu[0], iu[1]] = st[9:]
-        R = R + R.t() - torch.diag(torch.diagonal(R))
-        w64 = weight.detach().reshape(64, 9).double()
-        mean_nob = (w64 @ s) / P
-        cov = R / P - torch.outer(s, s) / (P * P)
-        var = torch.einsum("ct,tu,cu->c", w64, cov, w64).clamp_min_(0.0)
-        invstd = torch.rsqrt(var + eps)
-        scale = gamma.detach().double() * invstd
-        shift = beta.detach().double() - mean_nob * scale
         w32 = weight.detach().reshape(64, 9).contiguous()
-        scale32, shift32 = scale.float().contiguous(), shift.float().contiguous()
-        out = torch.empty((N, 64, H // 3, Wd // 3), dtype=torch.float32, device=x.device,
-                          memory_format=torch.channels_last)
-        _lib.check(h.afs_conv1_train_fwd(_ptr(x), N, H, Wd, _ptr(w32), _ptr(scale32), _ptr(shift32), float(slope),
+        b32, g32, be32 = bias.detach().contiguous(), gamma.detach().contiguous(), beta.detach().contiguous()
+        stats = torch.empty((90,), dtype=torch.float64, device=dev)
+        vec = torch.empty((4, 64), **f32)  # mean_nob, invstd, scale, shift
+        track = running_mean is not None and momentum is not None
+        _lib.check(h.afs_conv1_train_stats(_ptr(ac), N, H, Wd, _ptr(w32), _ptr(b32), _ptr(g32), _ptr(be32), float(eps),
+                                           float(momentum) if track else 0.0,
+                                           _ptr(running_mean) if track else None, _ptr(running_var) if track else None,
+                                           _ptr(stats), _ptr(vec[0]), _ptr(vec[1]), _ptr(vec[2]), _ptr(vec[3]),
+                                           _stream()), "afs_conv1_train_stats")
+        out = torch.empty((N, 64, H // 3, Wd // 3), memory_format=torch.channels_last, **f32)
+        _lib.check(h.afs_conv1_train_fwd(_ptr(x), N, H, Wd, _ptr(w32), _ptr(vec[2]), _ptr(vec[3]), float(slope),
                                          _ptr(out), _stream()), "afs_conv1_train_fwd")
-        if running_mean is not None and momentum is not None:  # nn.BatchNorm2d in train(): unbiased running variance
-            with torch.no_grad():
-                running_mean.mul_(1.0 - momentum).add_((mean_nob + bias.detach().double()).to(running_mean.dtype), alpha=momentum)
-                running_var.mul_(1.0 - momentum).add_((var * (P / max(P - 1.0, 1.0))).to(running_var.dtype), alpha=momentum)
-        ctx.save_for_backward(x, w32, scale32, shift32, mean_nob.float().contiguous(), invstd.float().contiguous())
-        ctx.stats = (s, R, w64, mean_nob, invstd, scale, P, float(slope))
+        ctx.save_for_backward(x, w32, g32, vec, stats)
+        ctx.consts = (float(eps), float(slope))
         ctx.shapes = (weight.shape, bias.shape)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        x, w32, scale32, shift32, mean32, invstd32 = ctx.saved_tensors
-        s, R, w64, mean_nob, invstd, scale, P, slope = ctx.stats
+        x, w32, g32, vec, stats = ctx.saved_tensors
+        eps, slope = ctx.consts
         h = _lib.lib()
         N, _, H, Wd = x.shape
+        f32 = dict(dtype=torch.float32, device=x.device)
         g = grad_out.contiguous(memory_format=torch.channels_last)
-        part = torch.empty((int(h.afs_conv1_train_num_partials(1)), 64, 11), dtype=torch.float32, device=x.device)
-        _lib.check(h.afs_conv1_train_bwd(_ptr(x), _ptr(g), N, H, Wd, _ptr(w32), _ptr(scale32), _ptr(shift32),
-                                         _ptr(mean32), _ptr(invstd32), slope, _ptr(part), _stream()),
+        part = torch.empty((int(h.afs_conv1_train_num_partials(1)), 64, 11), **f32)
+        _lib.check(h.afs_conv1_train_bwd(_ptr(x), _ptr(g), N, H, Wd, _ptr(w32), _ptr(vec[2]), _ptr(vec[3]),
+                                         _ptr(vec[0]), _ptr(vec[1]), slope, _ptr(part), _stream()),
                    "afs_conv1_train_bwd")
-        t = part.double().sum(0)
-        a1, a2, G = t[:, 0], t[:, 1], t[:, 2:]
-        Q = invstd[:, None] * (w64 @ R - mean_nob[:, None] * s[None, :])
-        dW = scale[:, None] * (G - (a1 / P)[:, None] * s[None, :] - (a2 / P)[:, None] * Q)
         w_shape, b_shape = ctx.shapes
-        return (None, dW.float().reshape(w_shape), torch.zeros(b_shape, dtype=torch.float32, device=x.device),
-                a2.float(), a1.float(), None, None, None, None, None)
+        dW = torch.empty((64, 9), **f32)
+        dgb = torch.empty((2, 64), **f32)
+        _lib.check(h.afs_conv1_train_grads(_ptr(part), N, H, Wd, _ptr(stats), _ptr(w32), _ptr(g32), eps, _ptr(dW),
+                                           _ptr(dgb[0]), _ptr(dgb[1]), _stream()), "afs_conv1_train_grads")
+        return (None, dW.reshape(w_shape), torch.zeros(b_shape, **f32), dgb[0], dgb[1], None, None, None, None, None)
 
 
 def conv1_bn_act_pool3_train(x, conv, bn, negative_slope=0.0):

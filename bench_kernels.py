@@ -147,5 +147,51 @@ def main():
     report("vote_kernel 5-way", "episode", 4096, 4 * 75 * 5 + 4 * 75 * 3, ms, mn, note="logits + q_start + target + pred")
 
 
+def extra():
+    """Kernels outside the evaluation step: PCM16 front-end, spectrogram augmentation, ResNet-12 block tail, and the
+    fused training block 1."""
+    import random
+
+    from audio_fewshot_b200 import augment as aug
+    dev = torch.device("cuda", 0)
+    flush = torch.empty(160 * 2 ** 20 // 4, dtype=torch.float32, device=dev)
+    fr = LogMelFrontEnd(hop_length=512, n_mels=128, mean=-15.0, std=26.0).to(dev).eval()
+    pcm = (torch.randn(800, 80000, device=dev) * 0.1 * 32768).round().clamp(-32768, 32767).to(torch.int16)
+    out = torch.empty(800, 1, 128, 157, device=dev)
+    ms, mn = timeit(lambda: fr(pcm, out=out), flush=flush)
+    report("logmel_kernel<false, int16> S5 (16-bit PCM input)", "clip", 800, 2 * 80000 + 4 * 128 * 157, ms, mn)
+
+    img = torch.randn(800, 1, 128, 157, device=dev)
+    for t in ("noise_suppression", "background_subtraction", "cutout"):
+        random.seed(1)
+        ms, mn = timeit(lambda: aug.augment_spectrogram(img, -15.0, 26.0, augmentation_type=t), flush=flush)
+        report("spec_augment_kernel " + t + " [800,1,128,157]", "clip", 800, 2 * 4 * 128 * 157, ms, mn)
+
+    a = torch.randn(320, 64, 128, 157, device=dev).contiguous(memory_format=torch.channels_last)
+    b = torch.randn_like(a).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(64, device=dev)
+    ms, mn = timeit(lambda: ops.add_bias_act_pool(a, b, bias, 0.1, 2), flush=flush)
+    report("add_bias_act_pool_nhwc_kernel k=2 [320,64,128,157] (ResNet-12 layer-1 tail)", "clip", 320,
+           4 * 64 * 128 * 157 * 2 + 4 * 64 * 64 * 78, ms, mn)
+
+    conv = torch.nn.Conv2d(1, 64, 3, padding=1).to(dev)
+    bn = torch.nn.BatchNorm2d(64).to(dev).train()
+    x = torch.randn(200, 1, 128, 157, device=dev)
+    g = torch.randn(200, 64, 42, 52, device=dev).contiguous(memory_format=torch.channels_last)
+    y = ops.conv1_bn_act_pool3_train(x, conv, bn, 0.0)
+    ms, mn = timeit(lambda: ops.conv1_bn_act_pool3_train(x, conv, bn, 0.0), flush=flush)
+    report("conv1 training block forward (autocorr + fwd kernels + batch-stat algebra) [200,1,128,157]", "clip", 200,
+           4 * 128 * 157 * 2 + 4 * 64 * 42 * 52, ms, mn, flops_per_unit=2 * 64 * 42 * 52 * 81)
+
+    def bwd():
+        y = ops.conv1_bn_act_pool3_train(x, conv, bn, 0.0)
+        y.backward(g)
+
+    ms_fb, mn_fb = timeit(bwd, flush=flush)
+    report("conv1 training block forward + backward [200,1,128,157]", "clip", 200,
+           4 * 128 * 157 * 3 + 2 * 4 * 64 * 42 * 52, ms_fb, mn_fb, flops_per_unit=3 * 2 * 64 * 42 * 52 * 81)
+
+
 if __name__ == "__main__":
     main()
+    extra()

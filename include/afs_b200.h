@@ -138,6 +138,17 @@ int afs_conv1_bn_act_pool3_fwd_tf32(const float* x, int32_t N, int32_t H, int32_
  *     dW[c,t] = scale_c (G[c,t] - A1_c/P s[t] - A2_c/P Q[c,t]), Q = invstd_c ((w_c R)[t] - mean_nob_c s[t]).        */
 int32_t afs_conv1_train_num_partials(int32_t which);
 int afs_conv1_autocorr(const float* x, int32_t N, int32_t H, int32_t Wd, float* partials, afs_stream_t stream);
+/* afs_conv1_train_stats: autocorrelation partials -> stats (90 doubles: s[9], R[9][9], kept for the backward),
+ * mean_nob / invstd / scale / shift [64] in fp64 arithmetic, and nn.BatchNorm2d's running-statistics update
+ * (running_mean / running_var nullable together; bias only enters the running mean).
+ * afs_conv1_train_grads: backward partials + stats -> dW [64*9], dgamma [64], dbeta [64] (fp64, fixed order).   */
+int afs_conv1_train_stats(const float* ac_partials, int32_t N, int32_t H, int32_t Wd, const float* w,
+                          const float* bias, const float* gamma, const float* beta, double eps, double momentum,
+                          float* running_mean, float* running_var, double* stats, float* mean_nob, float* invstd,
+                          float* scale, float* shift, afs_stream_t stream);
+int afs_conv1_train_grads(const float* bwd_partials, int32_t N, int32_t H, int32_t Wd, const double* stats,
+                          const float* w, const float* gamma, double eps, float* dW, float* dgamma, float* dbeta,
+                          afs_stream_t stream);
 int afs_conv1_train_fwd(const float* x, int32_t N, int32_t H, int32_t Wd, const float* w, const float* scale,
                         const float* shift, float negative_slope, float* out, afs_stream_t stream);
 int afs_conv1_train_bwd(const float* x, const float* grad_out, int32_t N, int32_t H, int32_t Wd, const float* w,
