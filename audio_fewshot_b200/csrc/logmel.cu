@@ -45,7 +45,7 @@ constexpr int kThreads = 256;
 constexpr int kGroups = kThreads / kGroup;
 constexpr int kFramesPerCta = 32;
 constexpr int kFramesPerGroup = kFramesPerCta / kGroups;
-constexpr int kMaxNnz = 3072;  // floats of the ELL weight table (128 slaney mels: 1 440)
+constexpr int kMaxNnz = 4096;  // floats of the ELL weight table (128 slaney mels: 1 440; 40 mels: 3 584)
 constexpr int kTileStride = kFramesPerCta + 1;
 constexpr int kGroupFloats = kBufA + kBufB + kMelBatch * kPStride;
 

@@ -72,3 +72,28 @@ extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, con
 
 // slot bijection check for the exchange-2 swizzle
 extern "C" int emul_e2_slot(int q, int j0, int p0) { return e2_slot(q, j0, p0); }
+
+// The kernel's ELL weight table (pack_mel_ell) expanded back to a dense [513, n_mels] matrix, plus, per warp-pass,
+// the number of table rows: lets the test check that the table reproduces the filterbank exactly, that every
+// filter is owned by exactly one (thread, pass), and how much padding the layout costs.  Returns the table size.
+extern "C" int emul_mel_ell_dense(const float* fb, int n_mels, float* dense /*[513, n_mels]*/, int* owner_count /*[n_mels]*/) {
+  std::vector<int> band;
+  std::vector<float> weights;
+  const int n = pack_mel_ell(fb, n_mels, band, weights);
+  for (int i = 0; i < kBins * n_mels; ++i) dense[i] = 0.f;
+  for (int m = 0; m < n_mels; ++m) owner_count[m] = 0;
+  for (int t = 0; t < kGroup; ++t) {
+    const int ids[2] = {t < n_mels ? t : -1, n_mels - 1 - t >= kGroup ? n_mels - 1 - t : -1};
+    for (int i = 0; i < 2; ++i) {
+      const int m = ids[i];
+      if (m < 0) continue;
+      owner_count[m] += 1;
+      const int lo = band[m], len = band[kMaxMels + m], off = band[2 * kMaxMels + m];
+      if (off % kEllStride != (t & 31)) return -1;  // weight i of lane l must sit at column l of its table row
+      for (int j = 0; j < len; ++j) dense[(lo + j) * n_mels + m] = weights[off + j * kEllStride];
+    }
+  }
+  return n;
+}
+
+extern "C" int emul_pskew(int k) { return pskew(k); }

@@ -81,3 +81,25 @@ def test_pure_tone_lands_in_the_right_mel_bin(emul):
     fb = fe.mel_filterbank()
     k = int(round(f0 / (sr / 1024)))
     assert int(out[:, 5].argmax()) == int(fb[k].argmax())
+
+
+@pytest.mark.parametrize("n_mels", [128, 80, 64, 40])
+def test_ell_weight_table_reproduces_the_filterbank(emul, n_mels):
+    """pack_mel_ell (the layout the kernel reads: [warp-pass][i][lane]) expands back to exactly the dense slaney
+    filterbank, every filter has exactly one owner thread, and the table fits the kernel's shared-memory budget."""
+    fb = fe.mel_filterbank(n_mels=n_mels)
+    dense = np.zeros((513, n_mels), np.float32)
+    owners = np.zeros(n_mels, np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = emul.emul_mel_ell_dense(vp(np.ascontiguousarray(fb)), n_mels, vp(dense), vp(owners))
+    assert 0 < n <= 4096 and n % 32 == 0  # kMaxNnz of csrc/logmel.cu
+    assert (owners == 1).all()
+    assert np.array_equal(dense, fb)
+
+
+def test_power_skew_is_injective_and_conflict_free_for_phase_d(emul):
+    sk = [emul.emul_pskew(k) for k in range(513)]
+    assert sk == sorted(set(sk)) and sk[-1] < 532  # kPStride
+    for m in range(4):  # a warp of phase D writes bins u + 64 m, u = 32 h .. 32 h + 31: 32 distinct banks
+        for h in range(2):
+            assert len({sk[u + 64 * m] % 32 for u in range(32 * h, 32 * h + 32)}) == 32
