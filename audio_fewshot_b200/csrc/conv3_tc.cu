@@ -13,8 +13,9 @@
 // UMMA operand [pixel][8 channels = 32 bytes] (32-byte swizzle, 8-pixel atoms of 256 bytes back to back), the A
 // operand of tap (dy,dx) for 128 consecutive output positions is the same buffer with its start address advanced
 // by (dy*HP + dx)*32 bytes: the nine taps need no im2col copies at all, and every A tile is one contiguous 4 KB
-// span (33 instead of 32 shared-memory lines when the shift is odd).  Positions with x >= W are junk rows of the GEMM (2 of every HP) and are
-// simply not stored.
+// span (33 instead of 32 shared-memory lines when the shift is odd).  The hardware applies the swizzle to absolute
+// address bits (checked on B200: the descriptor's base-offset field must stay 0 for shifted starts).  Positions
+// with x >= W are junk rows of the GEMM (2 of every HP) and are simply not stored.
 //
 // A tile is R image rows of one image = NM*128 accumulator rows (R*HP <= NM*128; block 2: R = 6, HP = 54, NM = 3).
 // Roles (one persistent CTA per SM, 352 threads):
@@ -27,6 +28,7 @@
 //   warps 0-3  epilogue: tcgen05.ld 8 channels at a time, + folded shift, activation, then either a direct
 //              channels-last store or the 3x3/3 max-pool through a small shared staging tile.
 // All 64x64x9 folded weights stay resident in shared memory (144 KB, pre-packed and TF32-rounded on the host).
+// A second kernel below runs the same scheme on CTA pairs (tcgen05 cta_group::2); see its comment for the outcome.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
