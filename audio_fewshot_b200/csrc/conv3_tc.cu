@@ -58,57 +58,7 @@ struct Bars3 {
   uint64_t acc_full[2], acc_empty[2];
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive3(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// K-major SWIZZLE_32B operand descriptor: rows of 32 bytes (8 TF32 values = one MMA K step), 8-row atoms of 256
-// bytes `sbo` apart, LBO unused.  The swizzle (16-byte chunk index ^= address bit 7) is a function of the shared
-// memory address, so a start address advanced by whole rows selects a shifted window of the same buffer; the
-// base-offset field carries the row phase of a start that is not atom-aligned.
-__device__ __forceinline__ uint64_t desc_kmajor_sw32(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
-  uint64_t d = static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(base_off & 7u) << 49;
-  d |= static_cast<uint64_t>(6) << 61;
-  return d;
-}
-// One lane polls the mbarrier, the warp then reconverges: 32 lanes spinning on try_wait are 32 shared-memory
-// accesses per probe, which the profiler shows as bank-conflict wavefronts competing with the tensor core's reads.
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
-  if (lane == 0) mbar_wait(bar, parity);
-  __syncwarp();
-}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-      : "r"(taddr));
-}
 
 struct Conv3Geom {
   int N, H, W, HP;        // HP = W + 2: padded row pitch
@@ -174,7 +124,7 @@ __device__ __forceinline__ void producer_loop(const float* x, const Conv3Geom& g
       if (pending > 0 && !ready) {
         cp_async_wait<0>();
         fence_async_smem();
-        for (; pending > 0; --pending) mbar_arrive3(smem_u32(&full[(gs - pending) % RING]));
+        for (; pending > 0; --pending) mbar_arrive(smem_u32(&full[(gs - pending) % RING]));
       }
       if (!ready) mbar_wait_warp(smem_u32(&empty[st]), ph ^ 1u, lane);
       plan.issue(ring_base + st * stage_bytes, kc, ptid, g.halo);
@@ -182,14 +132,14 @@ __device__ __forceinline__ void producer_loop(const float* x, const Conv3Geom& g
       if (pending > static_cast<uint32_t>(AHEAD)) {
         cp_async_wait<AHEAD>();
         fence_async_smem();
-        mbar_arrive3(smem_u32(&full[(gs + 1 - pending) % RING]));
+        mbar_arrive(smem_u32(&full[(gs + 1 - pending) % RING]));
         --pending;
       }
     }
   }
   cp_async_wait<0>();
   fence_async_smem();
-  for (; pending > 0; --pending) mbar_arrive3(smem_u32(&full[(gs - pending) % RING]));
+  for (; pending > 0; --pending) mbar_arrive(smem_u32(&full[(gs - pending) % RING]));
 }
 
 // Epilogue of one tile by the four epilogue warps (accumulator row == TMEM lane == tid): tcgen05.ld 8 channels at a
@@ -359,7 +309,7 @@ conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk
       mbar_wait_warp(smem_u32(&bars.acc_full[ab]), aph, lane);
       fence_after();
       epilogue_tile<NM>(g, n, y0, true, tmem_base + ab * (NM * kC3) + t_lane, s_stage, s_shift, out, tid, [&]() {
-        if (lane == 0) mbar_arrive3(smem_u32(&bars.acc_empty[ab]));
+        if (lane == 0) mbar_arrive(smem_u32(&bars.acc_empty[ab]));
       });
     }
   }
@@ -386,49 +336,6 @@ struct BarsP {
   uint64_t full[kRingP], empty[kRingP];
   uint64_t acc_full[2], acc_empty[2];
 };
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
-  const uint32_t acc = accumulate ? 1u : 0u;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void commit_pair(uint32_t bar) {  // arrives on the same barrier of both CTAs
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(static_cast<uint16_t>(3))
-               : "memory");
-}
 
 template <int NM>
 __global__ void __launch_bounds__(kThreads3, 1)

@@ -22,9 +22,14 @@
 #include <limits.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
+#include "topk.cuh"
 
 namespace afs {
 namespace {
+
+using namespace tc;
+using namespace topk;
 
 constexpr int kTcThreads = 128;
 constexpr int kTcRows = 128;   // UMMA M: query descriptors per tile == TMEM lanes == threads
@@ -32,55 +37,9 @@ constexpr int kTcCols = 128;   // UMMA N: support descriptors per column tile ==
 constexpr int kTcMaxC = 128;
 constexpr int kTcMaxWay = 32;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-
-// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
-// [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48),
-// layout type SWIZZLE_NONE (0) in [61,64).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  return d;
-}
-
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (1 << 4), A and B TF32 (2 << 7, 2 << 10),
 // both K-major (bits 15, 16 clear), N >> 3 in [17,23), M >> 4 in [24,29).
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kTcCols >> 3) << 17) | ((kTcRows >> 4) << 24);
-
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ float to_tf32(float x) {  // round to nearest (the MMA itself would truncate: biased)
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 
 // One thread writes one L2-normalised, TF32-rounded descriptor (C channels of feat[row, :, m], channel
 // stride HW) into row r of a K-major operand tile; a null src writes zeros.  Loads are issued 16 at a
@@ -121,47 +80,6 @@ __device__ __forceinline__ void fill_row(float* tile, int r, const float* __rest
     float4 v = dst[c4 * kTcRows];
     v.x = to_tf32(v.x * inv); v.y = to_tf32(v.y * inv); v.z = to_tf32(v.z * inv); v.w = to_tf32(v.w * inv);
     dst[c4 * kTcRows] = v;
-  }
-}
-
-// ---- branch-free streaming top-NK -------------------------------------------------------------------
-// A relation value and its column inside the 128-column tile travel as ONE sortable 32-bit key: the fp32
-// bit pattern mapped to an order-preserving unsigned integer, low 7 bits replaced by (127 - column).  A
-// sorted insert is then 2*NK-1 integer min/max instructions with no branch (the per-lane `if (x > worst)`
-// of a scalar insertion diverges on almost every column: 32 lanes each own a different row).  The 7 bits
-// cost 2^-16 relative resolution on the value, below the TF32 rounding of the operands; ties resolve
-// to the lower column, as torch.topk / the fp32 path.
-__device__ __forceinline__ uint32_t topk_key(uint32_t bits, int col_in_tile) {
-  const uint32_t mono = bits ^ (static_cast<uint32_t>(static_cast<int32_t>(bits) >> 31) | 0x80000000u);
-  return (mono & ~127u) | static_cast<uint32_t>(127 - col_in_tile);
-}
-__device__ __forceinline__ float topk_key_value(uint32_t key) {
-  const uint32_t mono = key & ~127u;
-  const uint32_t bits = (mono & 0x80000000u) ? (mono ^ 0x80000000u) : ~mono;
-  return __uint_as_float(bits);
-}
-template <int NK>
-__device__ __forceinline__ void topk_push(uint32_t (&t)[NK], uint32_t key) {
-#pragma unroll
-  for (int k = 0; k < NK; ++k) {
-    const uint32_t hi = max(t[k], key);
-    key = min(t[k], key);
-    t[k] = hi;
-  }
-}
-// scalar sorted insert of (value, global column) into the running result (once per selected key per tile)
-template <int NK>
-__device__ __forceinline__ void topk_merge(float (&tv)[NK], int (&ti)[NK], float x, int col) {
-  if (x > tv[NK - 1] || (x == tv[NK - 1] && col < ti[NK - 1])) {
-    tv[NK - 1] = x;
-    ti[NK - 1] = col;
-#pragma unroll
-    for (int k = NK - 1; k > 0; --k) {
-      if (tv[k] > tv[k - 1] || (tv[k] == tv[k - 1] && ti[k] < ti[k - 1])) {
-        const float fv = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = fv;
-        const int iv = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = iv;
-      }
-    }
   }
 }
 
@@ -248,8 +166,8 @@ dn4_tc_kernel(const float* __restrict__ feat, const int32_t* __restrict__ cls_ro
         if (tid == 0) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           for (int k8 = 0; k8 < C / 8; ++k8) {
-            const uint64_t da = umma_desc(a_addr + static_cast<uint32_t>(k8) * 2u * lbo, lbo, sbo);
-            const uint64_t db = umma_desc(b_addr + static_cast<uint32_t>(k8) * 2u * lbo, lbo, sbo);
+            const uint64_t da = desc_kmajor_noswizzle(a_addr + static_cast<uint32_t>(k8) * 2u * lbo, lbo, sbo);
+            const uint64_t db = desc_kmajor_noswizzle(b_addr + static_cast<uint32_t>(k8) * 2u * lbo, lbo, sbo);
             const uint32_t accumulate = k8 > 0 ? 1u : 0u;
             asm volatile(
                 "{\n\t"

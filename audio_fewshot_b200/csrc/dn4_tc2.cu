@@ -21,9 +21,14 @@
 #include <limits.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
+#include "topk.cuh"
 
 namespace afs {
 namespace {
+
+using namespace tc;
+using namespace topk;
 
 constexpr int kThreads2 = 192;
 constexpr int kRows2 = 128;   // UMMA M
@@ -60,64 +65,7 @@ bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint32_t C) {
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait2(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): rows are 128 B, 8-row groups 1024 B
-// apart (SBO), LBO unused (1), version 1, layout type 2.  `addr` may point 32*k bytes into the first row to
-// select the k-th group of 8 channels inside the swizzle atom.
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
-  uint64_t d = static_cast<uint64_t>((addr >> 4) & 0x3FFFu);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024u >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-
 constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((kCols2 >> 3) << 17) | ((kRows2 >> 4) << 24);
-
-__device__ __forceinline__ void tmem_ld32b(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // ---- pre-pass: normalise, round to TF32, write K-major; queries compacted in output-row order
 __global__ void __launch_bounds__(128)
@@ -160,47 +108,6 @@ struct Bars {
   uint64_t tmem_full[2], tmem_empty[2];
 };
 
-// ---- branch-free streaming top-NK -------------------------------------------------------------------
-// A relation value and its column inside the 128-column tile travel as ONE sortable 32-bit key: the fp32
-// bit pattern mapped to an order-preserving unsigned integer, low 7 bits replaced by (127 - column).  A
-// sorted insert is then 2*NK-1 integer min/max instructions with no branch (the per-lane `if (x > worst)`
-// of a scalar insertion diverges on almost every column: 32 lanes each own a different row).  The 7 bits
-// cost 2^-16 relative resolution on the value, below the TF32 rounding of the operands; ties resolve
-// to the lower column, as torch.topk / the fp32 path.
-__device__ __forceinline__ uint32_t topk_key(uint32_t bits, int col_in_tile) {
-  const uint32_t mono = bits ^ (static_cast<uint32_t>(static_cast<int32_t>(bits) >> 31) | 0x80000000u);
-  return (mono & ~127u) | static_cast<uint32_t>(127 - col_in_tile);
-}
-__device__ __forceinline__ float topk_key_value(uint32_t key) {
-  const uint32_t mono = key & ~127u;
-  const uint32_t bits = (mono & 0x80000000u) ? (mono ^ 0x80000000u) : ~mono;
-  return __uint_as_float(bits);
-}
-template <int NK>
-__device__ __forceinline__ void topk_push(uint32_t (&t)[NK], uint32_t key) {
-#pragma unroll
-  for (int k = 0; k < NK; ++k) {
-    const uint32_t hi = max(t[k], key);
-    key = min(t[k], key);
-    t[k] = hi;
-  }
-}
-// scalar sorted insert of (value, global column) into the running result (once per selected key per tile)
-template <int NK>
-__device__ __forceinline__ void topk_merge(float (&tv)[NK], int (&ti)[NK], float x, int col) {
-  if (x > tv[NK - 1] || (x == tv[NK - 1] && col < ti[NK - 1])) {
-    tv[NK - 1] = x;
-    ti[NK - 1] = col;
-#pragma unroll
-    for (int k = NK - 1; k > 0; --k) {
-      if (tv[k] > tv[k - 1] || (tv[k] == tv[k - 1] && ti[k] < ti[k - 1])) {
-        const float fv = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = fv;
-        const int iv = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = iv;
-      }
-    }
-  }
-}
-
 template <int NK>
 __global__ void __launch_bounds__(kThreads2)
 dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_s,
@@ -217,7 +124,7 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   const int lane = tid & 31;
   const int KH = C / 32;  // 128-byte K blocks per descriptor
   const uint32_t blk_bytes = static_cast<uint32_t>(KH) * kAtomBytes;
-  const uint32_t base = (s_u32(s_raw) + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
+  const uint32_t base = (smem_u32(s_raw) + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
   const uint32_t a_addr = base;
   const uint32_t b_addr0 = base + blk_bytes;
 
@@ -226,18 +133,18 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     s_qbase[tid] = cls_row[g] - g * S;
   }
   if (tid == 0) {
-    mbar_init(s_u32(&bars.full_a), 1);
-    mbar_init(s_u32(&bars.empty_a), 1);
+    mbar_init(smem_u32(&bars.full_a), 1);
+    mbar_init(smem_u32(&bars.empty_a), 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(s_u32(&bars.full_b[s]), 1);
-      mbar_init(s_u32(&bars.empty_b[s]), 1);
-      mbar_init(s_u32(&bars.tmem_full[s]), 1);
-      mbar_init(s_u32(&bars.tmem_empty[s]), 4);  // one arrival per epilogue warp
+      mbar_init(smem_u32(&bars.full_b[s]), 1);
+      mbar_init(smem_u32(&bars.empty_b[s]), 1);
+      mbar_init(smem_u32(&bars.tmem_full[s]), 1);
+      mbar_init(smem_u32(&bars.tmem_empty[s]), 4);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {  // two 128-column accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&s_tmem)), "r"(256u));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(256u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -257,20 +164,20 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (lane == 0) {
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-        mbar_wait2(s_u32(&bars.empty_a), (tcount & 1u) ^ 1u);  // MMAs of the previous tile have read A
-        mbar_expect_tx(s_u32(&bars.full_a), blk_bytes);
+        mbar_wait(smem_u32(&bars.empty_a), (tcount & 1u) ^ 1u);  // MMAs of the previous tile have read A
+        mbar_expect_tx(smem_u32(&bars.full_a), blk_bytes);
         const int qrow0 = out0 * HW + tile * kRows2;
         for (int kh = 0; kh < KH; ++kh)
-          tma_load_2d(a_addr + static_cast<uint32_t>(kh) * kAtomBytes, &map_q, kh * 32, qrow0, s_u32(&bars.full_a));
+          tma_load_2d(a_addr + static_cast<uint32_t>(kh) * kAtomBytes, &map_q, kh * 32, qrow0, smem_u32(&bars.full_a));
         for (int w = 0; w < W; ++w) {
           const int srow_base = (e * W + w) * S * HW;
           for (int ct = 0; ct < n_ctiles; ++ct, ++it) {
             const uint32_t st = it & 1u, ph = (it >> 1) & 1u;
-            mbar_wait2(s_u32(&bars.empty_b[st]), ph ^ 1u);
-            mbar_expect_tx(s_u32(&bars.full_b[st]), blk_bytes);
+            mbar_wait(smem_u32(&bars.empty_b[st]), ph ^ 1u);
+            mbar_expect_tx(smem_u32(&bars.full_b[st]), blk_bytes);
             for (int kh = 0; kh < KH; ++kh)
               tma_load_2d(b_addr0 + st * blk_bytes + static_cast<uint32_t>(kh) * kAtomBytes, &map_s, kh * 32,
-                          srow_base + ct * kCols2, s_u32(&bars.full_b[st]));
+                          srow_base + ct * kCols2, smem_u32(&bars.full_b[st]));
           }
         }
       }
@@ -280,12 +187,12 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (lane == 0) {
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-        mbar_wait2(s_u32(&bars.full_a), tcount & 1u);
+        mbar_wait(smem_u32(&bars.full_a), tcount & 1u);
         for (int w = 0; w < W; ++w) {
           for (int ct = 0; ct < n_ctiles; ++ct, ++it) {
             const uint32_t st = it & 1u, ph = (it >> 1) & 1u;
-            mbar_wait2(s_u32(&bars.full_b[st]), ph);
-            mbar_wait2(s_u32(&bars.tmem_empty[st]), ph ^ 1u);  // epilogue has drained this accumulator
+            mbar_wait(smem_u32(&bars.full_b[st]), ph);
+            mbar_wait(smem_u32(&bars.tmem_empty[st]), ph ^ 1u);  // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_tmem = tmem_base + st * kCols2;
             for (int kh = 0; kh < KH; ++kh) {
@@ -303,11 +210,11 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     : "memory");
               }
             }
-            umma_commit(s_u32(&bars.empty_b[st]));    // operand stage reusable once these MMAs finish
-            umma_commit(s_u32(&bars.tmem_full[st]));  // accumulator ready for the epilogue
+            commit(smem_u32(&bars.empty_b[st]));    // operand stage reusable once these MMAs finish
+            commit(smem_u32(&bars.tmem_full[st]));  // accumulator ready for the epilogue
           }
         }
-        umma_commit(s_u32(&bars.empty_a));
+        commit(smem_u32(&bars.empty_a));
       }
     }
   } else {
@@ -326,7 +233,7 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (int k = 0; k < NK; ++k) { tv[k] = -INFINITY; ti[k] = INT_MAX; }
         for (int ct = 0; ct < n_ctiles; ++ct, ++it) {
           const uint32_t st = it & 1u, ph = (it >> 1) & 1u;
-          mbar_wait2(s_u32(&bars.tmem_full[st]), ph);
+          mbar_wait(smem_u32(&bars.tmem_full[st]), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           uint32_t tk[NK];
 #pragma unroll
@@ -336,7 +243,7 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           for (int c0 = 0; c0 < kCols2; c0 += 32) {
             uint32_t v[32];
             if (c0 >= valid) break;  // tile-uniform: nothing left in this column tile
-            tmem_ld32b(t_row + st * kCols2 + static_cast<uint32_t>(c0), v);
+            tmem_ld32(t_row + st * kCols2 + static_cast<uint32_t>(c0), v);
             if (c0 + 32 <= valid) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) topk_push<NK>(tk, topk_key(v[j], c0 + j));
@@ -356,7 +263,7 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             if (tk[k] != 0u) topk_merge<NK>(tv, ti, topk_key_value(tk[k]), ct * kCols2 + 127 - static_cast<int>(tk[k] & 127u));
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(s_u32(&bars.tmem_empty[st]));
+          if (lane == 0) mbar_arrive(smem_u32(&bars.tmem_empty[st]));
         }
         if (live) {
           float sum = 0.f;
