@@ -145,3 +145,26 @@ def test_tta_helpers_match_live_reference(reference):
         a = rt.augment_images_with_mask(torch.from_numpy(img), torch.from_numpy(r), s, q, lambda x: x + 1, 2)
         b = tta.augment_images_with_mask(torch.from_numpy(img), torch.from_numpy(r), s, q, lambda x: x + 1, 2)
         assert torch.equal(a, b)
+
+
+def test_bench_reference_arm_line_and_no_cuda_refusal():
+    """`bench.py --impl reference` (the oracle port timed on the host cores) prints ONE JSON line with the contract's
+    keys; the B200 arm refuses to run without a CUDA device instead of falling back."""
+    import json
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "episodes/sec" and d["higher_is_better"] is True
+    assert d["metric"].startswith("episodes/sec (5w5s15q") and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    ours = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                          capture_output=True, text=True, env=env, timeout=300)
+    assert ours.returncode != 0 and "no CPU fallback" in (ours.stderr + ours.stdout)
+    assert not [l for l in ours.stdout.splitlines() if l.startswith("{")]
