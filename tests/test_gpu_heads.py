@@ -346,3 +346,30 @@ def test_bdc_backward_matches_autograd_of_oracle(cuda, B, C, H, Wd, triu):
     assert (xg.grad.cpu().double() - xc.grad).abs().max().item() <= 2e-3 * xc.grad.abs().max().item()
     assert tg.grad.shape == (1, 1)
     assert abs(tg.grad.item() - tc.grad.item()) <= 2e-3 * abs(tc.grad.item()) + 1e-6
+
+
+def test_utils_module_mirrors_reference_helpers(cuda, golden):
+    """audio_fewshot_b200.utils: reference-named helpers (accuracy, majority_vote, vote_catagorical_acc,
+    average_logits) against the oracle restatements pinned to the reference goldens."""
+    from audio_fewshot_b200 import utils as U
+    rng = np.random.default_rng(12)
+    nums = rng.integers(1, 5, size=37)
+    logits = torch.from_numpy(rng.standard_normal((int(nums.sum()), 5)).astype(np.float32))
+    want_vote = heads.majority_vote(logits, nums, tie_rule="smallest")
+    got_vote = U.majority_vote(logits.to(cuda), torch.from_numpy(nums), tie_rule="smallest")
+    assert got_vote.dtype == torch.float32 and not got_vote.is_cuda
+    assert np.array_equal(got_vote.numpy(), np.asarray(want_vote, dtype=np.float32))
+    want_avg = heads.average_logits(logits, nums)
+    got_avg = U.average_logits(logits.to(cuda), nums.tolist())
+    assert torch.allclose(got_avg.cpu(), torch.as_tensor(np.asarray(want_avg), dtype=torch.float32), atol=1e-6)
+    target = torch.from_numpy(rng.integers(0, 5, size=37)).float()
+    acc = U.vote_catagorical_acc(target, got_vote)
+    assert abs(float(acc) - 100.0 * float((got_vote == target).float().mean())) < 1e-4
+    out = torch.from_numpy(rng.standard_normal((64, 5)).astype(np.float32)).to(cuda)
+    tgt = torch.from_numpy(rng.integers(0, 5, size=64)).to(cuda)
+    a1 = U.accuracy(out, tgt)
+    assert isinstance(a1, float) and abs(a1 - 100.0 * float((out.argmax(1) == tgt).float().mean())) < 1e-4
+    a2 = U.accuracy(out, tgt, topk=2)
+    assert a2 >= a1
+    m, h = U.mean_confidence_interval([80.0, 82.0, 78.0, 85.0])
+    assert abs(m - 81.25) < 1e-9 and h > 0
