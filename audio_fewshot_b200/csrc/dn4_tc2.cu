@@ -15,8 +15,14 @@
 // descriptors K-major ([descriptor][C]) with queries compacted in output order and supports in class
 // order, so every operand tile is a contiguous row range: a plain 2-D TMA box.
 //
-// Built for C % 32 == 0, C <= 128 (one 128-byte swizzle atom per 32 channels); other widths use
-// dn4_tc.cu (C % 8 == 0) or the fp32 path dn4.cu.
+// Two operand schedules, one kernel (template flag KSTREAM):
+//   C <= 128 (Conv64F maps): the 128 query rows of a tile stay resident for all C channels while the support
+//            tiles stream through two whole-K stages;
+//   C  > 128 (ResNet-12 maps, C = 640: a 12.4 GFLOP GEMM per 5w5s episode): a 6-stage ring of
+//            [A slice | B slice] pairs of 32 channels each (32 KB per stage) feeds the K loop; the accumulator is
+//            committed to the epilogue after the last slice.
+// Built for C % 32 == 0 (one 128-byte swizzle atom per 32 channels); other widths use dn4_tc.cu (C % 8 == 0) or
+// the fp32 path dn4.cu.
 #include <cuda.h>
 #include <limits.h>
 
@@ -102,13 +108,16 @@ dn4_tc_prep_kernel(const float* __restrict__ feat, const int32_t* __restrict__ c
   }
 }
 
+constexpr int kStgK = 6;  // ring stages of the K-streaming schedule
+
 struct Bars {
   uint64_t full_a, empty_a;
   uint64_t full_b[2], empty_b[2];
   uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t full_k[kStgK], empty_k[kStgK];
 };
 
-template <int NK>
+template <int NK, bool KSTREAM>
 __global__ void __launch_bounds__(kThreads2)
 dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_s,
                const int32_t* __restrict__ cls_row, int W, int S, int C, int HW, float* __restrict__ rowsum,
@@ -141,6 +150,10 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       mbar_init(smem_u32(&bars.tmem_full[s]), 1);
       mbar_init(smem_u32(&bars.tmem_empty[s]), 4);  // one arrival per epilogue warp
     }
+    for (int s = 0; s < kStgK; ++s) {
+      mbar_init(smem_u32(&bars.full_k[s]), 1);
+      mbar_init(smem_u32(&bars.empty_k[s]), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {  // two 128-column accumulators
@@ -161,7 +174,25 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
   if (warp == 4) {
     // ================= TMA producer (one thread) =================
-    if (lane == 0) {
+    if (KSTREAM && lane == 0) {
+      uint32_t ks = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int qrow0 = out0 * HW + tile * kRows2;
+        for (int w = 0; w < W; ++w) {
+          const int srow_base = (e * W + w) * S * HW;
+          for (int ct = 0; ct < n_ctiles; ++ct) {
+            for (int kh = 0; kh < KH; ++kh, ++ks) {
+              const uint32_t st = ks % kStgK, ph = (ks / kStgK) & 1u;
+              mbar_wait(smem_u32(&bars.empty_k[st]), ph ^ 1u);
+              mbar_expect_tx(smem_u32(&bars.full_k[st]), 2u * kAtomBytes);
+              const uint32_t sa = base + st * (2u * kAtomBytes);
+              tma_load_2d(sa, &map_q, kh * 32, qrow0, smem_u32(&bars.full_k[st]));
+              tma_load_2d(sa + kAtomBytes, &map_s, kh * 32, srow_base + ct * kCols2, smem_u32(&bars.full_k[st]));
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
         mbar_wait(smem_u32(&bars.empty_a), (tcount & 1u) ^ 1u);  // MMAs of the previous tile have read A
@@ -184,7 +215,30 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
   } else if (warp == 5) {
     // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
+    if (KSTREAM && lane == 0) {
+      uint32_t ks = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int w = 0; w < W; ++w) {
+          for (int ct = 0; ct < n_ctiles; ++ct, ++it) {
+            const uint32_t acc_st = it & 1u, aph = (it >> 1) & 1u;
+            mbar_wait(smem_u32(&bars.tmem_empty[acc_st]), aph ^ 1u);  // epilogue has drained this accumulator
+            fence_after();
+            const uint32_t d_tmem = tmem_base + acc_st * kCols2;
+            for (int kh = 0; kh < KH; ++kh, ++ks) {
+              const uint32_t st = ks % kStgK, ph = (ks / kStgK) & 1u;
+              mbar_wait(smem_u32(&bars.full_k[st]), ph);
+              fence_after();
+              const uint32_t sa = base + st * (2u * kAtomBytes);
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                mma_tf32(d_tmem, desc_sw128(sa + k4 * 32u), desc_sw128(sa + kAtomBytes + k4 * 32u), kIdesc2, (kh | k4) != 0);
+              commit(smem_u32(&bars.empty_k[st]));  // slice reusable once these MMAs have read it
+            }
+            commit(smem_u32(&bars.tmem_full[acc_st]));  // all C channels accumulated: hand over to the epilogue
+          }
+        }
+      }
+    } else if (lane == 0) {
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
         mbar_wait(smem_u32(&bars.full_a), tcount & 1u);
@@ -304,14 +358,21 @@ dn4_tc2_reduce_kernel(const float* __restrict__ rowsum, int NQ, int W, int HW, f
   if (pred != nullptr) pred[o] = best_w;
 }
 
+template <int NK, bool KSTREAM>
+cudaError_t launch_tc2_impl(dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& mq, const CUtensorMap& ms,
+                            const int32_t* cls_row, int W, int S, int C, int HW, float* rowsum, int32_t* topk_idx) {
+  cudaError_t e = cudaFuncSetAttribute(dn4_tc2_kernel<NK, KSTREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  dn4_tc2_kernel<NK, KSTREAM><<<grid, kThreads2, smem, stream>>>(mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx);
+  return cudaSuccess;
+}
+
 template <int NK>
 cudaError_t launch_tc2(dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& mq, const CUtensorMap& ms,
                        const int32_t* cls_row, int W, int S, int C, int HW, float* rowsum, int32_t* topk_idx) {
-  cudaError_t e = cudaFuncSetAttribute(dn4_tc2_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
-  if (e != cudaSuccess) return e;
-  dn4_tc2_kernel<NK><<<grid, kThreads2, smem, stream>>>(mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx);
-  return cudaSuccess;
+  if (C > 128) return launch_tc2_impl<NK, true>(grid, smem, stream, mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx);
+  return launch_tc2_impl<NK, false>(grid, smem, stream, mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx);
 }
 
 size_t align256b(size_t x) { return (x + 255) / 256 * 256; }
@@ -335,7 +396,7 @@ extern "C" int afs_dn4_fwd_tc2(const float* feat, const int32_t* cls_row, int32_
   if (feat == nullptr || cls_row == nullptr || score == nullptr || E < 0 || W < 1 || W > kMaxWay2 || S < 1 ||
       C < 1 || HW < 1 || N < E * W * S || n_k < 1 || n_k > 8 || n_k > S * HW)
     return AFS_ERR_INVALID_ARG;
-  if ((C & 31) != 0 || C > 128) return AFS_ERR_UNSUPPORTED;
+  if ((C & 31) != 0 || C > 4096) return AFS_ERR_UNSUPPORTED;
   const int NQ = N - E * W * S;
   if (E == 0 || NQ == 0) return AFS_OK;
   if (E > 65535) return AFS_ERR_UNSUPPORTED;
@@ -360,7 +421,7 @@ extern "C" int afs_dn4_fwd_tc2(const float* feat, const int32_t* cls_row, int32_
   int tiles = static_cast<int>((avg_rows + kRows2 - 1) / kRows2);
   if (tiles < 1) tiles = 1;
   const dim3 grid(tiles, 1, E);
-  const size_t smem = 3 * static_cast<size_t>(C / 32) * kAtomBytes + 1024;
+  const size_t smem = (C > 128 ? static_cast<size_t>(kStgK) * 2 : 3 * static_cast<size_t>(C / 32)) * kAtomBytes + 1024;
   cudaError_t err = cudaSuccess;
   switch (n_k) {
     case 1: err = launch_tc2<1>(grid, smem, stream, mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx); break;

@@ -10,7 +10,7 @@ from .proto_net import accuracy_percent
 class DN4(MetricModel):
     def __init__(self, n_k=3, precision="fp32", **kwargs):
         """precision (not a reference kwarg): "fp32" keeps the bit-stable head; "tf32" runs the cosine relation
-        on the tcgen05 tensor cores in evaluation (Conv64F-sized maps)."""
+        on the tcgen05 tensor cores in evaluation (Conv64F maps, and ResNet-12 maps through the K-streaming schedule)."""
         super().__init__(**kwargs)
         self.n_k = n_k
         self.precision = precision
@@ -20,7 +20,8 @@ class DN4(MetricModel):
         image, repeats, support_size = self._unpack(batch)
         feat = self.emb_func(image)  # [N, C, H, W]
         tab = self._table(feat.shape[0], repeats, support_size)
-        precision = self.precision if (feat.shape[1] % 8 == 0 and feat.shape[1] <= 128) else "fp32"
+        c = feat.shape[1]
+        precision = self.precision if (c % 32 == 0 or (c % 8 == 0 and c <= 128)) else "fp32"
         output, _, _ = ops.dn4_scores(feat, tab.cls_row, tab.E, tab.W, tab.S, self.n_k, precision=precision)
         _, acc, _ = ops.vote_acc(output, tab.q_start, tab.q_target)
         return output, acc

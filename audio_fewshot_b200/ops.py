@@ -417,7 +417,8 @@ def dn4_scores(feat, cls_row, E, W, S, n_k, want_topk=False, want_pred=False, pr
     """DN4 head.  feat [N, C, H, W] (or [N, C, HW]) -> score [NQ, W] (+ topk_idx [NQ, W, HW, n_k], pred).
     Differentiable w.r.t. feat when it requires grad (top-k selection held fixed, as torch.topk's backward).
     precision: "fp32" = bit-stable SIMT path (parity with the reference's indices); "tf32" = tcgen05 tensor-core
-    path (C % 8 == 0, C <= 128), scores to ~1e-4, indices may differ at near-ties."""
+    path (C % 32 == 0 up to 4096 channels, or C % 8 == 0 up to 128), scores to ~1e-4, indices may differ at
+    near-ties."""
     if precision not in ("fp32", "tf32", "tf32_staged"):
         raise ValueError("precision must be 'fp32', 'tf32' or 'tf32_staged'")
     if torch.is_grad_enabled() and isinstance(feat, torch.Tensor) and feat.requires_grad:

@@ -127,7 +127,7 @@ def main():
         HW = H * Wd
         report("dn4 fp32 (normalize+main+reduce) " + tag, "episode", E, 4 * W * (S + Q) * C * HW + 4 * W * Q * W, ms, mn,
                flops_per_unit=2 * (W * Q * HW) * (W * S * HW) * C)
-        if C <= 128:
+        if C % 32 == 0:
             ms, mn = timeit(lambda: ops.dn4_scores(feat, tab.cls_row, E, W, S, 3, precision="tf32"), flush=flush)
             report("dn4 tf32 TMA+tcgen05 (prep+main+reduce) " + tag, "episode", E,
                    4 * W * (S + Q) * C * HW + 4 * W * Q * W, ms, mn, flops_per_unit=2 * (W * Q * HW) * (W * S * HW) * C)

@@ -151,9 +151,11 @@ def test_dn4_matches_reference_golden_and_topk(cuda, golden, name):
     assert len(diff) <= 1e-4 * mine.size
 
 
-@pytest.mark.parametrize("name", [n for n in sorted(cases.DN4_CASES) if cases.DN4_CASES[n]["C"] <= 128])
+@pytest.mark.parametrize("name", [n for n in sorted(cases.DN4_CASES)
+                                  if cases.DN4_CASES[n]["C"] <= 128 or cases.DN4_CASES[n]["C"] % 32 == 0])
 def test_dn4_tensor_core_path_matches_reference_golden(cuda, golden, name):
-    """tcgen05 TF32 path (csrc/dn4_tc.cu): scores within the north star's 1e-3 relative of the reference's
+    """tcgen05 TF32 path (csrc/dn4_tc.cu, csrc/dn4_tc2.cu incl. the K-streaming schedule for the ResNet-12 map with
+    C = 640): scores within the north star's 1e-3 relative of the reference's
     DN4Layer; selected descriptors are the oracle's top-k except where two cosines differ by less than TF32
     resolution; same argmax."""
     from audio_fewshot_b200 import ops
@@ -193,10 +195,20 @@ def test_dn4_tensor_core_path_ragged_multi_tile_and_unsupported(cuda):
     a, _, _ = ops.dn4_scores(feat, tab.cls_row, E, W, S, n_k)
     b, _, _ = ops.dn4_scores(feat, tab.cls_row, E, W, S, n_k, precision="tf32")
     assert (a - b).abs().max().item() <= 3e-4 * a.abs().max().item()
-    wide = torch.rand(2 * 5 * 3, 640, 2, 2, device=cuda)
+    # C = 640 (ResNet-12 maps): K-streaming schedule, ragged windows, three column tiles with a partial last one
+    E, W, S, Q, C, H, Wd = 2, 5, 5, 2, 640, 8, 9
+    rep = rng.integers(1, 3, size=E * W * Q)
+    n = E * W * S + int(rep.sum())
+    feat = torch.from_numpy(np.abs(rng.standard_normal((n, C, H, Wd))).astype(np.float32)).to(cuda)
+    tab = ragged_table(E, W, S, Q, rep, cuda)
+    a, ia, _ = ops.dn4_scores(feat, tab.cls_row, E, W, S, n_k, want_topk=True)
+    b, ib, _ = ops.dn4_scores(feat, tab.cls_row, E, W, S, n_k, want_topk=True, precision="tf32")
+    assert (a - b).abs().max().item() <= 3e-4 * a.abs().max().item()
+    assert (ia != ib).float().mean().item() <= 0.02
+    odd = torch.rand(2 * 5 * 3, 136, 2, 2, device=cuda)  # > 128 channels and not a multiple of 32: no tensor-core kernel
     tab2 = ragged_table(2, 5, 1, 2, np.ones(20, dtype=np.int64), cuda)
     with pytest.raises(AfsError):
-        ops.dn4_scores(wide, tab2.cls_row, 2, 5, 1, 2, precision="tf32")
+        ops.dn4_scores(odd, tab2.cls_row, 2, 5, 1, 2, precision="tf32")
 
 
 def test_dn4_ragged_matches_oracle(cuda):
