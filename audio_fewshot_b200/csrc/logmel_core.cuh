@@ -190,10 +190,6 @@ AFS_HD void phase_c(int t, const float* bufB, float* bufA) {
   }
 }
 
-// Power bin k is stored at pskew(k) = k + k/32: the mel projection reads bins lo_m + i with a different lo_m per
-// lane, and for the upper filters the lo_m are ~8-12 bins apart, which without the skew puts 3-4 lanes on one bank.
-AFS_HD int pskew(int k) { return k + (k >> 5); }
-
 // Phase D. thread u handles k = u + 64 m (m = 0..3) and its mirror 512 - k;
 // thread 0 also writes the self-paired bin 256.  Power spectrum into buffer B.
 AFS_HD void phase_d(int u, const ThreadTw& tw, const float* bufA, float* power) {
@@ -220,12 +216,12 @@ AFS_HD void phase_d(int u, const ThreadTw& tw, const float* bufA, float* power) 
     const cpx t2 = cmul(o2, td);
     const float xr = er + t2.re, xi = ei + t2.im;
     const float yr = er - t2.re, yi = ei - t2.im;
-    power[pskew(k)] = 0.25f * (xr * xr + xi * xi);
-    power[pskew(kHalf - k)] = 0.25f * (yr * yr + yi * yi);
+    power[k] = 0.25f * (xr * xr + xi * xi);
+    power[kHalf - k] = 0.25f * (yr * yr + yi * yi);
   }
   if (u == 0) {
     const float ar = re[256], ai = im[256];
-    power[pskew(256)] = ar * ar + ai * ai;
+    power[256] = ar * ar + ai * ai;
   }
 }
 
@@ -236,26 +232,25 @@ AFS_HD int64_t reflect_index(int64_t idx, int64_t L) {
   return idx;
 }
 
-// Banded mel projection of one filter: sum_i w[i * wstride] * P[lo+i] (P in the skewed layout).
+// Banded mel projection of one filter: sum_i w[i * wstride] * P[lo+i].
 AFS_HD float mel_dot(const float* power, const float* weights, int wstride, int lo, int len) {
   float acc = 0.f;
-  for (int i = 0; i < len; ++i) acc += weights[i * wstride] * power[pskew(lo + i)];
+  for (int i = 0; i < len; ++i) acc += weights[i * wstride] * power[lo + i];
   return acc;
 }
 
 // The same projection for kMelBatch frames at once (their power spectra kPStride floats apart): one
 // weight load feeds kMelBatch FMAs.  Summation order per frame is identical to mel_dot.
 constexpr int kMelBatch = 4;
-constexpr int kPStride = 532;  // 513 power bins + 16 of skew, padded to a multiple of 4 floats
+constexpr int kPStride = 516;  // 513 power bins, padded to a multiple of 4 floats
 AFS_HD void mel_dot_batch(const float* power, const float* weights, int wstride, int lo, int len,
                           float (&acc)[kMelBatch]) {
 #pragma unroll
   for (int f = 0; f < kMelBatch; ++f) acc[f] = 0.f;
   for (int i = 0; i < len; ++i) {
     const float w = weights[i * wstride];
-    const int k = pskew(lo + i);
 #pragma unroll
-    for (int f = 0; f < kMelBatch; ++f) acc[f] += w * power[f * kPStride + k];
+    for (int f = 0; f < kMelBatch; ++f) acc[f] += w * power[f * kPStride + lo + i];
   }
 }
 
@@ -299,11 +294,41 @@ inline int pack_mel_bands(const float* fb, int n_mels, IntVec& band, FloatVec& w
   return static_cast<int>(weights.size());
 }
 
+// Shared-memory wavefronts of one warp-pass of the mel projection for one frame: in iteration i lane l reads power
+// bin start[l] + i when i < n[l] (all lanes execute iteration i in the same instruction); an instruction costs as
+// many wavefronts as the largest number of DISTINCT words that fall on one of the 32 banks.
+inline int mel_read_wavefronts(const int (&start)[32], const int (&n)[32]) {
+  int total = 0;
+  for (int i = 0;; ++i) {
+    int words[32][32], cnt[32] = {0}, worst = 0;
+    bool any = false;
+    for (int l = 0; l < 32; ++l) {
+      if (i >= n[l]) continue;
+      any = true;
+      const int a = start[l] + i, b = a & 31;
+      bool seen = false;
+      for (int j = 0; j < cnt[b]; ++j) seen = seen || words[b][j] == a;
+      if (!seen) words[b][cnt[b]++] = a;
+      if (cnt[b] > worst) worst = cnt[b];
+    }
+    if (!any) break;
+    total += worst;
+  }
+  return total;
+}
+
 // The kernel's weight table (ELL layout): thread t of a 64-thread frame group owns filter t (pass 0) and filter
 // n_mels-1-t when that is >= 64 (pass 1).  The 32 lanes of a warp read weight i of their filter in the same
 // instruction, so the table is stored [warp-pass][i][lane] (zero padded to the longest filter of the warp-pass):
-// every weight load is one conflict-free wavefront.  band[m] = first bin, band[kMaxMels+m] = span length,
-// band[2*kMaxMels+m] = index of the filter's weight 0; consecutive weights are kEllStride apart.
+// every weight load is one conflict-free wavefront.
+// The POWER reads of that instruction are bins start_l + i with a different start_l per lane; the upper slaney
+// filters start 6-12 bins apart, which as it stands puts up to 4 lanes on one bank (102 wavefronts per frame for 43
+// instructions).  A filter shorter than the longest one of its warp-pass has slack: it may begin r iterations
+// late, i.e. read from bin lo - r with r leading zero weights, which moves its bank by -r in EVERY iteration
+// without touching the summation order of its non-zero terms.  The shifts are chosen here, once per plan, by a
+// deterministic local search on mel_read_wavefronts (47 wavefronts per frame for the 128-mel slaney bank).
+//   band[m] = first bin READ (lo - r), band[kMaxMels+m] = iterations (r + span length),
+//   band[2*kMaxMels+m] = index of the filter's table entry 0; consecutive entries are kEllStride apart.
 constexpr int kEllStride = 32;
 template <typename IntVec, typename FloatVec>
 inline int pack_mel_ell(const float* fb, int n_mels, IntVec& band, FloatVec& weights) {
@@ -314,22 +339,49 @@ inline int pack_mel_ell(const float* fb, int n_mels, IntVec& band, FloatVec& wei
   weights.clear();
   for (int pass = 0; pass < 2; ++pass) {
     for (int warp = 0; warp < kGroup / 32; ++warp) {
-      int filt[32], maxlen = 0;
+      int filt[32], lo[32], len[32], maxlen = 0;
       for (int lane = 0; lane < 32; ++lane) {
         const int t = warp * 32 + lane;
         int m = pass == 0 ? (t < n_mels ? t : -1) : (n_mels - 1 - t >= kGroup ? n_mels - 1 - t : -1);
         filt[lane] = m;
-        if (m >= 0 && b0[kMaxMels + m] > maxlen) maxlen = b0[kMaxMels + m];
+        lo[lane] = m >= 0 ? b0[m] : 0;
+        len[lane] = m >= 0 ? b0[kMaxMels + m] : 0;
+        if (len[lane] > maxlen) maxlen = len[lane];
+      }
+      // start shifts: r <= maxlen - len (the table does not grow) and r <= lo (the first bin read exists)
+      int shift[32] = {0}, start[32], n[32];
+      for (int lane = 0; lane < 32; ++lane) { start[lane] = lo[lane]; n[lane] = len[lane]; }
+      int best = mel_read_wavefronts(start, n);
+      uint32_t rng = 0x9E3779B9u + static_cast<uint32_t>(pass * 2 + warp);
+      for (int it = 0; it < 6000 && best > maxlen; ++it) {
+        rng = rng * 1664525u + 1013904223u;
+        const int lane = static_cast<int>((rng >> 8) & 31u);
+        if (len[lane] == 0) continue;
+        int room = maxlen - len[lane];
+        if (lo[lane] < room) room = lo[lane];
+        if (room == 0) continue;
+        rng = rng * 1664525u + 1013904223u;
+        const int cand = static_cast<int>((rng >> 8) % static_cast<uint32_t>(room + 1));
+        const int old = shift[lane];
+        if (cand == old) continue;
+        start[lane] = lo[lane] - cand; n[lane] = len[lane] + cand;
+        const int c = mel_read_wavefronts(start, n);
+        if (c <= best) {  // sideways moves are accepted: the landscape is full of plateaus
+          best = c; shift[lane] = cand;
+        } else {
+          start[lane] = lo[lane] - old; n[lane] = len[lane] + old;
+        }
       }
       const int base = static_cast<int>(weights.size());
       weights.resize(weights.size() + static_cast<size_t>(maxlen) * kEllStride, 0.f);
       for (int lane = 0; lane < 32; ++lane) {
         const int m = filt[lane];
         if (m < 0) continue;
-        band[m] = b0[m];
-        band[kMaxMels + m] = b0[kMaxMels + m];
+        band[m] = lo[lane] - shift[lane];
+        band[kMaxMels + m] = len[lane] + shift[lane];
         band[2 * kMaxMels + m] = base + lane;
-        for (int i = 0; i < b0[kMaxMels + m]; ++i) weights[base + i * kEllStride + lane] = w0[b0[2 * kMaxMels + m] + i];
+        for (int i = 0; i < len[lane]; ++i)
+          weights[base + (shift[lane] + i) * kEllStride + lane] = w0[b0[2 * kMaxMels + m] + i];
       }
     }
   }

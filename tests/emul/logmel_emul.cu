@@ -19,7 +19,7 @@ extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, con
                            float* power_out /*[T, 513] nullable*/) {
   std::vector<int> band;
   std::vector<float> weights;
-  pack_mel_bands(fb, n_mels, band, weights);
+  pack_mel_ell(fb, n_mels, band, weights);  // the table the kernel reads, start shifts included
   std::vector<float2> tw(kNfft);
   for (int k = 0; k < kNfft; ++k) {
     const double a = 6.283185307179586476925286766559 * k / kNfft;
@@ -49,7 +49,7 @@ extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, con
     const int slot = f % kMelBatch;
     float* power = bufP.data() + slot * kPStride;
     for (int t = 0; t < kGroup; ++t) phase_d(t, tws[t], bufA.data(), power);
-    if (power_out) for (int k = 0; k < kBins; ++k) power_out[static_cast<size_t>(f) * kBins + k] = power[pskew(k)];
+    if (power_out) for (int k = 0; k < kBins; ++k) power_out[static_cast<size_t>(f) * kBins + k] = power[k];
     if (slot != kMelBatch - 1 && f + 1 != T) continue;
     for (int t = 0; t < kGroup; ++t) {  // batched mel projection, as the kernel's epilogue
       int mel_id[2];
@@ -59,7 +59,7 @@ extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, con
         const int m = mel_id[i];
         if (m < 0) continue;
         float acc[kMelBatch];
-        mel_dot_batch(bufP.data(), weights.data() + band[2 * kMaxMels + m], 1, band[m], band[kMaxMels + m], acc);
+        mel_dot_batch(bufP.data(), weights.data() + band[2 * kMaxMels + m], kEllStride, band[m], band[kMaxMels + m], acc);
         const float scale = log_mult * 0.30102999566398120f / stdv[m];
         const float shift = -mean[m] / stdv[m];
         for (int b = 0; b <= slot; ++b)
@@ -96,4 +96,31 @@ extern "C" int emul_mel_ell_dense(const float* fb, int n_mels, float* dense /*[5
   return n;
 }
 
-extern "C" int emul_pskew(int k) { return pskew(k); }
+// Shared-memory wavefronts per frame of the mel projection's power reads, replayed from the packed table exactly as
+// the kernel's warps issue them (bank = word index mod 32; the four frames of a batch are separate instructions
+// with the same pattern).  *iterations = number of read instructions per frame = the conflict-free count.
+// shifted = 0 replays the un-shifted layout (every filter starts at its first non-zero bin) for comparison.
+extern "C" int emul_mel_read_wavefronts(const float* fb, int n_mels, int shifted, int* iterations) {
+  std::vector<int> band, b0;
+  std::vector<float> weights, w0;
+  pack_mel_ell(fb, n_mels, band, weights);
+  pack_mel_bands(fb, n_mels, b0, w0);
+  int total = 0;
+  *iterations = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int warp = 0; warp < kGroup / 32; ++warp) {
+      int start[32], n[32], longest = 0;
+      for (int lane = 0; lane < 32; ++lane) {
+        const int t = warp * 32 + lane;
+        const int m = pass == 0 ? (t < n_mels ? t : -1) : (n_mels - 1 - t >= kGroup ? n_mels - 1 - t : -1);
+        start[lane] = m < 0 ? 0 : (shifted ? band[m] : b0[m]);
+        n[lane] = m < 0 ? 0 : (shifted ? band[kMaxMels + m] : b0[kMaxMels + m]);
+        if (start[lane] < 0 || start[lane] + n[lane] > kBins) return -1;  // every read must hit a written bin
+        if (n[lane] > longest) longest = n[lane];
+      }
+      *iterations += longest;
+      total += mel_read_wavefronts(start, n);
+    }
+  }
+  return total;
+}
