@@ -183,8 +183,6 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
   const int tid = threadIdx.x;
   const int grp = tid >> 6;
   const int t = tid & 63;
-  const int clip = blockIdx.x / p.chunks;
-  const int chunk = blockIdx.x - clip * p.chunks;
 
   for (int i = tid; i < p.nnz; i += kThreads) s_w[i] = p.weights[i];
   for (int i = tid; i < 3 * kMaxMels; i += kThreads) s_band[i] = p.band[i];
@@ -205,36 +203,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
     mel_shift[i] = -mu / sd;
   }
 
-  const S* __restrict__ x = static_cast<const S*>(p.wav) + static_cast<int64_t>(clip) * p.L;
-
-  AugState aug;
-  aug.pcm_scale = p.pcm_scale;
-  if (AUG) {
-    const uint64_t cg = p.first_clip + static_cast<uint64_t>(clip);
-    aug.c_lo = static_cast<uint32_t>(cg);
-    aug.c_hi = static_cast<uint32_t>(cg >> 32);
-    aug.seed_lo = p.seed_lo;
-    aug.seed_hi = p.seed_hi;
-    u32x4 c;
-    c.x = 0u; c.y = kStreamParams; c.z = aug.c_lo; c.w = aug.c_hi;
-    const u32x4 r = philox4x32_10(c, p.seed_lo, p.seed_hi);
-    const float gain_db = __fadd_rn(p.gain_lo, __fmul_rn(__fsub_rn(p.gain_hi, p.gain_lo), u01(r.x)));
-    aug.g = exp10f(__fmul_rn(gain_db, 0.05f));
-    const int span = 2 * p.max_shift + 1;
-    int draw = static_cast<int>(floorf(__fmul_rn(u01(r.y), static_cast<float>(span))));
-    if (draw > span - 1) draw = span - 1;
-    aug.k = draw - p.max_shift;
-    aug.sigma = __fadd_rn(p.noise_lo, __fmul_rn(__fsub_rn(p.noise_hi, p.noise_lo), u01(r.z)));
-  }
-
   float* bufA = s_grp + grp * kGroupFloats;
   float* bufB = bufA + kBufA;
   float* bufP = bufB + kBufB;  // kMelBatch power spectra
-
-  const int t0 = chunk * kFramesPerCta;
-  const int nfr = min(kFramesPerCta, p.T - t0);
-  const int f_begin = grp * kFramesPerGroup;
-  const int f_end = min(f_begin + kFramesPerGroup, nfr);
   // this thread's 16 window coefficients stay in registers for every frame (the shared-memory pipe is the limiter)
   float2 win[8];
   {
@@ -242,62 +213,96 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) win[r] = __ldg(w2 + t + 64 * r);
   }
-
-  float2 raw[8];
-  if (f_begin < f_end) load_frame<AUG, S, 0>(x, static_cast<int64_t>(t0 + f_begin) * p.hop - p.pad, p.L, t, aug, raw);
   const bool half_overlap = p.hop * 2 == kNfft;  // consecutive frames share half of their (padded, augmented) samples
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
   __syncthreads();
 
-  for (int fl = f_begin; fl < f_end; ++fl) {
-    cpx z[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      z[r].re = raw[r].x * win[r].x;
-      z[r].im = raw[r].y * win[r].y;
+  // Persistent over (clip, chunk) items: the tables above are staged once per CTA, not once per 32 frames.
+  const int n_items = p.B * p.chunks;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int clip = item / p.chunks;
+    const int chunk = item - clip * p.chunks;
+    const S* __restrict__ x = static_cast<const S*>(p.wav) + static_cast<int64_t>(clip) * p.L;
+
+    AugState aug;
+    aug.pcm_scale = p.pcm_scale;
+    if (AUG) {
+      const uint64_t cg = p.first_clip + static_cast<uint64_t>(clip);
+      aug.c_lo = static_cast<uint32_t>(cg);
+      aug.c_hi = static_cast<uint32_t>(cg >> 32);
+      aug.seed_lo = p.seed_lo;
+      aug.seed_hi = p.seed_hi;
+      u32x4 c;
+      c.x = 0u; c.y = kStreamParams; c.z = aug.c_lo; c.w = aug.c_hi;
+      const u32x4 r = philox4x32_10(c, p.seed_lo, p.seed_hi);
+      const float gain_db = __fadd_rn(p.gain_lo, __fmul_rn(__fsub_rn(p.gain_hi, p.gain_lo), u01(r.x)));
+      aug.g = exp10f(__fmul_rn(gain_db, 0.05f));
+      const int span = 2 * p.max_shift + 1;
+      int draw = static_cast<int>(floorf(__fmul_rn(u01(r.y), static_cast<float>(span))));
+      if (draw > span - 1) draw = span - 1;
+      aug.k = draw - p.max_shift;
+      aug.sigma = __fadd_rn(p.noise_lo, __fmul_rn(__fsub_rn(p.noise_hi, p.noise_lo), u01(r.z)));
     }
-    if (fl + 1 < f_end) {  // prefetch the next frame while this one is transformed
-      const int64_t s_next = static_cast<int64_t>(t0 + fl + 1) * p.hop - p.pad;
-      if (half_overlap) {  // its first half is this frame's second half: sample index s_next + 2(t+64r) = s0 + 2(t+64(r+4))
-#pragma unroll
-        for (int r = 0; r < 4; ++r) raw[r] = raw[r + 4];
-        load_frame<AUG, S, 4>(x, s_next, p.L, t, aug, raw);
-      } else {
-        load_frame<AUG, S, 0>(x, s_next, p.L, t, aug, raw);
+
+    const int t0 = chunk * kFramesPerCta;
+    const int nfr = min(kFramesPerCta, p.T - t0);
+    const int f_begin = grp * kFramesPerGroup;
+    const int f_end = min(f_begin + kFramesPerGroup, nfr);
+
+    float2 raw[8];
+    if (f_begin < f_end) load_frame<AUG, S, 0>(x, static_cast<int64_t>(t0 + f_begin) * p.hop - p.pad, p.L, t, aug, raw);
+
+    for (int fl = f_begin; fl < f_end; ++fl) {
+      cpx z[8];
+  #pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        z[r].re = raw[r].x * win[r].x;
+        z[r].im = raw[r].y * win[r].y;
       }
-    }
-    const int slot = (fl - f_begin) % kMelBatch;
-    phase_a(t, z, tw, bufA);
-    group_bar(grp);
-    phase_b(t, tw, bufA, bufB);
-    group_bar(grp);
-    phase_c(t, bufB, bufA);
-    group_bar(grp);
-    phase_d(t, tw, bufA, bufP + slot * kPStride);
-    group_bar(grp);
-    if (slot == kMelBatch - 1 || fl + 1 == f_end) {
-      const int fl0 = fl - slot;  // first frame of this batch
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int m = mel_id[i];
-        if (m >= 0) {
-          float acc[kMelBatch];
-          mel_dot_batch(bufP, s_w + s_band[2 * kMaxMels + m], kEllStride, s_band[m], s_band[kMaxMels + m], acc);
-#pragma unroll
-          for (int f = 0; f < kMelBatch; ++f)
-            if (f <= slot) s_tile[m * kTileStride + fl0 + f] = norm_db(acc[f], p.log_eps, mel_scale[i], mel_shift[i]);
+      if (fl + 1 < f_end) {  // prefetch the next frame while this one is transformed
+        const int64_t s_next = static_cast<int64_t>(t0 + fl + 1) * p.hop - p.pad;
+        if (half_overlap) {  // its first half is this frame's second half: sample index s_next + 2(t+64r) = s0 + 2(t+64(r+4))
+  #pragma unroll
+          for (int r = 0; r < 4; ++r) raw[r] = raw[r + 4];
+          load_frame<AUG, S, 4>(x, s_next, p.L, t, aug, raw);
+        } else {
+          load_frame<AUG, S, 0>(x, s_next, p.L, t, aug, raw);
+        }
+      }
+      const int slot = (fl - f_begin) % kMelBatch;
+      phase_a(t, z, tw, bufA);
+      group_bar(grp);
+      phase_b(t, tw, bufA, bufB);
+      group_bar(grp);
+      phase_c(t, bufB, bufA);
+      group_bar(grp);
+      phase_d(t, tw, bufA, bufP + slot * kPStride);
+      group_bar(grp);
+      if (slot == kMelBatch - 1 || fl + 1 == f_end) {
+        const int fl0 = fl - slot;  // first frame of this batch
+  #pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int m = mel_id[i];
+          if (m >= 0) {
+            float acc[kMelBatch];
+            mel_dot_batch(bufP, s_w + s_band[2 * kMaxMels + m], kEllStride, s_band[m], s_band[kMaxMels + m], acc);
+  #pragma unroll
+            for (int f = 0; f < kMelBatch; ++f)
+              if (f <= slot) s_tile[m * kTileStride + fl0 + f] = norm_db(acc[f], p.log_eps, mel_scale[i], mel_shift[i]);
+          }
         }
       }
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  if (lane < nfr) {
-    float* o = p.out + (static_cast<int64_t>(clip) * p.n_mels) * p.T + t0 + lane;
-    for (int m = warp; m < p.n_mels; m += kThreads / 32) {
-      o[static_cast<int64_t>(m) * p.T] = s_tile[m * kTileStride + lane];
+    if (lane < nfr) {
+      float* o = p.out + (static_cast<int64_t>(clip) * p.n_mels) * p.T + t0 + lane;
+      for (int m = warp; m < p.n_mels; m += kThreads / 32) {
+        o[static_cast<int64_t>(m) * p.T] = s_tile[m * kTileStride + lane];
+      }
     }
+    __syncthreads();  // the tile is free before the next item's first mel batch writes it
   }
 }
 
@@ -407,8 +412,10 @@ int logmel_launch(const afs_logmel_plan* plan, const S* wav, float pcm_scale, in
   p.gain_lo = p.gain_hi = p.noise_lo = p.noise_hi = 0.f; p.max_shift = 0;
   p.seed_lo = static_cast<uint32_t>(seed); p.seed_hi = static_cast<uint32_t>(seed >> 32);
   p.first_clip = first_clip_index;
-  const int64_t grid = static_cast<int64_t>(B) * p.chunks;
-  if (grid > 0x7fffffffLL) return AFS_ERR_UNSUPPORTED;
+  const int64_t items = static_cast<int64_t>(B) * p.chunks;
+  if (items > 0x7fffffffLL) return AFS_ERR_UNSUPPORTED;
+  // persistent: 2 resident CTAs per SM (128 registers x 256 threads, 100 KB of shared memory each) walk the items
+  const int64_t grid = items < 2 * kNumSMs ? items : 2 * kNumSMs;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (aug != nullptr) {
     p.gain_lo = aug->gain_db_lo; p.gain_hi = aug->gain_db_hi;
