@@ -1,6 +1,8 @@
 """GPU parity of the drop-in classes: backbones (incl. the fused Conv64F inference path) against the
 reference's golden features, set_forward / set_forward_loss of ProtoNet, DN4, DeepBDC against the oracle
 drivers on identical features, and the waveform -> logits pipeline (plain and CUDA-graph)."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -500,8 +502,11 @@ def test_metabaseline_forward_and_cosine_backward_match_autograd_of_oracle(cuda)
 
 
 def test_graphed_train_step_matches_eager_maml(cuda):
-    """GraphedTrainStep (one CUDA graph for set_forward_loss + backward + Adam) reproduces the eager MAML step:
-    same loss sequence and the same parameters after three steps (Dropout disabled so both see the same masks)."""
+    """GraphedTrainStep (one CUDA graph for set_forward_loss + backward + optimizer step) reproduces the eager MAML
+    step: same loss sequence over three steps (Dropout disabled so both see the same masks).  The comparison runs
+    with plain SGD, whose update is proportional to the gradient, so the run-to-run rounding of cuDNN's backward
+    kernels stays at rounding level; Adam's first updates are ~lr*sign(g), which turns that rounding into O(lr)
+    parameter differences wherever a gradient is near zero, so with Adam only the captured update is checked."""
     import copy
     from audio_fewshot_b200 import model as arch
     from audio_fewshot_b200.graph_step import GraphedTrainStep
@@ -511,22 +516,18 @@ def test_graphed_train_step_matches_eager_maml(cuda):
     kw = dict(way_num=3, shot_num=2, query_num=3, test_way=3, test_shot=2, test_query=3, device=cuda)
     m1 = arch.MAML(inner_param={"lr": 0.01, "train_iter": 2, "test_iter": 2}, feat_dim=1600, emb_func=emb, **kw).to(cuda).train()
     m2 = copy.deepcopy(m1)
+    m3 = copy.deepcopy(m1)
     E, W, S, Q = 2, 3, 2, 3
     n = E * W * (S + Q)
     target = torch.arange(W).repeat_interleave(S + Q).repeat(E)
     batches = [torch.randn(n, 1, 128, 157, device=cuda) * 0.7 for _ in range(3)]
-    o1 = torch.optim.Adam(m1.parameters(), lr=1e-3)
-    o2 = torch.optim.Adam(m2.parameters(), lr=1e-3, capturable=True)
-    with pytest.raises(ValueError):
-        GraphedTrainStep(m2, torch.optim.Adam(m2.parameters(), lr=1e-3), batches[0].shape, target=target)
-    ref_state = copy.deepcopy(m2.state_dict())
+    ref_state = copy.deepcopy(m1.state_dict())
+
+    # (1) SGD: eager and graphed steps give the same losses
+    o1 = torch.optim.SGD(m1.parameters(), lr=1e-2)
+    o2 = torch.optim.SGD(m2.parameters(), lr=1e-2)
     step = GraphedTrainStep(m2, o2, batches[0].shape, target=target, warmup=1)
-    # the warm-up and the capture ran optimizer steps on zeros: restart both from the same point
-    m2.load_state_dict(ref_state)
-    for st in o2.state.values():
-        for k, v in st.items():
-            if torch.is_tensor(v):
-                v.zero_()
+    m2.load_state_dict(ref_state)  # the warm-up and the capture ran optimizer steps on zeros: restart from the same point
     losses1, losses2 = [], []
     for b in batches:
         o1.zero_grad(set_to_none=True)
@@ -539,12 +540,29 @@ def test_graphed_train_step_matches_eager_maml(cuda):
         # accuracy comes back as a 1-element device tensor; its VALUE is not compared: an untrained net has near-tied
         # logits, so a few of the 18 queries flip with the rounding of cuDNN's (possibly different) algorithms
         assert acc2.numel() == 1 and acc2.is_cuda and 0.0 <= float(acc2) <= 100.0 and 0.0 <= acc <= 100.0
-    # step 1 sees identical weights; afterwards Adam's first updates are ~lr*sign(g), which amplifies the
-    # run-to-run rounding differences of cuDNN's backward kernels, so later losses are compared more loosely
-    for l1, l2, tol in zip(losses1, losses2, (1e-4, 2e-3, 3e-2)):
+    for l1, l2, tol in zip(losses1, losses2, (1e-4, 1e-3, 1e-3)):
         assert abs(l1 - l2) <= tol * abs(l1), (losses1, losses2)
-    # the captured optimizer step really updates the live parameters
-    moved = [(m2.state_dict()[k] - v.to(cuda)).abs().max().item() for k, v in ref_state.items()
+    assert len(set(losses1)) == 3  # three different batches really went through
+    drift = max((m1.state_dict()[k] - m2.state_dict()[k]).abs().max().item() for k, v in ref_state.items()
+                if v.dtype.is_floating_point)
+    assert drift < 1e-3, drift
+
+    # (2) Adam must be capturable, and the captured Adam step really updates the live parameters
+    with pytest.raises(ValueError):
+        GraphedTrainStep(m3, torch.optim.Adam(m3.parameters(), lr=1e-3), batches[0].shape, target=target)
+    o3 = torch.optim.Adam(m3.parameters(), lr=1e-3, capturable=True)
+    step3 = GraphedTrainStep(m3, o3, batches[0].shape, target=target, warmup=1)
+    m3.load_state_dict(ref_state)
+    for st in o3.state.values():
+        for k, v in st.items():
+            if torch.is_tensor(v):
+                v.zero_()
+    for i, b in enumerate(batches):
+        _, _, loss3 = step3(b)
+        assert math.isfinite(float(loss3))
+        if i == 0:  # identical weights and batch: the same loss as the eager step, whatever the optimizer
+            assert abs(float(loss3) - losses1[0]) <= 1e-4 * abs(losses1[0])
+    moved = [(m3.state_dict()[k] - v.to(cuda)).abs().max().item() for k, v in ref_state.items()
              if v.dtype.is_floating_point and "running" not in k]
     assert 1e-3 <= max(moved) <= 3.5e-3  # three Adam steps of lr 1e-3
 
