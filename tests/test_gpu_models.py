@@ -503,10 +503,14 @@ def test_metabaseline_forward_and_cosine_backward_match_autograd_of_oracle(cuda)
 
 def test_graphed_train_step_matches_eager_maml(cuda):
     """GraphedTrainStep (one CUDA graph for set_forward_loss + backward + optimizer step) reproduces the eager MAML
-    step: same loss sequence over three steps (Dropout disabled so both see the same masks).  The comparison runs
-    with plain SGD, whose update is proportional to the gradient, so the run-to-run rounding of cuDNN's backward
-    kernels stays at rounding level; Adam's first updates are ~lr*sign(g), which turns that rounding into O(lr)
-    parameter differences wherever a gradient is near zero, so with Adam only the captured update is checked."""
+    step: from the same weights and the same batch, the same loss and the same parameter update, three batches in a
+    row (Dropout disabled so both see the same masks).
+
+    Both models are put on the same weights before every step: a randomly initialised MAML net is chaotic (dead
+    channels under batch-statistics BatchNorm amplify a 1e-7 weight difference into a 1e-3 loss difference one step
+    later, eager against eager as well -- tools/diag_graphed_maml.py, gpurun_out/maml_diag.txt), so free-running loss
+    sequences only agree when every kernel is bit-reproducible.  Measured on B200: update difference 1e-5 relative
+    with cuDNN's default algorithms, exactly 0 with cudnn.deterministic."""
     import copy
     from audio_fewshot_b200 import model as arch
     from audio_fewshot_b200.graph_step import GraphedTrainStep
@@ -523,48 +527,56 @@ def test_graphed_train_step_matches_eager_maml(cuda):
     batches = [torch.randn(n, 1, 128, 157, device=cuda) * 0.7 for _ in range(3)]
     ref_state = copy.deepcopy(m1.state_dict())
 
-    # (1) SGD: eager and graphed steps give the same losses
-    o1 = torch.optim.SGD(m1.parameters(), lr=1e-2)
-    o2 = torch.optim.SGD(m2.parameters(), lr=1e-2)
-    step = GraphedTrainStep(m2, o2, batches[0].shape, target=target, warmup=1)
-    m2.load_state_dict(ref_state)  # the warm-up and the capture ran optimizer steps on zeros: restart from the same point
-    losses1, losses2 = [], []
-    for b in batches:
-        o1.zero_grad(set_to_none=True)
-        out, acc, loss = m1([b, target])
-        loss.backward()
-        o1.step()
-        losses1.append(float(loss))
-        out2, acc2, loss2 = step(b)
-        losses2.append(float(loss2))
-        # accuracy comes back as a 1-element device tensor; its VALUE is not compared: an untrained net has near-tied
-        # logits, so a few of the 18 queries flip with the rounding of cuDNN's (possibly different) algorithms
-        assert acc2.numel() == 1 and acc2.is_cuda and 0.0 <= float(acc2) <= 100.0 and 0.0 <= acc <= 100.0
-    for l1, l2, tol in zip(losses1, losses2, (1e-4, 1e-3, 1e-3)):
-        assert abs(l1 - l2) <= tol * abs(l1), (losses1, losses2)
-    assert len(set(losses1)) == 3  # three different batches really went through
-    drift = max((m1.state_dict()[k] - m2.state_dict()[k]).abs().max().item() for k, v in ref_state.items()
-                if v.dtype.is_floating_point)
-    assert drift < 1e-3, drift
+    def flat(m):
+        return torch.cat([p.detach().reshape(-1) for p in m.parameters()])
 
-    # (2) Adam must be capturable, and the captured Adam step really updates the live parameters
-    with pytest.raises(ValueError):
-        GraphedTrainStep(m3, torch.optim.Adam(m3.parameters(), lr=1e-3), batches[0].shape, target=target)
-    o3 = torch.optim.Adam(m3.parameters(), lr=1e-3, capturable=True)
-    step3 = GraphedTrainStep(m3, o3, batches[0].shape, target=target, warmup=1)
-    m3.load_state_dict(ref_state)
-    for st in o3.state.values():
-        for k, v in st.items():
-            if torch.is_tensor(v):
-                v.zero_()
-    for i, b in enumerate(batches):
-        _, _, loss3 = step3(b)
-        assert math.isfinite(float(loss3))
-        if i == 0:  # identical weights and batch: the same loss as the eager step, whatever the optimizer
-            assert abs(float(loss3) - losses1[0]) <= 1e-4 * abs(losses1[0])
-    moved = [(m3.state_dict()[k] - v.to(cuda)).abs().max().item() for k, v in ref_state.items()
-             if v.dtype.is_floating_point and "running" not in k]
-    assert 1e-3 <= max(moved) <= 3.5e-3  # three Adam steps of lr 1e-3
+    old_det = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        # (1) SGD: eager and graphed steps from the same weights give the same loss and the same update
+        o1 = torch.optim.SGD(m1.parameters(), lr=1e-2)
+        o2 = torch.optim.SGD(m2.parameters(), lr=1e-2)
+        step = GraphedTrainStep(m2, o2, batches[0].shape, target=target, warmup=1)
+        losses1 = []
+        for b in batches:
+            m2.load_state_dict(m1.state_dict())  # also undoes the warm-up / capture steps on zeros the first time
+            w0 = flat(m1).clone()
+            o1.zero_grad(set_to_none=True)
+            out, acc, loss = m1([b, target])
+            loss.backward()
+            o1.step()
+            out2, acc2, loss2 = step(b)
+            l1, l2 = float(loss.detach()), float(loss2.detach())
+            losses1.append(l1)
+            assert abs(l1 - l2) <= 1e-4 * abs(l1), (l1, l2)
+            d1, d2 = flat(m1) - w0, flat(m2) - w0
+            assert d1.norm().item() > 1e-3  # the step moved the weights ...
+            assert (d2 - d1).norm().item() <= 1e-3 * d1.norm().item()  # ... and the captured step moved them alike
+            # accuracy comes back as a 1-element device tensor; its VALUE is not compared: an untrained net has
+            # near-tied logits
+            assert acc2.numel() == 1 and acc2.is_cuda and 0.0 <= float(acc2) <= 100.0 and 0.0 <= acc <= 100.0
+        assert len(set(losses1)) == 3  # three different batches really went through
+
+        # (2) Adam must be capturable, and the captured Adam step really updates the live parameters
+        with pytest.raises(ValueError):
+            GraphedTrainStep(m3, torch.optim.Adam(m3.parameters(), lr=1e-3), batches[0].shape, target=target)
+        o3 = torch.optim.Adam(m3.parameters(), lr=1e-3, capturable=True)
+        step3 = GraphedTrainStep(m3, o3, batches[0].shape, target=target, warmup=1)
+        m3.load_state_dict(ref_state)
+        for st in o3.state.values():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    v.zero_()
+        for i, b in enumerate(batches):
+            _, _, loss3 = step3(b)
+            assert math.isfinite(float(loss3.detach()))
+            if i == 0:  # identical weights and batch: the same loss as the eager step, whatever the optimizer
+                assert abs(float(loss3.detach()) - losses1[0]) <= 1e-4 * abs(losses1[0])
+        moved = [(m3.state_dict()[k] - v.to(cuda)).abs().max().item() for k, v in ref_state.items()
+                 if v.dtype.is_floating_point and "running" not in k]
+        assert 1e-3 <= max(moved) <= 3.5e-3  # three Adam steps of lr 1e-3
+    finally:
+        torch.backends.cudnn.deterministic = old_det
 
 
 @pytest.mark.parametrize("N,H,Wd,leaky", [(6, 128, 157, False), (3, 20, 23, True), (2, 9, 10, False)])
