@@ -8,9 +8,11 @@
 // (frame overlap is served by L1/L2) and the output once.  Algorithmic bytes
 // per clip: 4*L + 4*n_mels*T.
 //
-// CTA = 256 threads = 4 frame groups of 64 threads; a CTA owns 32 consecutive
-// frames of one clip (8 per group) and stages its [n_mels x 32] output tile in
-// shared memory so the global store is coalesced along time.  The mel filters
+// CTA = 256 threads = 4 frame groups of 64 threads; a work item is 32
+// consecutive frames of one clip (8 per group), whose [n_mels x 32] output tile
+// is staged in shared memory so the global store is coalesced along time.  The
+// grid is persistent (2 CTAs per SM walk the items): the mel weight table, band
+// table, twiddle bases and window coefficients are staged once per CTA.  The mel filters
 // are triangular (<= 2 filters per bin), so the projection is a banded fp32 dot
 // product (1 009 non-zeros for 128 slaney mels) rather than a dense 513x128
 // GEMM: exact fp32, ~20x fewer flops than the dense contraction.
