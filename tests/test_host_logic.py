@@ -168,3 +168,39 @@ def test_bench_reference_arm_line_and_no_cuda_refusal():
                           capture_output=True, text=True, env=env, timeout=300)
     assert ours.returncode != 0 and "no CPU fallback" in (ours.stderr + ours.stdout)
     assert not [l for l in ours.stdout.splitlines() if l.startswith("{")]
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """profiles/r01_bench_n*.json are bench.py's JSON lines as measured on B200: every key of the bench contract is
+    there, the numbers are mutually consistent, and the roofline entry is the algorithmic bytes over the measured time."""
+    import glob
+    import json
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_n[1248].json")))
+    assert paths
+    for path in paths:
+        d = json.loads(open(path).read())
+        n = d["n_gpus"]
+        assert d["metric"].startswith("episodes/sec (5w5s15q") and d["unit"] == "episodes/sec"
+        assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+        assert d["data"] == "synthetic" and d["dtype"] == "f32" and d["warmup"] >= 3 and d["steps"] >= 1
+        cfg = d["config"]
+        assert "workload" in cfg and "model" not in cfg and "l2_policy" in cfg
+        per_step = cfg["episodes_per_step_per_gpu"] * n
+        assert abs(d["value"] - per_step / d["ms_per_step"] * 1e3) <= 1e-6 * d["value"]
+        e2e = d["e2e"]
+        assert e2e["unit"] == d["unit"] and 0 < e2e["value"] < d["value"]
+        # host fp32 waveforms of one step, and its logits + accuracy back
+        assert e2e["h2d_bytes_per_step"] == cfg["clips_per_step_per_gpu"] * cfg["clip_samples"] * 4
+        assert e2e["d2h_bytes_per_step"] == cfg["episodes_per_step_per_gpu"] * cfg["way"] * cfg["query"] * cfg["way"] * 4 + 4
+        assert d["gpu_launches"] > 0
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert r["bytes_per_launch"] == cfg["clips_per_step_per_gpu"] * 400384  # SURVEY 8(d): 4 L + 4 n_mels T per clip
+        assert abs(r["achieved"] - r["bytes_per_launch"] / r["ms_per_launch"] / 1e6) <= 1e-6 * r["achieved"]
+        assert r["traffic"] is None or 0.5 * r["bytes_per_launch"] < r["traffic"] < 1.5 * r["bytes_per_launch"]
+        c = d["clocks"]
+        assert c["sm_mhz"] > 0.9 * c["sm_max_mhz"] and not set(c["reasons"]) & {
+            "hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if n == 1:
+            b = d["cpu_baseline"]
+            assert b["kind"] == "port" and b["cores"] >= 1 and b["unit"] == d["unit"] and 0 < b["value"] < e2e["value"]
