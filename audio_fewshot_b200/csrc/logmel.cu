@@ -20,12 +20,14 @@
 // There is no reference implementation of this stage; the
 // canonical spec is oracle/frontend.py.
 #include <math.h>
+#include <stdlib.h>
 
 #include <new>
 #include <vector>
 
 #include "common.cuh"
 #include "logmel_core.cuh"
+#include "logmel_packed.cuh"
 #include "philox.cuh"
 
 struct afs_logmel_plan {
@@ -36,6 +38,7 @@ struct afs_logmel_plan {
   float2* d_tw1024;  // [1024]
   int* d_band;       // [3][128]: lo, len, off
   float* d_weights;  // [nnz]
+  int packed;        // 1: packed-f32x2 FFT phases (logmel_packed.cuh; AFS_LOGMEL_PACKED=1 when the plan is created)
 };
 
 namespace afs {
@@ -174,7 +177,7 @@ __device__ __forceinline__ void load_frame(const S* __restrict__ x, int64_t s0, 
   }
 }
 
-template <bool AUG, typename S>
+template <bool AUG, typename S, bool PACKED>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
   float* s_w = smem;
@@ -257,15 +260,20 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
 
     for (int fl = f_begin; fl < f_end; ++fl) {
       cpx z[8];
-  #pragma unroll
+      float2 zp[8];
+#pragma unroll
       for (int r = 0; r < 8; ++r) {
-        z[r].re = raw[r].x * win[r].x;
-        z[r].im = raw[r].y * win[r].y;
+        if (PACKED) {
+          zp[r] = p_mul(raw[r], win[r]);
+        } else {
+          z[r].re = raw[r].x * win[r].x;
+          z[r].im = raw[r].y * win[r].y;
+        }
       }
       if (fl + 1 < f_end) {  // prefetch the next frame while this one is transformed
         const int64_t s_next = static_cast<int64_t>(t0 + fl + 1) * p.hop - p.pad;
         if (half_overlap) {  // its first half is this frame's second half: sample index s_next + 2(t+64r) = s0 + 2(t+64(r+4))
-  #pragma unroll
+#pragma unroll
           for (int r = 0; r < 4; ++r) raw[r] = raw[r + 4];
           load_frame<AUG, S, 4>(x, s_next, p.L, t, aug, raw);
         } else {
@@ -273,23 +281,36 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
         }
       }
       const int slot = (fl - f_begin) % kMelBatch;
-      phase_a(t, z, tw, bufA);
-      group_bar(grp);
-      phase_b(t, tw, bufA, bufB);
-      group_bar(grp);
-      phase_c(t, bufB, bufA);
-      group_bar(grp);
-      phase_d(t, tw, bufA, bufP + slot * kPStride);
-      group_bar(grp);
+      if (PACKED) {  // complex numbers as (re, im) register pairs, 64-bit exchanges (logmel_packed.cuh)
+        float2* a2 = reinterpret_cast<float2*>(bufA);
+        float2* b2 = reinterpret_cast<float2*>(bufB);
+        phase_a_p(t, zp, tw, a2);
+        group_bar(grp);
+        phase_b_p(t, tw, a2, b2);
+        group_bar(grp);
+        phase_c_p(t, b2, a2);
+        group_bar(grp);
+        phase_d_p(t, tw, a2, bufP + slot * kPStride);
+        group_bar(grp);
+      } else {
+        phase_a(t, z, tw, bufA);
+        group_bar(grp);
+        phase_b(t, tw, bufA, bufB);
+        group_bar(grp);
+        phase_c(t, bufB, bufA);
+        group_bar(grp);
+        phase_d(t, tw, bufA, bufP + slot * kPStride);
+        group_bar(grp);
+      }
       if (slot == kMelBatch - 1 || fl + 1 == f_end) {
         const int fl0 = fl - slot;  // first frame of this batch
-  #pragma unroll
+#pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int m = mel_id[i];
           if (m >= 0) {
             float acc[kMelBatch];
             mel_dot_batch(bufP, s_w + s_band[2 * kMaxMels + m], kEllStride, s_band[m], s_band[kMaxMels + m], acc);
-  #pragma unroll
+#pragma unroll
             for (int f = 0; f < kMelBatch; ++f)
               if (f <= slot) s_tile[m * kTileStride + fl0 + f] = norm_db(acc[f], p.log_eps, mel_scale[i], mel_shift[i]);
           }
@@ -345,6 +366,10 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   plan->device = device;
   plan->nnz = static_cast<int>(weights.size());
   plan->d_window = nullptr; plan->d_tw1024 = nullptr; plan->d_band = nullptr; plan->d_weights = nullptr;
+  {  // experimental packed-f32x2 phases: opt-in per plan, never the default
+    const char* v = getenv("AFS_LOGMEL_PACKED");
+    plan->packed = (v != nullptr && v[0] == '1') ? 1 : 0;
+  }
 
   int prev = 0;
   cudaError_t e = cudaGetDevice(&prev);
@@ -358,10 +383,14 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   if (e == cudaSuccess) e = cudaMemcpy(plan->d_band, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(plan->d_weights, weights.data(), weights.size() * sizeof(float), cudaMemcpyHostToDevice);
   const int smem = static_cast<int>(kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (plan->packed && e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (plan->packed && e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, int16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (plan->packed && e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (plan->packed && e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, int16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaSetDevice(prev);
   if (e != cudaSuccess) {
     afs_logmel_plan_destroy(plan);
@@ -419,13 +448,16 @@ int logmel_launch(const afs_logmel_plan* plan, const S* wav, float pcm_scale, in
   // persistent: 2 resident CTAs per SM (128 registers x 256 threads, 100 KB of shared memory each) walk the items
   const int64_t grid = items < 2 * kNumSMs ? items : 2 * kNumSMs;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const unsigned g = static_cast<unsigned>(grid);
   if (aug != nullptr) {
     p.gain_lo = aug->gain_db_lo; p.gain_hi = aug->gain_db_hi;
     p.noise_lo = aug->noise_std_lo; p.noise_hi = aug->noise_std_hi;
     p.max_shift = aug->max_shift;
-    logmel_kernel<true, S><<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(p);
+    if (plan->packed) logmel_kernel<true, S, true><<<g, kThreads, kSmemBytes, stream>>>(p);
+    else logmel_kernel<true, S, false><<<g, kThreads, kSmemBytes, stream>>>(p);
   } else {
-    logmel_kernel<false, S><<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(p);
+    if (plan->packed) logmel_kernel<false, S, true><<<g, kThreads, kSmemBytes, stream>>>(p);
+    else logmel_kernel<false, S, false><<<g, kThreads, kSmemBytes, stream>>>(p);
   }
   AFS_LAUNCH_CHECK();
   return AFS_OK;

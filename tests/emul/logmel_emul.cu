@@ -10,13 +10,14 @@
 #include <vector>
 
 #include "logmel_core.cuh"
+#include "logmel_packed.cuh"
 
 using namespace afs::logmel;
 
-extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, const float* fb,
-                           const float* window, int n_mels, const float* mean, const float* stdv,
-                           float log_mult, float log_eps, float* out /*[n_mels, T]*/,
-                           float* power_out /*[T, 513] nullable*/) {
+static int emul_logmel_impl(bool packed, const float* wav, int64_t L, int hop, int center, const float* fb,
+                            const float* window, int n_mels, const float* mean, const float* stdv,
+                            float log_mult, float log_eps, float* out /*[n_mels, T]*/,
+                            float* power_out /*[T, 513] nullable*/) {
   std::vector<int> band;
   std::vector<float> weights;
   pack_mel_ell(fb, n_mels, band, weights);  // the table the kernel reads, start shifts included
@@ -42,13 +43,27 @@ extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, con
         z[r].re = wav[i0] * window[2 * n];
         z[r].im = wav[i1] * window[2 * n + 1];
       }
-      phase_a(t, z, tws[t], bufA.data());
+      if (packed) {
+        float2 zp[8];
+        for (int r = 0; r < 8; ++r) zp[r] = make_float2(z[r].re, z[r].im);
+        phase_a_p(t, zp, tws[t], reinterpret_cast<float2*>(bufA.data()));
+      } else {
+        phase_a(t, z, tws[t], bufA.data());
+      }
     }
-    for (int t = 0; t < kGroup; ++t) phase_b(t, tws[t], bufA.data(), bufB.data());
-    for (int t = 0; t < kGroup; ++t) phase_c(t, bufB.data(), bufA.data());
     const int slot = f % kMelBatch;
     float* power = bufP.data() + slot * kPStride;
-    for (int t = 0; t < kGroup; ++t) phase_d(t, tws[t], bufA.data(), power);
+    if (packed) {
+      float2* a2 = reinterpret_cast<float2*>(bufA.data());
+      float2* b2 = reinterpret_cast<float2*>(bufB.data());
+      for (int t = 0; t < kGroup; ++t) phase_b_p(t, tws[t], a2, b2);
+      for (int t = 0; t < kGroup; ++t) phase_c_p(t, b2, a2);
+      for (int t = 0; t < kGroup; ++t) phase_d_p(t, tws[t], a2, power);
+    } else {
+      for (int t = 0; t < kGroup; ++t) phase_b(t, tws[t], bufA.data(), bufB.data());
+      for (int t = 0; t < kGroup; ++t) phase_c(t, bufB.data(), bufA.data());
+      for (int t = 0; t < kGroup; ++t) phase_d(t, tws[t], bufA.data(), power);
+    }
     if (power_out) for (int k = 0; k < kBins; ++k) power_out[static_cast<size_t>(f) * kBins + k] = power[k];
     if (slot != kMelBatch - 1 && f + 1 != T) continue;
     for (int t = 0; t < kGroup; ++t) {  // batched mel projection, as the kernel's epilogue
@@ -68,6 +83,58 @@ extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, con
     }
   }
   return T;
+}
+
+extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, const float* fb,
+                           const float* window, int n_mels, const float* mean, const float* stdv,
+                           float log_mult, float log_eps, float* out, float* power_out) {
+  return emul_logmel_impl(false, wav, L, hop, center, fb, window, n_mels, mean, stdv, log_mult, log_eps, out, power_out);
+}
+
+// the same frames through the packed-f32x2 phases of logmel_packed.cuh (host fallbacks of the packed intrinsics)
+extern "C" int emul_logmel_packed(const float* wav, int64_t L, int hop, int center, const float* fb,
+                                  const float* window, int n_mels, const float* mean, const float* stdv,
+                                  float log_mult, float log_eps, float* out, float* power_out) {
+  return emul_logmel_impl(true, wav, L, hop, center, fb, window, n_mels, mean, stdv, log_mult, log_eps, out, power_out);
+}
+
+// Packed layouts: worst number of distinct 64-bit words that one half-warp (16 consecutive threads) puts on one of
+// the 16 eight-byte banks, over every shared-memory access pattern of the packed phases (1 = conflict-free), and
+// whether the exchange-2 slot function is a bijection onto [0, 512).  Returns the worst count, or -1.
+extern "C" int emul_packed_bank_check() {
+  bool seen[kHalf] = {false};
+  for (int q = 0; q < 8; ++q)
+    for (int j = 0; j < 8; ++j)
+      for (int p = 0; p < 8; ++p) {
+        const int s = e2p_slot(q, j, p);
+        if (s < 0 || s >= kHalf || seen[s]) return -1;
+        seen[s] = true;
+      }
+  int worst = 0;
+  auto half_warp = [&](auto addr_of_thread) {
+    for (int h = 0; h < 4; ++h) {
+      int words[16][16], cnt[16] = {0};
+      for (int l = 0; l < 16; ++l) {
+        const int a = addr_of_thread(16 * h + l), b = a & 15;
+        bool dup = false;
+        for (int i = 0; i < cnt[b]; ++i) dup = dup || words[b][i] == a;
+        if (!dup) words[b][cnt[b]++] = a;
+        if (cnt[b] > worst) worst = cnt[b];
+      }
+    }
+  };
+  for (int r = 0; r < 8; ++r) {
+    half_warp([&](int t) { return e1p_slot(r, t); });                        // phase A writes (q = r)
+    half_warp([&](int t) { return e1p_slot(t & 7, (t >> 3) + 8 * r); });     // phase B reads (j1 = r)
+    half_warp([&](int t) { return e2p_slot(t & 7, t >> 3, r); });            // phase B writes (p0 = r)
+    half_warp([&](int t) { return e2p_slot(t & 7, r, t >> 3); });            // phase C reads (j0 = r)
+    half_warp([&](int t) { return t + 64 * r; });                            // phase C writes (p1 = r)
+  }
+  for (int m = 0; m < 4; ++m) {
+    half_warp([&](int t) { return t + 64 * m; });                            // phase D reads Z[k]
+    half_warp([&](int t) { return (kHalf - (t + 64 * m)) & (kHalf - 1); });  // phase D reads Z[512 - k]
+  }
+  return worst;
 }
 
 // slot bijection check for the exchange-2 swizzle

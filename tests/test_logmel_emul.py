@@ -18,7 +18,8 @@ LIB = os.path.join(OUT_DIR, "liblogmel_emul.so")
 @pytest.fixture(scope="module")
 def emul():
     os.makedirs(OUT_DIR, exist_ok=True)
-    deps = [SRC, os.path.join(ROOT, "audio_fewshot_b200", "csrc", "logmel_core.cuh")]
+    deps = [SRC, os.path.join(ROOT, "audio_fewshot_b200", "csrc", "logmel_core.cuh"),
+            os.path.join(ROOT, "audio_fewshot_b200", "csrc", "logmel_packed.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-x", "cu",
                                "-Wno-deprecated-gpu-targets",
@@ -26,10 +27,11 @@ def emul():
                                "-I", os.path.join(ROOT, "include"), SRC, "-o", LIB])
     lib = C.CDLL(LIB)
     lib.emul_logmel.restype = C.c_int
+    lib.emul_logmel_packed.restype = C.c_int
     return lib
 
 
-def run(lib, x, hop, n_mels=128, mean=-15.1, std=26.2):
+def run(lib, x, hop, n_mels=128, mean=-15.1, std=26.2, packed=False):
     L = x.shape[0]
     fb = fe.mel_filterbank(n_mels=n_mels)
     win = fe.hann_periodic()
@@ -39,7 +41,7 @@ def run(lib, x, hop, n_mels=128, mean=-15.1, std=26.2):
     m = np.full(n_mels, mean, np.float32)
     s = np.full(n_mels, std, np.float32)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    got_T = lib.emul_logmel(vp(x), C.c_int64(L), hop, 1, vp(fb), vp(win), n_mels, vp(m), vp(s), C.c_float(10.0),
+    got_T = (lib.emul_logmel_packed if packed else lib.emul_logmel)(vp(x), C.c_int64(L), hop, 1, vp(fb), vp(win), n_mels, vp(m), vp(s), C.c_float(10.0),
                             C.c_float(fe.LOG_EPS), vp(out), vp(power))
     assert got_T == T
     return out, power, m, s
@@ -57,6 +59,27 @@ def test_phases_match_float64_spec(emul, L, hop, n_mels):
     ref = fe.logmel_f64(x[None], hop=hop, n_mels=n_mels, mean=m, std=s)[0, 0]
     db_err = np.abs(out - ref).max() * 26.2
     assert db_err < 1e-4, db_err  # north-star tolerance 1e-4 (de-normalised dB)
+
+
+@pytest.mark.parametrize("L,hop,n_mels", [(8000, 512, 128), (3000, 102, 128), (2049, 511, 128), (1500, 512, 64)])
+def test_packed_phases_match_float64_spec_and_scalar_phases(emul, L, hop, n_mels):
+    """logmel_packed.cuh (complex numbers as (re, im) register pairs, 64-bit exchanges; opt-in on the device) through
+    the host fallbacks of the packed intrinsics: same tolerance against the float64 spec as the scalar phases, and
+    within rounding of them."""
+    rng = np.random.default_rng(L + hop)
+    x = (rng.standard_normal(L) * 0.1).astype(np.float32)
+    out, power, m, s = run(emul, x, hop, n_mels, packed=True)
+    out0, power0, _, _ = run(emul, x, hop, n_mels)
+    fr = fe.frames(x[None].astype(np.float64), hop)[0] * fe.hann_periodic().astype(np.float64)
+    pref = np.abs(np.fft.rfft(fr, axis=-1)) ** 2
+    assert np.abs(power - pref).max() / pref.max() < 2e-6
+    assert np.abs(power - power0).max() / pref.max() < 2e-6
+    ref = fe.logmel_f64(x[None], hop=hop, n_mels=n_mels, mean=m, std=s)[0, 0]
+    assert np.abs(out - ref).max() * 26.2 < 1e-4
+
+
+def test_packed_layouts_are_bijective_and_conflict_free(emul):
+    assert emul.emul_packed_bank_check() == 1
 
 
 def test_exchange2_swizzle_is_a_bijection(emul):
