@@ -41,8 +41,9 @@ def run(lib, x, hop, n_mels=128, mean=-15.1, std=26.2, packed=False):
     m = np.full(n_mels, mean, np.float32)
     s = np.full(n_mels, std, np.float32)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    got_T = (lib.emul_logmel_packed if packed else lib.emul_logmel)(vp(x), C.c_int64(L), hop, 1, vp(fb), vp(win), n_mels, vp(m), vp(s), C.c_float(10.0),
-                            C.c_float(fe.LOG_EPS), vp(out), vp(power))
+    fn = lib.emul_logmel_packed if packed else lib.emul_logmel
+    got_T = fn(vp(x), C.c_int64(L), hop, 1, vp(fb), vp(win), n_mels, vp(m), vp(s), C.c_float(10.0),
+               C.c_float(fe.LOG_EPS), vp(out), vp(power))
     assert got_T == T
     return out, power, m, s
 
