@@ -509,8 +509,8 @@ def test_graphed_train_step_matches_eager_maml(cuda):
     Both models are put on the same weights before every step: a randomly initialised MAML net is chaotic (dead
     channels under batch-statistics BatchNorm amplify a 1e-7 weight difference into a 1e-3 loss difference one step
     later, eager against eager as well -- tools/diag_graphed_maml.py, profiles/r01_maml_step_reproducibility.txt),
-    so free-running loss sequences only agree when every kernel is bit-reproducible.  Measured on B200: update difference 1e-5 relative
-    with cuDNN's default algorithms, exactly 0 with cudnn.deterministic."""
+    so free-running loss sequences only agree when every kernel is bit-reproducible.  Measured on B200: update
+    difference 1e-5 relative with cuDNN's default algorithms, exactly 0 with cudnn.deterministic."""
     import copy
     from audio_fewshot_b200 import model as arch
     from audio_fewshot_b200.graph_step import GraphedTrainStep
