@@ -38,7 +38,8 @@ struct afs_logmel_plan {
   float2* d_tw1024;  // [1024]
   int* d_band;       // [3][128]: lo, len, off
   float* d_weights;  // [nnz]
-  int packed;        // 1: packed-f32x2 FFT phases (logmel_packed.cuh; AFS_LOGMEL_PACKED=1 when the plan is created)
+  int packed;        // 1: packed-f32x2 FFT phases (logmel_packed.cuh; AFS_LOGMEL_PACKED=1 when the plan is created);
+                     // 2: the same plus the pointer-bump frame prefetch
 };
 
 namespace afs {
@@ -76,6 +77,7 @@ struct Params {
   int max_shift;
   uint32_t seed_lo, seed_hi;
   uint64_t first_clip;
+  int lean;  // packed variant only (AFS_LOGMEL_PACKED=2): pointer-bump prefetch for groups whose frames are all interior
 };
 
 struct AugState {
@@ -257,6 +259,20 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
 
     float2 raw[8];
     if (f_begin < f_end) load_frame<AUG, S, 0>(x, static_cast<int64_t>(t0 + f_begin) * p.hop - p.pad, p.L, t, aug, raw);
+    // EXPERIMENTAL (packed variant, level 2): when every frame of this group lies inside the clip and starts on an
+    // aligned sample pair, the prefetch is four 64-bit loads off a pointer that advances by hop -- the general path
+    // spends ~35 instructions per frame on 64-bit index arithmetic and the interior / alignment / reflect selection.
+    bool lean = false;
+    const S* fptr = x;
+    if constexpr (PACKED && !AUG) {
+      if (p.lean != 0 && f_begin < f_end) {
+        const int64_t s_first = static_cast<int64_t>(t0 + f_begin) * p.hop - p.pad;
+        const int64_t s_last = static_cast<int64_t>(t0 + f_end - 1) * p.hop - p.pad;
+        lean = (p.hop & 1) == 0 && s_first >= 0 && s_last + kNfft <= p.L &&
+               (reinterpret_cast<uintptr_t>(x + s_first) & (2 * sizeof(S) - 1)) == 0;
+        fptr = x + s_first + 2 * t;
+      }
+    }
 
     for (int fl = f_begin; fl < f_end; ++fl) {
       cpx z[8];
@@ -270,7 +286,20 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
           z[r].im = raw[r].y * win[r].y;
         }
       }
-      if (fl + 1 < f_end) {  // prefetch the next frame while this one is transformed
+      if (PACKED && !AUG && lean) {
+        if (fl + 1 < f_end) {
+          fptr += p.hop;  // sample 2 (t + 64 r) of the next frame is fptr[128 r]
+          if (half_overlap) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) raw[r] = raw[r + 4];
+#pragma unroll
+            for (int r = 4; r < 8; ++r) raw[r] = ld_pair(fptr + 128 * r, aug.pcm_scale);
+          } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) raw[r] = ld_pair(fptr + 128 * r, aug.pcm_scale);
+          }
+        }
+      } else if (fl + 1 < f_end) {  // prefetch the next frame while this one is transformed
         const int64_t s_next = static_cast<int64_t>(t0 + fl + 1) * p.hop - p.pad;
         if (half_overlap) {  // its first half is this frame's second half: sample index s_next + 2(t+64r) = s0 + 2(t+64(r+4))
 #pragma unroll
@@ -368,7 +397,7 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   plan->d_window = nullptr; plan->d_tw1024 = nullptr; plan->d_band = nullptr; plan->d_weights = nullptr;
   {  // experimental packed-f32x2 phases: opt-in per plan, never the default
     const char* v = getenv("AFS_LOGMEL_PACKED");
-    plan->packed = (v != nullptr && v[0] == '1') ? 1 : 0;
+    plan->packed = (v != nullptr && (v[0] == '1' || v[0] == '2')) ? v[0] - '0' : 0;  // 2: + pointer-bump prefetch
   }
 
   int prev = 0;
@@ -443,6 +472,7 @@ int logmel_launch(const afs_logmel_plan* plan, const S* wav, float pcm_scale, in
   p.gain_lo = p.gain_hi = p.noise_lo = p.noise_hi = 0.f; p.max_shift = 0;
   p.seed_lo = static_cast<uint32_t>(seed); p.seed_hi = static_cast<uint32_t>(seed >> 32);
   p.first_clip = first_clip_index;
+  p.lean = plan->packed == 2 ? 1 : 0;
   const int64_t items = static_cast<int64_t>(B) * p.chunks;
   if (items > 0x7fffffffLL) return AFS_ERR_UNSUPPORTED;
   // persistent: 2 resident CTAs per SM (128 registers x 256 threads, 100 KB of shared memory each) walk the items

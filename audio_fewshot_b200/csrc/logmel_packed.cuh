@@ -1,5 +1,6 @@
 // Packed-f32x2 formulation of the log-mel kernel's FFT phases (EXPERIMENTAL, opt-in: AFS_LOGMEL_PACKED=1 at plan
-// creation; the default kernel uses the scalar phases of logmel_core.cuh).
+// creation, =2 adds the pointer-bump frame prefetch of logmel.cu; the default kernel uses the scalar phases of
+// logmel_core.cuh).
 //
 // Why: after the conflict-free mel reads the kernel is instruction-issue bound (profiles/r01_logmel_v5_ncu.csv:
 // 66 % of the issue slots at 4 warps per scheduler, 695 warp-instructions per warp-frame, 339 of them FP).  sm_100a
