@@ -141,3 +141,38 @@ def test_phase_d_power_writes_are_conflict_free():
         for h in range(2):
             ks = [u + 64 * m for u in range(32 * h, 32 * h + 32)]
             assert len({k % 32 for k in ks}) == 32 and len({(512 - k) % 32 for k in ks}) == 32
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_ell_packing_on_random_triangular_filterbanks(emul, seed):
+    """Whatever the filterbank (random band edges, overlapping or not, filters starting at bin 0 or ending at bin 512,
+    an empty filter), the shifted ELL table reproduces it exactly, every filter has one owner, and every power read
+    stays inside the 513 written bins."""
+    rng = np.random.default_rng(seed)
+    n_mels = int(rng.integers(33, 129))
+    edges = np.sort(rng.integers(0, 513, size=n_mels + 2))
+    edges[0], edges[-1] = 0, 512
+    fb = np.zeros((513, n_mels), np.float32)
+    k = np.arange(513)
+    for m in range(n_mels):
+        lo, c, hi = edges[m], edges[m + 1], edges[m + 2]
+        if hi - lo > 60:  # keep the table inside the kernel's 16 KB budget
+            hi = lo + 60
+            c = min(c, hi)
+        up = (k - lo) / max(c - lo, 1)
+        down = (hi - k) / max(hi - c, 1)
+        fb[:, m] = np.clip(np.minimum(up, down), 0.0, None) * rng.uniform(0.5, 2.0)
+    if seed == 0:
+        fb[:, 3] = 0.0  # an empty filter
+    fb = np.ascontiguousarray(fb)
+    dense = np.zeros((513, n_mels), np.float32)
+    owners = np.zeros(n_mels, np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = emul.emul_mel_ell_dense(vp(fb), n_mels, vp(dense), vp(owners))
+    assert 0 < n <= 4096 and n % 32 == 0
+    assert (owners == 1).all() and np.array_equal(dense, fb)
+    it0, it1 = C.c_int(0), C.c_int(0)
+    plain = emul.emul_mel_read_wavefronts(vp(fb), n_mels, 0, C.byref(it0))
+    shifted = emul.emul_mel_read_wavefronts(vp(fb), n_mels, 1, C.byref(it1))
+    assert plain >= 0 and shifted >= 0  # -1: a read outside [0, 513)
+    assert it1.value == it0.value and shifted <= plain
