@@ -338,7 +338,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
           const int m = mel_id[i];
           if (m >= 0) {
             float acc[kMelBatch];
-            mel_dot_batch(bufP, s_w + s_band[2 * kMaxMels + m], kEllStride, s_band[m], s_band[kMaxMels + m], acc);
+            if (PACKED) mel_dot_batch_p(bufP, s_w + s_band[2 * kMaxMels + m], kEllStride, s_band[m], s_band[kMaxMels + m], acc);
+            else mel_dot_batch(bufP, s_w + s_band[2 * kMaxMels + m], kEllStride, s_band[m], s_band[kMaxMels + m], acc);
 #pragma unroll
             for (int f = 0; f < kMelBatch; ++f)
               if (f <= slot) s_tile[m * kTileStride + fl0 + f] = norm_db(acc[f], p.log_eps, mel_scale[i], mel_shift[i]);

@@ -158,5 +158,21 @@ AFS_HD void phase_d_p(int u, const ThreadTw& tw, const float2* bufA, float* powe
   }
 }
 
+// mel_dot_batch with the four frames as two register pairs: one FFMA2 per pair and weight (the weight is a scalar
+// broadcast operand, the two power values are the destinations of two LDS); same products and sums as the scalar loop.
+AFS_HD void mel_dot_batch_p(const float* power, const float* weights, int wstride, int lo, int len,
+                            float (&acc)[kMelBatch]) {
+  static_assert(kMelBatch == 4, "two pairs of frames");
+  float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+  const float* p0 = power + lo;
+  for (int i = 0; i < len; ++i) {
+    const float w = weights[i * wstride];
+    const float2 ww = make_float2(w, w);
+    a01 = p_fma(ww, make_float2(p0[i], p0[kPStride + i]), a01);
+    a23 = p_fma(ww, make_float2(p0[2 * kPStride + i], p0[3 * kPStride + i]), a23);
+  }
+  acc[0] = a01.x; acc[1] = a01.y; acc[2] = a23.x; acc[3] = a23.y;
+}
+
 }  // namespace logmel
 }  // namespace afs

@@ -74,7 +74,8 @@ static int emul_logmel_impl(bool packed, const float* wav, int64_t L, int hop, i
         const int m = mel_id[i];
         if (m < 0) continue;
         float acc[kMelBatch];
-        mel_dot_batch(bufP.data(), weights.data() + band[2 * kMaxMels + m], kEllStride, band[m], band[kMaxMels + m], acc);
+        if (packed) mel_dot_batch_p(bufP.data(), weights.data() + band[2 * kMaxMels + m], kEllStride, band[m], band[kMaxMels + m], acc);
+        else mel_dot_batch(bufP.data(), weights.data() + band[2 * kMaxMels + m], kEllStride, band[m], band[kMaxMels + m], acc);
         const float scale = log_mult * 0.30102999566398120f / stdv[m];
         const float shift = -mean[m] / stdv[m];
         for (int b = 0; b <= slot; ++b)
