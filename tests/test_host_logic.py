@@ -164,6 +164,11 @@ def test_bench_reference_arm_line_and_no_cuda_refusal():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # under torchrun only rank 0 runs the reference arm; the other ranks exit 0 without work or output
+    other = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                            "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300,
+                           env=dict(env, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2"))
+    assert other.returncode == 0 and not [l for l in other.stdout.splitlines() if l.startswith("{")]
     ours = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
                           capture_output=True, text=True, env=env, timeout=300)
     assert ours.returncode != 0 and "no CPU fallback" in (ours.stderr + ours.stdout)
