@@ -36,13 +36,6 @@ struct Conv1TcParams {
   float shift[kCh1];
 };
 
-// NTC = output channels computed by the tensor cores (UMMA N).  NTC = 64 is the kernel described above.  NTC = 32 is
-// the EXPERIMENTAL hybrid (opt-in, AFS_CONV1_HYBRID=1; written at the end of round 1 and not yet run on a GPU): the
-// kernel above is bound by moving every conv output out of tensor memory (64 B/clk/SM) while the FMA pipe idles, so
-// channels 32..63 are computed by the SAME thread from the patch it already holds in registers -- 27 FFMAs per
-// channel and window row with the weights as constant-bank operands, as in conv1.cu -- and only channels 0..31
-// cross tensor memory: 18 clk of TMEM reads and ~20 clk of FMA-pipe time per pooled pixel and SM instead of 36.
-template <int NTC>
 __global__ void __launch_bounds__(kPix1)
 conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, int PH, int PW, float slope,
                 float* __restrict__ out, const __grid_constant__ Conv1TcParams prm) {
@@ -55,11 +48,10 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
   const uint32_t a_base = smem_u32(s_buf);
   const uint32_t w_base = a_base + 2u * kBufBytes;
 
-  static_assert(NTC == 64 || NTC == 32, "UMMA N: all channels, or half of them with the rest on the FMA pipe");
-  constexpr uint32_t kTmemCols1 = NTC == 64 ? 256 : 128;  // 3 accumulators x NTC columns, power of two
+  constexpr uint32_t kTmemCols1 = 256;  // 3 accumulators x 64 columns, power of two
   // folded weights -> K-major operand [chunk][channel][4 taps], TF32-rounded; taps 9..15 are zero
-  for (int i = tid; i < 4 * NTC; i += kPix1) {
-    const int chunk = i / NTC, c = i - chunk * NTC;
+  for (int i = tid; i < 4 * kCh1; i += kPix1) {
+    const int chunk = i / kCh1, c = i - chunk * kCh1;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (chunk == 0) v = make_float4(to_tf32(prm.w[c * 9 + 0]), to_tf32(prm.w[c * 9 + 1]), to_tf32(prm.w[c * 9 + 2]), to_tf32(prm.w[c * 9 + 3]));
     if (chunk == 1) v = make_float4(to_tf32(prm.w[c * 9 + 4]), to_tf32(prm.w[c * 9 + 5]), to_tf32(prm.w[c * 9 + 6]), to_tf32(prm.w[c * 9 + 7]));
@@ -82,7 +74,7 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
   const uint32_t tmem_base = s_tmem;
   const uint32_t bar = smem_u32(&s_bar);
   const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  constexpr uint32_t kIdesc = idesc_tf32(kPix1, NTC);
+  constexpr uint32_t kIdesc = idesc_tf32(kPix1, kCh1);
 
   const int64_t n_tiles = (total_pix + kPix1 - 1) / kPix1;
   const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -156,35 +148,11 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
 #pragma unroll
         for (int k8 = 0; k8 < 2; ++k8) {
           const uint64_t da = desc_kmajor_noswizzle(buf + dx * kWinBytes + k8 * 2u * (16u * kPix1), 16u * kPix1, 128u);
-          const uint64_t db = desc_kmajor_noswizzle(w_base + k8 * 2u * (16u * NTC), 16u * NTC, 128u);
-          mma_tf32(tmem_base + dx * NTC, da, db, kIdesc, k8 > 0);
+          const uint64_t db = desc_kmajor_noswizzle(w_base + k8 * 2u * (16u * kCh1), 16u * kCh1, 128u);
+          mma_tf32(tmem_base + dx * kCh1, da, db, kIdesc, k8 > 0);
         }
       }
       commit(bar);
-    }
-    if constexpr (NTC < kCh1) {  // channels NTC..63 of this window row on the FMA pipe, from the register patch, while the MMAs run
-      const int gs = static_cast<int>(step % 3);
-#pragma unroll
-      for (int gg = 0; gg < 3; ++gg) {
-        if (gg == gs) {  // compile-time gg inside each copy: p[] keeps static indices
-#pragma unroll
-          for (int c = NTC; c < kCh1; ++c) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                const float w = prm.w[c * 9 + ky * 3 + kx];
-                a0 = fmaf(w, p[gg + ky][kx], a0);
-                a1 = fmaf(w, p[gg + ky][kx + 1], a1);
-                a2 = fmaf(w, p[gg + ky][kx + 2], a2);
-              }
-            }
-            const float m = fmaxf(a0, fmaxf(a1, a2));
-            best[c] = gg == 0 ? m : fmaxf(best[c], m);
-          }
-        }
-      }
     }
     if (step + 1 < n_steps) build(step + 1);  // overlaps the MMAs just issued (other buffer)
     mbar_wait(bar, phase);
@@ -193,10 +161,10 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
 
     const int g = static_cast<int>(step % 3);
 #pragma unroll
-    for (int half = 0; half < NTC / 32; ++half) {  // 32 channels at a time: three windows x 32 columns, loads batched
+    for (int half = 0; half < kCh1 / 32; ++half) {  // 32 channels at a time: three windows x 32 columns, loads batched
       uint32_t v0[32], v1[32];
-      tmem_ld32_nowait(t_row + static_cast<uint32_t>(0 * NTC + half * 32), v0);
-      tmem_ld32_nowait(t_row + static_cast<uint32_t>(1 * NTC + half * 32), v1);
+      tmem_ld32_nowait(t_row + static_cast<uint32_t>(0 * kCh1 + half * 32), v0);
+      tmem_ld32_nowait(t_row + static_cast<uint32_t>(1 * kCh1 + half * 32), v1);
       tmem_wait_ld();
       if (g == 0) {
 #pragma unroll
@@ -206,7 +174,7 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
         for (int j = 0; j < 32; ++j)
           best[half * 32 + j] = fmaxf(best[half * 32 + j], fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
       }
-      tmem_ld32(t_row + static_cast<uint32_t>(2 * NTC + half * 32), v0);
+      tmem_ld32(t_row + static_cast<uint32_t>(2 * kCh1 + half * 32), v0);
 #pragma unroll
       for (int j = 0; j < 32; ++j) best[half * 32 + j] = fmaxf(best[half * 32 + j], __uint_as_float(v0[j]));
     }
@@ -259,15 +227,8 @@ extern "C" int afs_conv1_bn_act_pool3_fwd_tf32(const float* x, int32_t N, int32_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t smem = 2 * kBufBytes + kWBytes;
   int64_t blocks = n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs;  // persistent: 2 CTAs per SM (256 TMEM columns each)
-  static const bool hybrid = [] { const char* v = getenv("AFS_CONV1_HYBRID"); return v != nullptr && v[0] == '1'; }();
-  if (hybrid) {  // experimental: half of the channels on the FMA pipe (see the kernel's comment); never the default
-    AFS_CUDA_TRY(cudaFuncSetAttribute(conv1_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    conv1_tc_kernel<32><<<static_cast<unsigned>(blocks), kPix1, smem, stream>>>(x, total, H, Wd, PH, PW, negative_slope, out, prm);
-    AFS_LAUNCH_CHECK();
-    return AFS_OK;
-  }
-  AFS_CUDA_TRY(cudaFuncSetAttribute(conv1_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  conv1_tc_kernel<64><<<static_cast<unsigned>(blocks), kPix1, smem, stream>>>(x, total, H, Wd, PH, PW, negative_slope, out, prm);
+  AFS_CUDA_TRY(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  conv1_tc_kernel<<<static_cast<unsigned>(blocks), kPix1, smem, stream>>>(x, total, H, Wd, PH, PW, negative_slope, out, prm);
   AFS_LAUNCH_CHECK();
   return AFS_OK;
 }

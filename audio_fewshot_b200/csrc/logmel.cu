@@ -27,7 +27,7 @@
 
 #include "common.cuh"
 #include "logmel_core.cuh"
-#include "logmel_packed.cuh"
+#include "logmel_fft.cuh"
 #include "philox.cuh"
 
 struct afs_logmel_plan {
@@ -38,8 +38,6 @@ struct afs_logmel_plan {
   float2* d_tw1024;  // [1024]
   int* d_band;       // [3][128]: lo, len, off
   float* d_weights;  // [nnz]
-  int packed;        // 1: packed-f32x2 FFT phases (logmel_packed.cuh; AFS_LOGMEL_PACKED=1 when the plan is created);
-                     // 2: the same plus the pointer-bump frame prefetch
 };
 
 namespace afs {
@@ -77,7 +75,6 @@ struct Params {
   int max_shift;
   uint32_t seed_lo, seed_hi;
   uint64_t first_clip;
-  int lean;  // packed variant only (AFS_LOGMEL_PACKED=2): pointer-bump prefetch for groups whose frames are all interior
 };
 
 struct AugState {
@@ -179,7 +176,7 @@ __device__ __forceinline__ void load_frame(const S* __restrict__ x, int64_t s0, 
   }
 }
 
-template <bool AUG, typename S, bool PACKED>
+template <bool AUG, typename S>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
   float* s_w = smem;
@@ -259,13 +256,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
 
     float2 raw[8];
     if (f_begin < f_end) load_frame<AUG, S, 0>(x, static_cast<int64_t>(t0 + f_begin) * p.hop - p.pad, p.L, t, aug, raw);
-    // EXPERIMENTAL (packed variant, level 2): when every frame of this group lies inside the clip and starts on an
-    // aligned sample pair, the prefetch is four 64-bit loads off a pointer that advances by hop -- the general path
-    // spends ~35 instructions per frame on 64-bit index arithmetic and the interior / alignment / reflect selection.
+    // When every frame of this group lies inside the clip and starts on an aligned sample pair, the prefetch is
+    // four 64-bit loads off a pointer that advances by hop -- the general path spends ~35 instructions per frame on
+    // 64-bit index arithmetic and the interior / alignment / reflect selection.
     bool lean = false;
     const S* fptr = x;
-    if constexpr (PACKED && !AUG) {
-      if (p.lean != 0 && f_begin < f_end) {
+    if constexpr (!AUG) {
+      if (f_begin < f_end) {
         const int64_t s_first = static_cast<int64_t>(t0 + f_begin) * p.hop - p.pad;
         const int64_t s_last = static_cast<int64_t>(t0 + f_end - 1) * p.hop - p.pad;
         lean = (p.hop & 1) == 0 && s_first >= 0 && s_last + kNfft <= p.L &&
@@ -275,18 +272,10 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
     }
 
     for (int fl = f_begin; fl < f_end; ++fl) {
-      cpx z[8];
-      float2 zp[8];
+      float2 zp[8];  // complex numbers as (re, im) register pairs, 64-bit exchanges (logmel_fft.cuh)
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if (PACKED) {
-          zp[r] = p_mul(raw[r], win[r]);
-        } else {
-          z[r].re = raw[r].x * win[r].x;
-          z[r].im = raw[r].y * win[r].y;
-        }
-      }
-      if (PACKED && !AUG && lean) {
+      for (int r = 0; r < 8; ++r) zp[r] = p_mul(raw[r], win[r]);
+      if (!AUG && lean) {
         if (fl + 1 < f_end) {
           fptr += p.hop;  // sample 2 (t + 64 r) of the next frame is fptr[128 r]
           if (half_overlap) {
@@ -310,27 +299,16 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
         }
       }
       const int slot = (fl - f_begin) % kMelBatch;
-      if (PACKED) {  // complex numbers as (re, im) register pairs, 64-bit exchanges (logmel_packed.cuh)
-        float2* a2 = reinterpret_cast<float2*>(bufA);
-        float2* b2 = reinterpret_cast<float2*>(bufB);
-        phase_a_p(t, zp, tw, a2);
-        group_bar(grp);
-        phase_b_p(t, tw, a2, b2);
-        group_bar(grp);
-        phase_c_p(t, b2, a2);
-        group_bar(grp);
-        phase_d_p(t, tw, a2, bufP + slot * kPStride);
-        group_bar(grp);
-      } else {
-        phase_a(t, z, tw, bufA);
-        group_bar(grp);
-        phase_b(t, tw, bufA, bufB);
-        group_bar(grp);
-        phase_c(t, bufB, bufA);
-        group_bar(grp);
-        phase_d(t, tw, bufA, bufP + slot * kPStride);
-        group_bar(grp);
-      }
+      float2* a2 = reinterpret_cast<float2*>(bufA);
+      float2* b2 = reinterpret_cast<float2*>(bufB);
+      phase_a_p(t, zp, tw, a2);
+      group_bar(grp);
+      phase_b_p(t, tw, a2, b2);
+      group_bar(grp);
+      phase_c_p(t, b2, a2);
+      group_bar(grp);
+      phase_d_p(t, tw, a2, bufP + slot * kPStride);
+      group_bar(grp);
       if (slot == kMelBatch - 1 || fl + 1 == f_end) {
         const int fl0 = fl - slot;  // first frame of this batch
 #pragma unroll
@@ -338,8 +316,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
           const int m = mel_id[i];
           if (m >= 0) {
             float acc[kMelBatch];
-            if (PACKED) mel_dot_batch_p(bufP, s_w + s_band[2 * kMaxMels + m], kEllStride, s_band[m], s_band[kMaxMels + m], acc);
-            else mel_dot_batch(bufP, s_w + s_band[2 * kMaxMels + m], kEllStride, s_band[m], s_band[kMaxMels + m], acc);
+            mel_dot_batch_p(bufP, s_w + s_band[2 * kMaxMels + m], kEllStride, s_band[m], s_band[kMaxMels + m], acc);
 #pragma unroll
             for (int f = 0; f < kMelBatch; ++f)
               if (f <= slot) s_tile[m * kTileStride + fl0 + f] = norm_db(acc[f], p.log_eps, mel_scale[i], mel_shift[i]);
@@ -396,10 +373,6 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   plan->device = device;
   plan->nnz = static_cast<int>(weights.size());
   plan->d_window = nullptr; plan->d_tw1024 = nullptr; plan->d_band = nullptr; plan->d_weights = nullptr;
-  {  // experimental packed-f32x2 phases: opt-in per plan, never the default
-    const char* v = getenv("AFS_LOGMEL_PACKED");
-    plan->packed = (v != nullptr && (v[0] == '1' || v[0] == '2')) ? v[0] - '0' : 0;  // 2: + pointer-bump prefetch
-  }
 
   int prev = 0;
   cudaError_t e = cudaGetDevice(&prev);
@@ -413,14 +386,10 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   if (e == cudaSuccess) e = cudaMemcpy(plan->d_band, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(plan->d_weights, weights.data(), weights.size() * sizeof(float), cudaMemcpyHostToDevice);
   const int smem = static_cast<int>(kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (plan->packed && e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (plan->packed && e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, int16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (plan->packed && e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (plan->packed && e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, int16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaSetDevice(prev);
   if (e != cudaSuccess) {
     afs_logmel_plan_destroy(plan);
@@ -473,7 +442,6 @@ int logmel_launch(const afs_logmel_plan* plan, const S* wav, float pcm_scale, in
   p.gain_lo = p.gain_hi = p.noise_lo = p.noise_hi = 0.f; p.max_shift = 0;
   p.seed_lo = static_cast<uint32_t>(seed); p.seed_hi = static_cast<uint32_t>(seed >> 32);
   p.first_clip = first_clip_index;
-  p.lean = plan->packed == 2 ? 1 : 0;
   const int64_t items = static_cast<int64_t>(B) * p.chunks;
   if (items > 0x7fffffffLL) return AFS_ERR_UNSUPPORTED;
   // persistent: 2 resident CTAs per SM (128 registers x 256 threads, 100 KB of shared memory each) walk the items
@@ -484,11 +452,9 @@ int logmel_launch(const afs_logmel_plan* plan, const S* wav, float pcm_scale, in
     p.gain_lo = aug->gain_db_lo; p.gain_hi = aug->gain_db_hi;
     p.noise_lo = aug->noise_std_lo; p.noise_hi = aug->noise_std_hi;
     p.max_shift = aug->max_shift;
-    if (plan->packed) logmel_kernel<true, S, true><<<g, kThreads, kSmemBytes, stream>>>(p);
-    else logmel_kernel<true, S, false><<<g, kThreads, kSmemBytes, stream>>>(p);
+    logmel_kernel<true, S><<<g, kThreads, kSmemBytes, stream>>>(p);
   } else {
-    if (plan->packed) logmel_kernel<false, S, true><<<g, kThreads, kSmemBytes, stream>>>(p);
-    else logmel_kernel<false, S, false><<<g, kThreads, kSmemBytes, stream>>>(p);
+    logmel_kernel<false, S><<<g, kThreads, kSmemBytes, stream>>>(p);
   }
   AFS_LAUNCH_CHECK();
   return AFS_OK;

@@ -1,25 +1,21 @@
-// Packed-f32x2 formulation of the log-mel kernel's FFT phases (EXPERIMENTAL, opt-in: AFS_LOGMEL_PACKED=1 at plan
-// creation, =2 adds the pointer-bump frame prefetch of logmel.cu; the default kernel uses the scalar phases of
-// logmel_core.cuh).
+// FFT phases of the fused log-mel kernel (logmel.cu) on packed-f32x2 arithmetic.
 //
-// Why: after the conflict-free mel reads the kernel is instruction-issue bound (profiles/r01_logmel_v5_ncu.csv:
-// 66 % of the issue slots at 4 warps per scheduler, 695 warp-instructions per warp-frame, 339 of them FP).  sm_100a
-// has FADD2 / FMUL2 / FFMA2 on aligned register pairs, with operand modifiers for a half swap (.LO_HI), a one-lane
-// negation (.NP) and a scalar broadcast (Rn.F32) -- so with a complex number held as the pair (re, im):
+// sm_100a has FADD2 / FMUL2 / FFMA2 on aligned register pairs, with operand modifiers for a half swap (.LO_HI), a
+// one-lane negation (.NP) and a scalar broadcast (Rn.F32) -- so with a complex number held as the pair (re, im):
 //   complex add / sub            = 1 instruction (2 scalar)
 //   multiplication by -i         = free (swap + one-lane negate fold into the consumer)
 //   complex multiplication       = 2 instructions (FMUL2 + FFMA2; 4 scalar)
 //   radix-8 butterfly            = 27 instructions (54 scalar)      [static counts: tools/probe_packed_fft.cu]
 // and every shared-memory exchange moves (re, im) as one 64-bit word: half the LDS/STS instructions for the same
-// wavefronts.  Static SASS count of the four phases: 276 instructions per thread-frame against 485.
+// wavefronts.  Measured on B200 against the scalar phases this file replaced in round 2: 0.936 -> 0.798 ms per
+// 3 200 clips (profiles/r02_logmel_variants.txt), same tolerance against the float64 spec.
 //
 // Layouts (float2 units; a 64-bit access is served per half-warp, 16 lanes x 8 B = one 128 B wavefront when the 16
 // words fall into 16 different 8-byte banks -- checked for every access pattern by tests/emul):
 //   exchange 1: element (q, j) at q * 66 + j             (66 == 2 mod 16: the read side q + 8 j0 is conflict-free)
 //   exchange 2: element (q, j0, p0) at q + 8 ((j0 ^ p0) & 1) + 16 (j0 + 8 (p0 >> 1))     (dense bijection on [0, 512))
 //   exchange 3: Z[k] at k (natural order)
-// Same index derivation, buffers and barriers as logmel_core.cuh; status: numerics and bank model verified on the
-// CPU emulator, SASS verified statically, NOT yet run on a GPU (round 1 ran out of GPU budget).
+// Index derivation: logmel_core.cuh.
 #pragma once
 #include "logmel_core.cuh"
 
@@ -62,7 +58,7 @@ AFS_HD float2 c_mul(float2 a, float2 b) {
   return p_fma(make_float2(a.x, a.x), b, make_float2(-t.y, t.x));
 }
 
-// In-place forward 8-point DFT, natural order out (the packed twin of dft8).
+// In-place forward 8-point DFT, natural order out: a[q] = sum_r a[r] W_8^{rq}.
 AFS_HD void dft8_p(float2 (&a)[8]) {
   const float h = 0.70710678118654752440f;
   const float2 hh = make_float2(h, h);

@@ -85,9 +85,7 @@ typedef struct afs_logmel_plan afs_logmel_plan; /* opaque; owns device tables */
  * plan packs each filter's contiguous non-zero band and uploads it together
  * with the window and the FFT twiddles.  device: CUDA device ordinal.
  * AFS_ERR_UNSUPPORTED when the packed table exceeds the kernel's 16 KB budget (very wide filters: fewer than
- * about 30 slaney mels at n_fft 1024).
- * Environment: AFS_LOGMEL_PACKED=1, read here, selects the experimental packed-f32x2 FFT phases for this plan
- * (csrc/logmel_packed.cuh), =2 additionally the pointer-bump frame prefetch; unset, the default kernel runs. */
+ * about 30 slaney mels at n_fft 1024). */
 int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb_host,
                            const float* window_host, int device, afs_logmel_plan** plan_out);
 int afs_logmel_plan_destroy(afs_logmel_plan* plan);

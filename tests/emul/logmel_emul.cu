@@ -1,7 +1,7 @@
 // CPU emulation of the fused log-mel kernel's per-thread phases (host logic test).
 //
 // Runs the SAME __host__ __device__ phase functions the kernel runs
-// (audio_fewshot_b200/csrc/logmel_core.cuh) with the 64 threads of a frame group
+// (audio_fewshot_b200/csrc/logmel_core.cuh, logmel_fft.cuh) with the 64 threads of a frame group
 // looped sequentially per phase (the loop boundary plays the role of bar.sync).
 // Built by tests/test_logmel_emul.py with `nvcc -x cu` (host code only is used).
 #include <math.h>
@@ -10,11 +10,11 @@
 #include <vector>
 
 #include "logmel_core.cuh"
-#include "logmel_packed.cuh"
+#include "logmel_fft.cuh"
 
 using namespace afs::logmel;
 
-static int emul_logmel_impl(bool packed, const float* wav, int64_t L, int hop, int center, const float* fb,
+static int emul_logmel_impl(const float* wav, int64_t L, int hop, int center, const float* fb,
                             const float* window, int n_mels, const float* mean, const float* stdv,
                             float log_mult, float log_eps, float* out /*[n_mels, T]*/,
                             float* power_out /*[T, 513] nullable*/) {
@@ -35,35 +35,22 @@ static int emul_logmel_impl(bool packed, const float* wav, int64_t L, int hop, i
     const int64_t s0 = static_cast<int64_t>(f) * hop - pad;
     const bool interior = s0 >= 0 && s0 + kNfft <= L;
     for (int t = 0; t < kGroup; ++t) {
-      cpx z[8];
+      float2 zp[8];
       for (int r = 0; r < 8; ++r) {
         const int n = t + 64 * r;
         int64_t i0 = s0 + 2 * n, i1 = i0 + 1;
         if (!interior) { i0 = reflect_index(i0, L); i1 = reflect_index(i1, L); }
-        z[r].re = wav[i0] * window[2 * n];
-        z[r].im = wav[i1] * window[2 * n + 1];
+        zp[r] = make_float2(wav[i0] * window[2 * n], wav[i1] * window[2 * n + 1]);
       }
-      if (packed) {
-        float2 zp[8];
-        for (int r = 0; r < 8; ++r) zp[r] = make_float2(z[r].re, z[r].im);
-        phase_a_p(t, zp, tws[t], reinterpret_cast<float2*>(bufA.data()));
-      } else {
-        phase_a(t, z, tws[t], bufA.data());
-      }
+      phase_a_p(t, zp, tws[t], reinterpret_cast<float2*>(bufA.data()));
     }
     const int slot = f % kMelBatch;
     float* power = bufP.data() + slot * kPStride;
-    if (packed) {
-      float2* a2 = reinterpret_cast<float2*>(bufA.data());
-      float2* b2 = reinterpret_cast<float2*>(bufB.data());
-      for (int t = 0; t < kGroup; ++t) phase_b_p(t, tws[t], a2, b2);
-      for (int t = 0; t < kGroup; ++t) phase_c_p(t, b2, a2);
-      for (int t = 0; t < kGroup; ++t) phase_d_p(t, tws[t], a2, power);
-    } else {
-      for (int t = 0; t < kGroup; ++t) phase_b(t, tws[t], bufA.data(), bufB.data());
-      for (int t = 0; t < kGroup; ++t) phase_c(t, bufB.data(), bufA.data());
-      for (int t = 0; t < kGroup; ++t) phase_d(t, tws[t], bufA.data(), power);
-    }
+    float2* a2 = reinterpret_cast<float2*>(bufA.data());
+    float2* b2 = reinterpret_cast<float2*>(bufB.data());
+    for (int t = 0; t < kGroup; ++t) phase_b_p(t, tws[t], a2, b2);
+    for (int t = 0; t < kGroup; ++t) phase_c_p(t, b2, a2);
+    for (int t = 0; t < kGroup; ++t) phase_d_p(t, tws[t], a2, power);
     if (power_out) for (int k = 0; k < kBins; ++k) power_out[static_cast<size_t>(f) * kBins + k] = power[k];
     if (slot != kMelBatch - 1 && f + 1 != T) continue;
     for (int t = 0; t < kGroup; ++t) {  // batched mel projection, as the kernel's epilogue
@@ -74,8 +61,7 @@ static int emul_logmel_impl(bool packed, const float* wav, int64_t L, int hop, i
         const int m = mel_id[i];
         if (m < 0) continue;
         float acc[kMelBatch];
-        if (packed) mel_dot_batch_p(bufP.data(), weights.data() + band[2 * kMaxMels + m], kEllStride, band[m], band[kMaxMels + m], acc);
-        else mel_dot_batch(bufP.data(), weights.data() + band[2 * kMaxMels + m], kEllStride, band[m], band[kMaxMels + m], acc);
+        mel_dot_batch_p(bufP.data(), weights.data() + band[2 * kMaxMels + m], kEllStride, band[m], band[kMaxMels + m], acc);
         const float scale = log_mult * 0.30102999566398120f / stdv[m];
         const float shift = -mean[m] / stdv[m];
         for (int b = 0; b <= slot; ++b)
@@ -89,17 +75,10 @@ static int emul_logmel_impl(bool packed, const float* wav, int64_t L, int hop, i
 extern "C" int emul_logmel(const float* wav, int64_t L, int hop, int center, const float* fb,
                            const float* window, int n_mels, const float* mean, const float* stdv,
                            float log_mult, float log_eps, float* out, float* power_out) {
-  return emul_logmel_impl(false, wav, L, hop, center, fb, window, n_mels, mean, stdv, log_mult, log_eps, out, power_out);
+  return emul_logmel_impl(wav, L, hop, center, fb, window, n_mels, mean, stdv, log_mult, log_eps, out, power_out);
 }
 
-// the same frames through the packed-f32x2 phases of logmel_packed.cuh (host fallbacks of the packed intrinsics)
-extern "C" int emul_logmel_packed(const float* wav, int64_t L, int hop, int center, const float* fb,
-                                  const float* window, int n_mels, const float* mean, const float* stdv,
-                                  float log_mult, float log_eps, float* out, float* power_out) {
-  return emul_logmel_impl(true, wav, L, hop, center, fb, window, n_mels, mean, stdv, log_mult, log_eps, out, power_out);
-}
-
-// Packed layouts: worst number of distinct 64-bit words that one half-warp (16 consecutive threads) puts on one of
+// Exchange layouts: worst number of distinct 64-bit words that one half-warp (16 consecutive threads) puts on one of
 // the 16 eight-byte banks, over every shared-memory access pattern of the packed phases (1 = conflict-free), and
 // whether the exchange-2 slot function is a bijection onto [0, 512).  Returns the worst count, or -1.
 extern "C" int emul_packed_bank_check() {
@@ -137,9 +116,6 @@ extern "C" int emul_packed_bank_check() {
   }
   return worst;
 }
-
-// slot bijection check for the exchange-2 swizzle
-extern "C" int emul_e2_slot(int q, int j0, int p0) { return e2_slot(q, j0, p0); }
 
 // The kernel's ELL weight table (pack_mel_ell) expanded back to a dense [513, n_mels] matrix, plus, per warp-pass,
 // the number of table rows: lets the test check that the table reproduces the filterbank exactly, that every

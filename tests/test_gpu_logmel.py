@@ -148,28 +148,3 @@ def test_logmel_rejects_bad_input(cuda):
         fr(torch.zeros(1, 4000))  # CPU tensor: no fallback
     with pytest.raises(TypeError):
         fr(torch.zeros(1, 4000, device=cuda, dtype=torch.float16))  # fp32 or int16 PCM only
-
-
-@pytest.mark.skipif(os.environ.get("AFS_TEST_EXPERIMENTAL") != "1",
-                    reason="packed-f32x2 log-mel phases are opt-in until they have been run on a GPU "
-                           "(AFS_TEST_EXPERIMENTAL=1 enables this test; csrc/logmel_packed.cuh)")
-@pytest.mark.parametrize("level", ["1", "2"])  # 1: packed FFT phases; 2: + pointer-bump frame prefetch
-@pytest.mark.parametrize("B,L,hop,n_mels", [(3, 80000, 512, 128), (2, 16000, 102, 128), (1, 4099, 511, 128),
-                                            (2, 12345, 160, 80), (5, 33 * 512, 512, 128)])
-def test_logmel_packed_variant_matches_spec_and_default(cuda, monkeypatch, B, L, hop, n_mels, level):
-    """AFS_LOGMEL_PACKED=1|2 at plan creation selects the kernel with complex numbers as (re, im) register pairs
-    (FADD2 / FMUL2 / FFMA2, 64-bit exchanges): same tolerance against the float64 spec, rounding-level
-    agreement with the default kernel, and the int16 PCM entry point bit-identical to the converted fp32 waveform."""
-    rng = np.random.default_rng(L * 7 + hop)
-    x = (rng.standard_normal((B, L)) * 0.1).astype(np.float32)
-    base = make_frontend(cuda, hop, n_mels)
-    want_dev = base(torch.from_numpy(x).to(cuda))
-    monkeypatch.setenv("AFS_LOGMEL_PACKED", level)
-    packed = make_frontend(cuda, hop, n_mels)
-    got_dev = packed(torch.from_numpy(x).to(cuda))  # the plan is created here, under the switch
-    monkeypatch.delenv("AFS_LOGMEL_PACKED")
-    got = got_dev.cpu().numpy()
-    assert_db_close(got, fe.logmel_f64(x, hop=hop, n_mels=n_mels, mean=MEAN, std=STD))
-    assert np.abs(got - want_dev.cpu().numpy()).max() * STD < 1e-4  # dB; both kernels are within 1e-4 of the spec
-    pcm = torch.from_numpy((x * 32768.0).clip(-32768, 32767).astype(np.int16)).to(cuda)
-    assert torch.equal(packed(pcm), packed(pcm.float() * (1.0 / 32768.0)))
