@@ -18,6 +18,7 @@ classes are looked up BY NAME in one namespace -- here `audio_fewshot_b200.model
 """
 import os
 import random
+import re
 
 import yaml
 
@@ -29,9 +30,28 @@ DEFAULTS = {  # keys the callers read unconditionally; the reference takes them 
 }
 
 
+class _Loader(yaml.SafeLoader):
+    """SafeLoader whose float resolver also accepts `1e-2` (PyYAML's YAML-1.1 rule demands a dot, so the reference's
+    `inner_param.lr: 1e-2` in config/classifiers/MAML.yaml would load as a string).  Same regular expression as
+    upstream LibFewShot's config loader."""
+
+
+_Loader.add_implicit_resolver(
+    "tag:yaml.org,2002:float",
+    re.compile(r"""^(?:
+     [-+]?(?:[0-9][0-9_]*)\.[0-9_]*(?:[eE][-+]?[0-9]+)?
+    |[-+]?(?:[0-9][0-9_]*)(?:[eE][-+]?[0-9]+)
+    |\.[0-9_]+(?:[eE][-+][0-9]+)?
+    |[-+]?[0-9][0-9_]*(?::[0-5]?[0-9])+\.[0-9_]*
+    |[-+]?\.(?:inf|Inf|INF)
+    |\.(?:nan|NaN|NAN))$""", re.X),
+    list("-+0123456789."),
+)
+
+
 def _load_yaml(path):
     with open(path, "r", encoding="utf-8") as fin:
-        return yaml.safe_load(fin.read()) or {}
+        return yaml.load(fin.read(), Loader=_Loader) or {}
 
 
 def find_config_root(config_file):

@@ -28,17 +28,8 @@
 #include "common.cuh"
 #include "logmel_core.cuh"
 #include "logmel_fft.cuh"
+#include "logmel_plan.cuh"
 #include "philox.cuh"
-
-struct afs_logmel_plan {
-  afs_logmel_cfg cfg;
-  int device;
-  int nnz;
-  float* d_window;   // [1024]
-  float2* d_tw1024;  // [1024]
-  int* d_band;       // [3][128]: lo, len, off
-  float* d_weights;  // [nnz]
-};
 
 namespace afs {
 namespace {
@@ -57,88 +48,8 @@ constexpr size_t kSmemFloats = kMaxNnz + 3 * kMaxMels + kGroups * kGroupFloats +
                                kMaxMels * kTileStride;
 constexpr size_t kSmemBytes = kSmemFloats * sizeof(float);
 
-struct Params {
-  const void* wav;     // [B, L] fp32, or int16 PCM when launched with T = int16_t
-  float pcm_scale;     // int16 PCM only: sample = (float)pcm * pcm_scale (1/32768 for full-scale [-1, 1))
-  float* out;
-  const float* mean;
-  const float* stdv;
-  const float* window;
-  const float2* tw1024;
-  const int* band;
-  const float* weights;
-  int64_t L;
-  int nnz, B, T, hop, n_mels, pad, chunks;
-  float log_mult, log_eps;
-  // augmentation
-  float gain_lo, gain_hi, noise_lo, noise_hi;
-  int max_shift;
-  uint32_t seed_lo, seed_hi;
-  uint64_t first_clip;
-};
-
-struct AugState {
-  float g, sigma, pcm_scale;
-  int k;
-  uint32_t c_lo, c_hi, seed_lo, seed_hi;
-};
-
 __device__ __forceinline__ void group_bar(int grp) {
   asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
-}
-
-// Sample fetch: fp32 waveforms as they are, int16 PCM converted on the fly (exact in fp32 for a
-// power-of-two scale), so 16-bit audio crosses PCIe and HBM at half the bytes.
-__device__ __forceinline__ float ld_sample(const float* p, float) { return __ldg(p); }
-__device__ __forceinline__ float ld_sample(const int16_t* p, float s) {
-  return __fmul_rn(static_cast<float>(__ldg(p)), s);
-}
-__device__ __forceinline__ float2 ld_pair(const float* p, float) { return __ldg(reinterpret_cast<const float2*>(p)); }
-__device__ __forceinline__ float2 ld_pair(const int16_t* p, float s) {
-  const short2 v = __ldg(reinterpret_cast<const short2*>(p));
-  return make_float2(__fmul_rn(static_cast<float>(v.x), s), __fmul_rn(static_cast<float>(v.y), s));
-}
-
-// One augmented sample y[idx] = g * x[idx - k] + sigma * n[idx]; n[2i], n[2i+1]
-// are the (cos, sin) Box-Muller pair of the first two words of
-// Philox(counter = (i, 1, clip_lo, clip_hi), key = seed).
-template <typename S>
-__device__ __forceinline__ float aug_sample(const S* __restrict__ x, int64_t idx, int64_t L,
-                                            const AugState& a) {
-  const int64_t src = idx - a.k;
-  float v = (src >= 0 && src < L) ? __fmul_rn(a.g, ld_sample(x + src, a.pcm_scale)) : 0.f;
-  if (a.sigma > 0.f) {
-    u32x4 c;
-    c.x = static_cast<uint32_t>(idx >> 1); c.y = kStreamNoise; c.z = a.c_lo; c.w = a.c_hi;
-    const u32x4 r = philox4x32_10(c, a.seed_lo, a.seed_hi);
-    const float rad = sqrtf(-2.0f * logf(u01(r.x)));
-    float sn, cs;
-    sincospif(2.0f * u01(r.y), &sn, &cs);
-    const float z = (idx & 1) ? rad * sn : rad * cs;
-    v = __fadd_rn(v, __fmul_rn(a.sigma, z));
-  }
-  return v;
-}
-
-// Both samples of an aligned pair (idx even, idx + 1): they share one Philox block and one Box-Muller draw
-// (cos for the even sample, sin for the odd one), so the pair costs one RNG evaluation instead of two.
-template <typename S>
-__device__ __forceinline__ float2 aug_pair(const S* __restrict__ x, int64_t idx, int64_t L, const AugState& a) {
-  const int64_t s0 = idx - a.k, s1 = s0 + 1;
-  float2 v;
-  v.x = (s0 >= 0 && s0 < L) ? __fmul_rn(a.g, ld_sample(x + s0, a.pcm_scale)) : 0.f;
-  v.y = (s1 >= 0 && s1 < L) ? __fmul_rn(a.g, ld_sample(x + s1, a.pcm_scale)) : 0.f;
-  if (a.sigma > 0.f) {
-    u32x4 c;
-    c.x = static_cast<uint32_t>(idx >> 1); c.y = kStreamNoise; c.z = a.c_lo; c.w = a.c_hi;
-    const u32x4 r = philox4x32_10(c, a.seed_lo, a.seed_hi);
-    const float rad = sqrtf(-2.0f * logf(u01(r.x)));
-    float sn, cs;
-    sincospif(2.0f * u01(r.y), &sn, &cs);
-    v.x = __fadd_rn(v.x, __fmul_rn(a.sigma, rad * cs));
-    v.y = __fadd_rn(v.y, __fmul_rn(a.sigma, rad * sn));
-  }
-  return v;
 }
 
 // Raw (augmented, reflect-padded, NOT yet windowed) samples 2n, 2n+1 for n = t + 64 r of the frame that
@@ -231,23 +142,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
 
     AugState aug;
     aug.pcm_scale = p.pcm_scale;
-    if (AUG) {
-      const uint64_t cg = p.first_clip + static_cast<uint64_t>(clip);
-      aug.c_lo = static_cast<uint32_t>(cg);
-      aug.c_hi = static_cast<uint32_t>(cg >> 32);
-      aug.seed_lo = p.seed_lo;
-      aug.seed_hi = p.seed_hi;
-      u32x4 c;
-      c.x = 0u; c.y = kStreamParams; c.z = aug.c_lo; c.w = aug.c_hi;
-      const u32x4 r = philox4x32_10(c, p.seed_lo, p.seed_hi);
-      const float gain_db = __fadd_rn(p.gain_lo, __fmul_rn(__fsub_rn(p.gain_hi, p.gain_lo), u01(r.x)));
-      aug.g = exp10f(__fmul_rn(gain_db, 0.05f));
-      const int span = 2 * p.max_shift + 1;
-      int draw = static_cast<int>(floorf(__fmul_rn(u01(r.y), static_cast<float>(span))));
-      if (draw > span - 1) draw = span - 1;
-      aug.k = draw - p.max_shift;
-      aug.sigma = __fadd_rn(p.noise_lo, __fmul_rn(__fsub_rn(p.noise_hi, p.noise_lo), u01(r.z)));
-    }
+    if (AUG) init_clip_aug(aug, p, clip);
 
     const int t0 = chunk * kFramesPerCta;
     const int nfr = min(kFramesPerCta, p.T - t0);
@@ -336,12 +231,6 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const Params p) {
   }
 }
 
-int num_frames(const afs_logmel_cfg& cfg, int64_t L) {
-  if (cfg.center) return static_cast<int>(1 + L / cfg.hop);
-  if (L < cfg.n_fft) return 0;
-  return static_cast<int>(1 + (L - cfg.n_fft) / cfg.hop);
-}
-
 }  // namespace
 }  // namespace afs
 
@@ -373,6 +262,8 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   plan->device = device;
   plan->nnz = static_cast<int>(weights.size());
   plan->d_window = nullptr; plan->d_tw1024 = nullptr; plan->d_band = nullptr; plan->d_weights = nullptr;
+  plan->d_tc = nullptr;
+  plan->engine = AFS_LOGMEL_ENGINE_FFT;
 
   int prev = 0;
   cudaError_t e = cudaGetDevice(&prev);
@@ -390,6 +281,7 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess && logmel::tc_tables_create(plan, window_host) != AFS_OK) e = cudaErrorMemoryAllocation;
   cudaSetDevice(prev);
   if (e != cudaSuccess) {
     afs_logmel_plan_destroy(plan);
@@ -405,7 +297,15 @@ extern "C" int afs_logmel_plan_destroy(afs_logmel_plan* plan) {
   cudaFree(plan->d_tw1024);
   cudaFree(plan->d_band);
   cudaFree(plan->d_weights);
+  afs::logmel::tc_tables_destroy(plan);
   delete plan;
+  return AFS_OK;
+}
+
+extern "C" int afs_logmel_plan_set_engine(afs_logmel_plan* plan, int32_t engine) {
+  if (plan == nullptr || (engine != AFS_LOGMEL_ENGINE_FFT && engine != AFS_LOGMEL_ENGINE_TC)) return AFS_ERR_INVALID_ARG;
+  if (engine == AFS_LOGMEL_ENGINE_TC && plan->d_tc == nullptr) return AFS_ERR_UNSUPPORTED;
+  plan->engine = engine;
   return AFS_OK;
 }
 
@@ -452,6 +352,9 @@ int logmel_launch(const afs_logmel_plan* plan, const S* wav, float pcm_scale, in
     p.gain_lo = aug->gain_db_lo; p.gain_hi = aug->gain_db_hi;
     p.noise_lo = aug->noise_std_lo; p.noise_hi = aug->noise_std_hi;
     p.max_shift = aug->max_shift;
+  }
+  if (plan->engine == AFS_LOGMEL_ENGINE_TC) return logmel::tc_launch<S>(plan, p, aug != nullptr, stream);
+  if (aug != nullptr) {
     logmel_kernel<true, S><<<g, kThreads, kSmemBytes, stream>>>(p);
   } else {
     logmel_kernel<false, S><<<g, kThreads, kSmemBytes, stream>>>(p);

@@ -156,6 +156,7 @@ AFS_HD void phase_d_p(int u, const ThreadTw& tw, const float2* bufA, float* powe
 
 // mel_dot_batch with the four frames as two register pairs: one FFMA2 per pair and weight (the weight is a scalar
 // broadcast operand, the two power values are the destinations of two LDS); same products and sums as the scalar loop.
+template <int PS = kPStride>
 AFS_HD void mel_dot_batch_p(const float* power, const float* weights, int wstride, int lo, int len,
                             float (&acc)[kMelBatch]) {
   static_assert(kMelBatch == 4, "two pairs of frames");
@@ -164,8 +165,8 @@ AFS_HD void mel_dot_batch_p(const float* power, const float* weights, int wstrid
   for (int i = 0; i < len; ++i) {
     const float w = weights[i * wstride];
     const float2 ww = make_float2(w, w);
-    a01 = p_fma(ww, make_float2(p0[i], p0[kPStride + i]), a01);
-    a23 = p_fma(ww, make_float2(p0[2 * kPStride + i], p0[3 * kPStride + i]), a23);
+    a01 = p_fma(ww, make_float2(p0[i], p0[PS + i]), a01);
+    a23 = p_fma(ww, make_float2(p0[2 * PS + i], p0[3 * PS + i]), a23);
   }
   acc[0] = a01.x; acc[1] = a01.y; acc[2] = a23.x; acc[3] = a23.y;
 }

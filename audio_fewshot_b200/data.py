@@ -36,12 +36,20 @@ N_MELS, N_FRAMES = 128, 157
 
 class EpisodeSampler:
     """Global episode-batch indices of this rank for one epoch: batch b covers episodes
-    [b*episode_size, (b+1)*episode_size); ranks take batches round-robin."""
+    [b*episode_size, (b+1)*episode_size); ranks take batches round-robin.  `episode_size` is per rank (the global
+    batch is world_size * episode_size) and every rank iterates the same number of batches."""
 
     def __init__(self, n_episodes, episode_size, rank=0, world_size=1, seed=0):
         if n_episodes % episode_size:
             raise ValueError("episodes %d %% episode_size %d != 0 (trainer.py:724-754)" % (n_episodes, episode_size))
         self.n_batches = n_episodes // episode_size
+        if world_size > 1 and self.n_batches % world_size:
+            # every step ends in collectives (accuracy all-reduce, gradient all-reduce): ranks with different batch
+            # counts would deadlock on the last one.  The reference gets equal counts by splitting episode_size over
+            # the GPUs (trainer.py:724-754 asserts episode_size % n_gpu == 0); here episode_size is PER RANK and the
+            # global batch is world_size * episode_size, so the batch count must divide.
+            raise ValueError("%d episode batches do not divide over %d ranks: choose episodes as a multiple of "
+                             "episode_size * world_size (= %d)" % (self.n_batches, world_size, episode_size * world_size))
         self.episode_size, self.rank, self.world_size, self.seed = episode_size, rank, world_size, seed
         self.epoch = 0
 

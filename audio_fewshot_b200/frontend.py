@@ -60,8 +60,9 @@ class LogMelFrontEnd(nn.Module):
 
     def __init__(self, sample_rate=16000, n_fft=1024, hop_length=512, n_mels=128, f_min=0.0, f_max=None,
                  mean=0.0, std=1.0, mean_std_file=None, center=True, log_mult=10.0, log_eps=LOG_EPS, aug=None,
-                 seed=0, pcm_scale=1.0 / 32768.0):
+                 seed=0, pcm_scale=1.0 / 32768.0, engine=None):
         super().__init__()
+        self.engine = engine
         if mean_std_file is not None:
             mean, std = load_mean_std(mean_std_file)
         self.sample_rate, self.n_fft, self.hop_length, self.n_mels = sample_rate, n_fft, hop_length, n_mels
@@ -76,7 +77,7 @@ class LogMelFrontEnd(nn.Module):
     def plan(self):
         if self._plan is None:
             self._plan = ops.LogMelPlan(self._fb, self._window, self.hop_length, self.n_mels, self.center,
-                                        self.log_mult, self.log_eps, device=self.mean.device)
+                                        self.log_mult, self.log_eps, device=self.mean.device, engine=self.engine)
         return self._plan
 
     def forward(self, wav, first_clip_index=0, out=None):

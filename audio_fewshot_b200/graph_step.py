@@ -18,7 +18,14 @@ the host inside step() (torch.optim.Adam/AdamW need capturable=True; SGD is fine
 device tensor (model.acc_on_device is switched on), `output` / `loss` are the graph's static tensors -- copy them
 if they must outlive the next call.  With torch.distributed initialised, pass reduce_gradients=True to capture the
 flat NCCL gradient all-reduce (dist.all_reduce_gradients) between backward and step.
+
+Construction runs `warmup` eager steps and the capture itself on an all-zero batch (cuDNN heuristics, episode tables,
+lazily created optimizer state).  Those steps would move parameters, BatchNorm running statistics and optimizer
+moments; the model's and the optimizer's state are therefore snapshotted before and restored IN PLACE after them
+(the graph keeps pointing at the same tensors), so the first replay starts from exactly the caller's state.
 """
+import copy
+
 import torch
 
 from . import dist as afs_dist
@@ -40,6 +47,10 @@ class GraphedTrainStep:
         self.reduce_gradients = reduce_gradients
         model.acc_on_device = True
 
+        model_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        optim_state = copy.deepcopy(optimizer.state_dict())
+        had_state = {id(p) for p in optimizer.state}
+
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):  # eager warm-up: cuDNN heuristics, episode tables, optimizer state
@@ -52,6 +63,33 @@ class GraphedTrainStep:
         optimizer.zero_grad(set_to_none=True)  # backward inside the capture then WRITES fresh static .grad tensors
         with torch.cuda.graph(self.graph):
             self.output, self.acc, self.loss = self._eager_step()
+        self._restore(model_state, optim_state, had_state)
+
+    def _restore(self, model_state, optim_state, had_state):
+        """Undo the warm-up / capture steps in place (graph-captured tensors keep their addresses)."""
+        with torch.no_grad():
+            for k, v in self.model.state_dict().items():
+                v.copy_(model_state[k])
+            # optimizer state: tensors are copied into the live (captured) ones; entries that did not exist before
+            # the warm-up (lazily created moments, step counters) are reset to zero, their initial value
+            saved = optim_state["state"]
+            index = {}
+            i = 0
+            for group in self.optimizer.param_groups:
+                for prm in group["params"]:
+                    index[id(prm)] = i
+                    i += 1
+            for prm, st in self.optimizer.state.items():
+                old = saved.get(index[id(prm)]) if id(prm) in had_state else None
+                for name, val in st.items():
+                    if torch.is_tensor(val):
+                        if old is not None and torch.is_tensor(old.get(name)):
+                            val.copy_(old[name])
+                        else:
+                            val.zero_()
+                    elif old is not None and name in old:
+                        st[name] = old[name]
+        torch.cuda.synchronize(torch.device(self.model.device))
 
     def _eager_step(self):
         self.optimizer.zero_grad(set_to_none=True)

@@ -34,6 +34,10 @@ def _need_cuda(t, name, dtype=torch.float32):
         raise _lib.AfsError("%s must be a CUDA tensor (no CPU fallback exists)" % name)
     if t.dtype != dtype:
         raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the CURRENT device's current stream; a tensor of another GPU would fault in the kernel
+        raise _lib.AfsError("%s lives on %s but the current CUDA device is cuda:%d; wrap the call in "
+                            "`with torch.cuda.device(%r):`" % (name, t.device, torch.cuda.current_device(), str(t.device)))
     return t
 
 
@@ -41,11 +45,15 @@ def _need_cuda(t, name, dtype=torch.float32):
 class LogMelPlan:
     """Owns an afs_logmel_plan (device tables: window, twiddles, packed mel bands)."""
 
+    ENGINES = {"fft": 0, "tc": 1}
+
     def __init__(self, fb, window, hop, n_mels, center=True, log_mult=10.0, log_eps=2.220446049250313e-16,
-                 device=None):
+                 device=None, engine=None):
         if device is None:
             device = torch.cuda.current_device()
         device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        if device.index is None:  # "cuda" without an ordinal means the current device, not GPU 0
+            device = torch.device("cuda", torch.cuda.current_device())
         self.device = device
         fb = np.ascontiguousarray(np.asarray(fb, dtype=np.float32))
         window = np.ascontiguousarray(np.asarray(window, dtype=np.float32))
@@ -57,8 +65,16 @@ class LogMelPlan:
         self._handle = C.c_void_p(0)
         h = _lib.lib()
         _lib.check(h.afs_logmel_plan_create(C.byref(self.cfg), fb.ctypes.data_as(C.c_void_p),
-                                            window.ctypes.data_as(C.c_void_p), device.index or 0,
+                                            window.ctypes.data_as(C.c_void_p), device.index,
                                             C.byref(self._handle)), "afs_logmel_plan_create")
+        self.engine = "fft"
+        if engine is not None:
+            self.set_engine(engine)
+
+    def set_engine(self, engine):
+        """"fft": radix-8 FFT on the FMA pipe; "tc": four-step DFT on the tcgen05 tensor cores."""
+        _lib.check(_lib.lib().afs_logmel_plan_set_engine(self._handle, self.ENGINES[engine]), "afs_logmel_plan_set_engine")
+        self.engine = engine
 
     def num_frames(self, L):
         return int(_lib.lib().afs_logmel_num_frames(self._handle, int(L)))
@@ -72,6 +88,8 @@ class LogMelPlan:
         _need_cuda(std, "std")
         if wav.dim() != 2:
             raise ValueError("wav must be [B, L]")
+        if wav.device != self.device:
+            raise _lib.AfsError("wav lives on %s but the plan's tables are on %s" % (wav.device, self.device))
         if mean.numel() != self.n_mels or std.numel() != self.n_mels:
             raise ValueError("mean/std must have n_mels entries")
         wav = wav.contiguous()

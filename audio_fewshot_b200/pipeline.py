@@ -7,7 +7,11 @@ One call = H2D of the waveforms (when they arrive on the host) -> fused log-mel 
 emb_func (cuDNN) -> head kernel -> vote/accuracy kernel.  Nothing synchronises with the host;
 `acc` is a 0-dim CUDA tensor.  With `use_graph=True` the device work of a fixed batch shape is
 captured once into a CUDA graph (the per-episode launch sequence is short and launch-bound for
-small batches) and replayed from a static input buffer.
+small batches) and replayed from a static input buffer.  The graph bakes in everything the launches take by value:
+the cache key therefore covers the batch shape, the episode layout, `first_clip_index`, the front-end's seed and
+augmentation switch and the version counters of every model parameter and buffer (a reloaded state_dict or an
+optimizer step re-captures).  A graphed call returns the graph's STATIC output tensors -- the next replay overwrites
+them; clone what must outlive it.
 
     for output_host, acc_host in pipe.stream(batches, repeats, support_size): ...
 
@@ -34,13 +38,21 @@ class EpisodePipeline:
         target = None
         return self.model.set_forward([image, target, repeats, support_size])
 
+    def _state_key(self):
+        """Everything a captured graph holds by value: front-end switches and the versions of the model's tensors
+        (folded weights travel as kernel parameters, see Conv64F)."""
+        fe = self.frontend
+        versions = tuple(t._version for t in list(self.model.parameters()) + list(self.model.buffers()))
+        return (bool(fe.training), int(getattr(fe, "seed", 0)), bool(self.model.training), hash(versions))
+
     @torch.no_grad()
     def __call__(self, wav, repeats, support_size, first_clip_index=0):
         dev = self.frontend.mean.device
         if not self.use_graph:
             wav_dev = wav.to(dev, non_blocking=True)
             return self._device_forward(wav_dev, repeats, support_size, first_clip_index)
-        key = (tuple(wav.shape), wav.dtype, support_size, None if repeats is None else bytes(repeats.cpu().numpy().tobytes()))
+        key = (tuple(wav.shape), wav.dtype, support_size, None if repeats is None else bytes(repeats.cpu().numpy().tobytes()),
+               int(first_clip_index), self._state_key())
         entry = self._graphs.get(key)
         if entry is None:
             static_in = torch.empty(wav.shape, dtype=wav.dtype, device=dev)
@@ -62,7 +74,7 @@ class EpisodePipeline:
         return out
 
     @torch.no_grad()
-    def stream(self, batches, repeats, support_size, first_clip_index=0, depth=2):
+    def stream(self, batches, repeats, support_size, first_clip_index=0, depth=3):
         """Yield (output, acc) as pinned HOST tensors for every [N, L] pinned host batch of `batches`
         (all of one shape).  Results are yielded `depth` batches late, once their D2H copy has finished."""
         dev = self.frontend.mean.device

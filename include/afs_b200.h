@@ -89,6 +89,17 @@ typedef struct afs_logmel_plan afs_logmel_plan; /* opaque; owns device tables */
 int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb_host,
                            const float* window_host, int device, afs_logmel_plan** plan_out);
 int afs_logmel_plan_destroy(afs_logmel_plan* plan);
+/* Two engines compute the same features (both within the 1e-4 dB tolerance of the float64 spec):
+ *   AFS_LOGMEL_ENGINE_FFT  radix-8 FFT in registers on the FMA pipe (packed-f32x2 arithmetic), csrc/logmel.cu
+ *   AFS_LOGMEL_ENGINE_TC   four-step 32x32 DFT as tcgen05 GEMMs (fp16 hi/lo operand pairs, fp32 accumulators in
+ *                          tensor memory), csrc/logmel_tc.cu
+ * AFS_ERR_UNSUPPORTED when the plan cannot run the requested engine.                                       */
+#define AFS_LOGMEL_ENGINE_FFT 0
+#define AFS_LOGMEL_ENGINE_TC 1
+int afs_logmel_plan_set_engine(afs_logmel_plan* plan, int32_t engine);
+/* Development hook: when device_buffer is non-null the TC engine dumps the step-1 accumulators [256][32] and the
+ * power spectra [8][528] of its first chunk there (>= 12 416 floats); pass NULL to switch it off.           */
+int afs_logmel_tc_debug_buffer(float* device_buffer);
 /* number of output frames for clips of L samples */
 int afs_logmel_num_frames(const afs_logmel_plan* plan, int64_t L);
 

@@ -53,10 +53,13 @@ def test_reference_baseline_configs_build(reference, name, cls, backbone):
 def test_sampler_shards_by_global_index_and_loader_layout():
     from audio_fewshot_b200.data import EpisodeSampler, SyntheticSpectrogramEpisodes
     full = EpisodeSampler(12, 2, 0, 1, seed=3)
-    parts = [EpisodeSampler(12, 2, r, 4, seed=3) for r in range(4)]
+    parts = [EpisodeSampler(12, 2, r, 3, seed=3) for r in range(3)]
     assert sorted(sum([list(p) for p in parts], [])) == list(full) == list(range(6))
+    assert len({len(p) for p in parts}) == 1  # every rank iterates the same number of batches (collectives per step)
     with pytest.raises(ValueError):
         EpisodeSampler(7, 2)
+    with pytest.raises(ValueError):  # 6 batches over 4 ranks: the last step's collectives would deadlock
+        EpisodeSampler(12, 2, 0, 4)
     one = SyntheticSpectrogramEpisodes(full, 5, 2, 3, max_windows=3)
     shard = SyntheticSpectrogramEpisodes(parts[1], 5, 2, 3, max_windows=3)
     batches = {b: one.batch(b) for b in full}
@@ -146,3 +149,17 @@ def test_wav_folder_loader_serves_pcm16_windows(tmp_path):
         w8.setnchannels(1); w8.setsampwidth(1); w8.setframerate(16000); w8.writeframes(b"\x00" * 10)
     with pytest.raises(ValueError):
         read_wav_pcm16(str(tmp_path / "bad.wav"))
+
+
+def test_yaml_scientific_notation_floats(tmp_path):
+    """PyYAML's YAML-1.1 resolver reads `1e-2` as a string; the reference writes learning rates that way
+    (config/classifiers/MAML.yaml inner_param.lr).  The loader must hand floats to the optimisers."""
+    from audio_fewshot_b200 import config
+    f = tmp_path / "c.yaml"
+    f.write_text("lr: 1e-2\nwd: 5.0e-4\nn: 12\nname: 1e\nquoted: '1e-2'\n")
+    d = config._load_yaml(str(f))
+    assert d == {"lr": 0.01, "wd": 5.0e-4, "n": 12, "name": "1e", "quoted": "1e-2"}
+    ref = "/root/reference/config/classifiers/MAML.yaml"
+    if os.path.exists(ref):
+        lr = config._load_yaml(ref)["classifier"]["kwargs"]["inner_param"]["lr"]
+        assert isinstance(lr, float) and lr == 0.01
