@@ -129,7 +129,7 @@ inline int num_frames(const afs_logmel_cfg& cfg, int64_t L) {
 }
 
 // logmel_tc.cu
-int tc_tables_create(afs_logmel_plan* plan, const float* window_host);  // sets plan->d_tc (or leaves it null)
+int tc_tables_create(afs_logmel_plan* plan, const float* fb_host);  // sets plan->d_tc (or leaves it null)
 void tc_tables_destroy(afs_logmel_plan* plan);
 template <typename S>
 int tc_launch(const afs_logmel_plan* plan, const Params& p, bool aug, cudaStream_t stream);

@@ -97,9 +97,6 @@ int afs_logmel_plan_destroy(afs_logmel_plan* plan);
 #define AFS_LOGMEL_ENGINE_FFT 0
 #define AFS_LOGMEL_ENGINE_TC 1
 int afs_logmel_plan_set_engine(afs_logmel_plan* plan, int32_t engine);
-/* Development hook: when device_buffer is non-null the TC engine dumps the step-1 accumulators [256][32] and the
- * power spectra [8][528] of its first chunk there (>= 12 416 floats); pass NULL to switch it off.           */
-int afs_logmel_tc_debug_buffer(float* device_buffer);
 /* number of output frames for clips of L samples */
 int afs_logmel_num_frames(const afs_logmel_plan* plan, int64_t L);
 

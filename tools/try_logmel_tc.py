@@ -1,7 +1,5 @@
-"""Bring-up check of the tensor-core log-mel engine (csrc/logmel_tc.cu) on a B200: intermediate dumps of the first
-chunk against numpy (step-1 accumulators, power spectra), final features against the float64 spec and the FFT
+"""Bring-up check of the tensor-core log-mel engine (csrc/logmel_tc.cu) on a B200: final features against the float64 spec and the FFT
 engine, and the two engines' times.   python tools/try_logmel_tc.py [--quick]"""
-import ctypes as C
 import os
 import sys
 
@@ -9,7 +7,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from audio_fewshot_b200 import _lib
 from audio_fewshot_b200.frontend import LogMelFrontEnd
 from oracle import frontend as fe
 
@@ -23,12 +20,8 @@ def check(B, L, hop, n_mels=128, dump=False, seed=0):
     tc = LogMelFrontEnd(hop_length=hop, n_mels=n_mels, mean=MEAN, std=STD, engine="tc").to(dev).eval()
     fft = LogMelFrontEnd(hop_length=hop, n_mels=n_mels, mean=MEAN, std=STD, engine="fft").to(dev).eval()
     xd = torch.from_numpy(x).to(dev)
-    dbg = torch.zeros(256 * 32 + 8 * 528, device=dev)
-    if dump:
-        _lib.lib().afs_logmel_tc_debug_buffer(C.c_void_p(dbg.data_ptr()))
     got = tc(xd)
     torch.cuda.synchronize()
-    _lib.lib().afs_logmel_tc_debug_buffer(C.c_void_p(0))
     ref = fe.logmel_f64(x, hop=hop, n_mels=n_mels, mean=MEAN, std=STD)
     g = got.cpu().numpy()
     err = np.abs(g - ref) * STD  # de-normalised dB
@@ -37,33 +30,6 @@ def check(B, L, hop, n_mels=128, dump=False, seed=0):
     err_fft = np.abs(base - ref) * STD
     print("B=%d L=%d hop=%d mels=%d: tc max dB err %.3e (worst err/tol %.3f, nan %d), fft engine %.3e" %
           (B, L, hop, n_mels, err.max(), (err / tol).max(), int(np.isnan(g).sum()), err_fft.max()))
-    if dump:
-        d = dbg.cpu().numpy()
-        fr = fe.frames(x[:1].astype(np.float64), hop)[0][:8] * fe.hann_periodic().astype(np.float64)  # [8, 1024]
-        mx = np.abs(fr.astype(np.float32)).max()
-        es = 13 - int(np.floor(np.log2(mx)))
-        xs = fr * 2.0 ** es
-        n2 = np.arange(32)
-        Y = np.zeros((8, 32, 32))
-        xm = xs.reshape(8, 32, 32)  # [f, n2, n1]
-        for c in range(32):
-            if c == 0:
-                w = np.ones(32)
-            elif c == 1:
-                w = (-1.0) ** n2
-            else:
-                a = 2 * np.pi * n2 * (c >> 1) / 32
-                w = -np.sin(a) if c & 1 else np.cos(a)
-            Y[:, :, c] = np.einsum("fkn,k->fn", xm, w)
-        got_y = d[:8192].reshape(8, 32, 32)
-        print("  step-1 accumulators: max err / max|Y| = %.3e" % (np.abs(got_y - Y).max() / np.abs(Y).max()))
-        P = np.abs(np.fft.rfft(fr, axis=-1)) ** 2  # [8, 513]
-        got_p = d[8192:].reshape(8, 528)[:, :513]
-        rel = np.abs(got_p - P).max(axis=0) / P.max()
-        print("  power: max err / max P = %.3e; worst bins %s" % (rel.max(), np.argsort(rel)[-6:]))
-        bad = np.where(rel > 1e-4)[0]
-        if bad.size:
-            print("  bins off by > 1e-4: %d; k mod 32 histogram %s" % (bad.size, np.bincount(bad % 32, minlength=32)))
     return err.max()
 
 
