@@ -101,31 +101,10 @@ def backbone_input():
     return (_rng(61).standard_normal((2, 1, 128, 157)) * 0.5).astype(np.float32)
 
 
-def perturb_bn_(net):
-    """Overwrite EVERY parameter and buffer with values derived from its name and shape, so that a
-    reference module and a product module with the same state_dict layout get identical weights
-    (and non-trivial BatchNorm statistics) without shipping a checkpoint."""
-    import torch
-
-    sd = net.state_dict()
-    for key in sorted(sd.keys()):
-        t = sd[key]
-        if key.endswith("num_batches_tracked"):
-            continue
-        r = _rng(zlib.crc32(key.encode()))
-        shape = tuple(t.shape)
-        if key.endswith("running_var") or (key.endswith("weight") and t.dim() == 1):
-            v = r.uniform(0.5, 1.5, size=shape)
-        elif key.endswith("running_mean") or key.endswith("bias"):
-            v = r.standard_normal(shape) * 0.1
-        elif key.endswith("temperature"):
-            v = np.full(shape, np.log(1.0 / 200.0))
-        else:
-            fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else 1
-            v = r.standard_normal(shape) * np.sqrt(2.0 / max(fan_in, 1))
-        with torch.no_grad():
-            t.copy_(torch.from_numpy(np.asarray(v, dtype=np.float32)))
-    return net
+# the weight recipe and the waveform generator live in the product package (bench.py and smoke() must not depend on
+# test infrastructure); the parity cases use the same functions under their historical names
+from audio_fewshot_b200.synthetic import name_seeded_weights_ as perturb_bn_  # noqa: E402,F401
+from audio_fewshot_b200.synthetic import synthetic_clip_batch  # noqa: E402,F401
 
 
 # ------------------------------------------------------------------ spectrogram-domain augmentations
@@ -161,18 +140,3 @@ MAML_GRAD_KEYS = ("emb_func.layer1.0.weight", "emb_func.layer3.1.bias", "emb_fun
 def maml_images(c=MAML_CASE):
     n = c["E"] * c["W"] * (c["S"] + c["Q"])
     return (_rng(c["seed"]).standard_normal((n, 1, 128, 157)) * 0.5).astype(np.float32)
-
-
-# ------------------------------------------------------------------ synthetic waveforms (SURVEY.md 8d)
-def synthetic_clip_batch(seed, first_episode, n_episodes, W, S, Q, L, sample_rate=16000):
-    """[E*W*(S+Q), L] fp32, class-major rows: N(0,1)*0.1 noise + a class-dependent tone
-    0.05*sin(2 pi f_c t), f_c = 200*(c+1) Hz.  Content depends only on the global episode index."""
-    t = np.arange(L, dtype=np.float64) / sample_rate
-    out = np.empty((n_episodes, W, S + Q, L), dtype=np.float32)
-    for e in range(n_episodes):
-        r = _rng((seed, first_episode + e))
-        noise = r.standard_normal((W, S + Q, L)).astype(np.float32) * np.float32(0.1)
-        for c in range(W):
-            tone = (0.05 * np.sin(2.0 * np.pi * 200.0 * (c + 1) * t)).astype(np.float32)
-            out[e, c] = noise[c] + tone[None, :]
-    return out.reshape(n_episodes * W * (S + Q), L)

@@ -153,7 +153,7 @@ def test_bench_reference_arm_line_and_no_cuda_refusal():
     import json
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=300)
+                          "--warmup", "0", "--episodes-per-step", "2"], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-500:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -164,6 +164,7 @@ def test_bench_reference_arm_line_and_no_cuda_refusal():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["config"]["episodes_per_step_per_gpu"] == 2  # the CPU arm runs the B200 arm's step, not one episode
     # under torchrun only rank 0 runs the reference arm; the other ranks exit 0 without work or output
     other = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                             "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300,
