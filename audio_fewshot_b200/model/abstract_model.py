@@ -84,3 +84,26 @@ class AbstractModel(nn.Module):
 class MetricModel(AbstractModel):
     def __init__(self, init_type="normal", **kwargs):
         super().__init__(init_type, ModelType.METRIC, **kwargs)
+
+
+class FinetuningModel(AbstractModel):
+    """The third model family of the boundary (libfewshot_core/model/finetuning/finetuning_model.py:10-31): a
+    backbone pre-trained with a plain classifier, adapted per episode at test time.  The contract is three
+    methods -- `set_forward` (episodic evaluation), `set_forward_loss` (pre-training step on a flat batch) and
+    `set_forward_adaptation` (the per-episode fine-tuning loop) -- and `sub_optimizer`, which builds the optimiser of
+    that loop from a `{"name": ..., "kwargs": ...}` config block exactly as the reference does.  Concrete fine-tuning
+    classifiers are outside SURVEY 8's scope; the class exists so that user code written against the reference's
+    base class binds here unchanged."""
+
+    def __init__(self, init_type="normal", **kwargs):
+        super().__init__(init_type, ModelType.FINETUNING, **kwargs)
+
+    def set_forward_adaptation(self, *args, **kwargs):
+        raise NotImplementedError
+
+    def sub_optimizer(self, model, config):  # finetuning_model.py:26-31
+        kwargs = dict()
+        if config["kwargs"] is not None:
+            kwargs.update(config["kwargs"])
+        return getattr(torch.optim, config["name"])(model.parameters(), **kwargs)
+

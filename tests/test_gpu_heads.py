@@ -385,3 +385,19 @@ def test_utils_module_mirrors_reference_helpers(cuda, golden):
     assert a2 >= a1
     m, h = U.mean_confidence_interval([80.0, 82.0, 78.0, 85.0])
     assert abs(m - 81.25) < 1e-9 and h > 0
+
+
+@pytest.mark.parametrize("C,H,Wd,E", [(64, 4, 5, 24), (640, 8, 9, 4)])
+def test_dn4_tensor_core_head_repeats_bit_identically(cuda, C, H, Wd, E):
+    """dn4_tc2 (TMA + tcgen05 + TMEM double buffering, the K-streaming ring for C = 640): scores, top-k indices and
+    predictions of repeated launches are bit-identical -- the stand-in for racecheck on the GPU pool."""
+    from audio_fewshot_b200 import ops
+    rng = np.random.default_rng(C + E)
+    W, S, Q, n_k = 5, 5, 6, 3
+    n = E * W * (S + Q)
+    feat = torch.from_numpy(np.abs(rng.standard_normal((n, C, H, Wd))).astype(np.float32)).to(cuda)
+    tab = ragged_table(E, W, S, Q, np.ones(E * W * Q, dtype=np.int64), cuda)
+    s0, i0, p0 = ops.dn4_scores(feat, tab.cls_row, E, W, S, n_k, want_topk=True, want_pred=True, precision="tf32")
+    for _ in range(4):
+        s, i, p = ops.dn4_scores(feat, tab.cls_row, E, W, S, n_k, want_topk=True, want_pred=True, precision="tf32")
+        assert torch.equal(s, s0) and torch.equal(i, i0) and torch.equal(p, p0)

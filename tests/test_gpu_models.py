@@ -682,3 +682,26 @@ def test_energy_gated_tta_step(cuda, tmp_path, monkeypatch):
         acc2, _ = tta.energy_tta_step(m, [x, None, repeats, E * W * S], num_augmentations=2, mean=-15.0, std=26.0)
         assert 0.0 <= float(acc2) <= 100.0
     assert (tmp_path / "test_uncertainty.npy").exists()
+
+
+def test_tcgen05_kernels_repeat_bit_identically(cuda):
+    """Stand-in for a race detector (compute-sanitizer is not available on the GPU pool): every hand-rolled
+    mbarrier / TMEM pipeline must produce bit-identical outputs over repeated launches on a large batch -- a missing
+    fence or a barrier phase error shows up as run-to-run differences long before it shows up as a wrong mean."""
+    from audio_fewshot_b200 import ops
+    rng = np.random.default_rng(99)
+    # stem: conv1_tc (three TMEM accumulators per window row, double-buffered im2col)
+    x = torch.from_numpy(rng.standard_normal((200, 1, 128, 157)).astype(np.float32)).to(cuda)
+    w1 = rng.standard_normal((64, 9)).astype(np.float32) * 0.3
+    b1 = rng.standard_normal(64).astype(np.float32)
+    first = ops.conv1_bn_act_pool3(x, w1, b1, 0.0, tf32=True)
+    for _ in range(4):
+        assert torch.equal(ops.conv1_bn_act_pool3(x, w1, b1, 0.0, tf32=True), first)
+    # blocks 2-3: conv3_tc (producer / three MMA warps / epilogue warps over a 4-stage ring)
+    a = first.contiguous(memory_format=torch.channels_last)
+    w3 = torch.from_numpy((rng.standard_normal((64, 64, 3, 3)) * 0.06).astype(np.float32)).to(cuda)
+    b3 = torch.from_numpy(rng.standard_normal(64).astype(np.float32)).to(cuda)
+    packed = torch.from_numpy(ops.conv3x3_c64_pack_weights(w3)).to(cuda)
+    ref3 = ops.conv3x3_c64_bn_act(a, packed, b3, 0.0, pool=True)
+    for _ in range(4):
+        assert torch.equal(ops.conv3x3_c64_bn_act(a, packed, b3, 0.0, pool=True), ref3)

@@ -60,6 +60,39 @@ def test_model_contract_on_cpu():
         m([torch.zeros(55, 1, 128, 157), torch.zeros(55), torch.ones(50, dtype=torch.long), 5])
 
 
+def test_finetuning_model_contract():
+    """FinetuningModel (finetuning_model.py:10-31): model_type, the three abstract methods, sub_optimizer from a
+    {"name", "kwargs"} block -- checked against the reference class when it is importable."""
+    from audio_fewshot_b200 import model as arch
+
+    class Probe(arch.FinetuningModel):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            self.classifier = torch.nn.Linear(4, 2)
+
+        def set_forward(self, batch):
+            return "eval"
+
+        def set_forward_loss(self, batch):
+            return "train"
+
+    m = Probe(way_num=5, shot_num=1, query_num=15, test_way=5, test_shot=1, test_query=15, device="cpu")
+    assert m.model_type == arch.ModelType.FINETUNING and m.way_num == 5 and m.init_type == "normal"
+    assert m.train()([0]) == "train" and m.eval()([0]) == "eval"
+    with pytest.raises(NotImplementedError):
+        m.set_forward_adaptation()
+    opt = m.sub_optimizer(m.classifier, {"name": "SGD", "kwargs": {"lr": 0.01, "momentum": 0.9}})
+    assert isinstance(opt, torch.optim.SGD) and opt.param_groups[0]["momentum"] == 0.9
+    assert isinstance(m.sub_optimizer(m.classifier, {"name": "Adam", "kwargs": None}), torch.optim.Adam)
+    from oracle import ref_import
+    if ref_import.reference_available():
+        ref = ref_import.import_reference()
+        import importlib
+        ref_cls = importlib.import_module("libfewshot_core.model.finetuning.finetuning_model").FinetuningModel
+        want = {n for n in vars(ref_cls) if not n.startswith("_")}
+        assert want <= {n for n in dir(arch.FinetuningModel)}, want
+
+
 def test_sharding_is_a_partition():
     from audio_fewshot_b200.dist import shard_episodes
     for n, ws in [(10, 1), (10, 4), (1250, 8), (3, 8)]:

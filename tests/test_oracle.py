@@ -1,9 +1,12 @@
 """Pins the CPU oracle: against the committed goldens (generated from the REAL reference by
 oracle/make_golden.py) and, in the authoring container, against the reference classes directly."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
+from conftest import GOLDEN
 from oracle import backbones as obb
 from oracle import cases, frontend as fe, heads
 
@@ -182,3 +185,20 @@ def test_torch_mode_cuda_rule_matches_measured_golden(golden):
         assert heads.torch_mode_cuda(y) == int(m)
         differs_from_cpu_rule += int(torch.mode(torch.from_numpy(y))[0].item() != int(m))
     assert differs_from_cpu_rule > 100  # the two rules really are different
+
+
+@pytest.mark.parametrize("case", ["s5", "s1", "odd"])
+def test_frontend_spec_matches_the_torchaudio_golden(case):
+    """Pins oracle/frontend.py to the committed torchaudio outputs (tests/golden/logmel_torchaudio.npz, written by
+    oracle/make_frontend_golden.py): with torchaudio's own fp32 filterbank and window the float64 spec reproduces
+    torchaudio's dB values to 1e-5 -- the only external anchor the waveform stage can have."""
+    from oracle.make_frontend_golden import CASES, waveform
+    g = np.load(os.path.join(GOLDEN, "logmel_torchaudio.npz"), allow_pickle=False)
+    c = CASES[case]
+    x = waveform(c)
+    got = fe.logmel_f64(x, hop=c["hop"], n_mels=c["n_mels"], fb=g[case + "_fb"], window=g[case + "_window"])[:, 0]
+    assert got.shape == g[case + "_db"].shape
+    assert np.abs(got - g[case + "_db"]).max() < 1e-5
+    # and the repo's own tables (float64 design, rounded once) are torchaudio's up to its fp32 construction
+    assert np.abs(fe.mel_filterbank(n_mels=c["n_mels"]) - g[case + "_fb"]).max() < 1e-6
+    assert np.abs(fe.hann_periodic() - g[case + "_window"]).max() < 3e-7  # torch.hann_window evaluates the cosine in fp32
