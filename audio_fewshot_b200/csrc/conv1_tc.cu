@@ -6,15 +6,28 @@
 // pooled pixel: 0.37 ms per 800 clips, 69 % of the fp32 FMA peak).  The reference runs its convolutions in
 // TF32 by default (torch.backends.cudnn.allow_tf32 = True), and under that setting this kernel is used.
 //
-// Formulation: a tile is 128 POOLED pixels = 128 accumulator rows = 128 TMEM lanes = 128 threads.  For each of
-// the 9 positions d of the pooling window one GEMM  D_d[128 x 64] = P_d[128 x 16] . Wf^T[16 x 64]  (K = 9 taps
-// zero-padded to 16) gives the conv output at that window position for all 64 channels; the max over d is an
-// elementwise max over nine accumulators that all sit in the SAME lane, so the pooling needs no cross-thread
-// traffic at all.  The three windows of one window row share a shared-memory buffer and 192 TMEM columns; the
-// im2col rows P_d are written by the thread that owns the pooled pixel straight from its 5x5 register patch
-// (K-major no-swizzle UMMA layout, conflict-free 128-bit stores), double-buffered so that building the next
-// window row overlaps the MMAs of the current one.  Epilogue: tcgen05.ld, running max, + folded shift,
-// activation, 256-byte NHWC row store.
+// Formulation: a tile is 128 POOLED pixels = 128 accumulator rows = 128 TMEM lanes.  For each of the 9 positions d
+// of the pooling window one GEMM  D_d[128 x 64] = P_d[128 x 16] . Wf^T[16 x 64]  (K = 9 taps zero-padded to 16)
+// gives the conv output at that window position for all 64 channels; the max over d is an elementwise max over
+// nine accumulators that all sit in the SAME lane, so the pooling needs no cross-thread traffic at all.
+//
+// One persistent CTA per SM, 13 warps in three roles chained by mbarriers (round 2; the round-1 kernel ran build ->
+// MMA -> TMEM read as phases of one 128-thread CTA and spent 5 800 clk per tile where the 18 MMAs need 900):
+//   BUILD warps 0-3   thread = pooled pixel: 5x5 input patch (prefetched one tile ahead), TF32 rounding, the nine
+//                     im2col rows of the tile (K-major no-swizzle UMMA layout, conflict-free 128-bit stores) into one
+//                     of two 72 KB operand buffers
+//   EPI   warps 4-11  thread = (pooled pixel, 32-channel half): tcgen05.ld, running max over the nine windows,
+//                     + folded shift, activation, warp transpose through a padded staging tile so that every store
+//                     instruction writes whole 128-byte half-rows of the NHWC output (a thread storing its own 32
+//                     channels touched 32 different lines per instruction)
+//   MMA   warp 12     one thread: per window row 3 x 2 tcgen05.mma M128 N64 K8 (TF32) into one of two 192-column
+//                     accumulator sets; tcgen05.commit hands accumulators to the epilogue and operand buffers back
+//                     to BUILD
+// Measured on B200, 3 200 clips (profiles/r02_conv1_tc_variants.txt): round-1 kernel 1.08 ms; this structure with
+// per-thread stores 0.95 ms, with the staged stores 0.77 ms.  At that point the shared-memory / L1 data path is ~70 %
+// busy (im2col stores 55 KB + operand reads 108 KB + staging 64 KB per tile) and BUILD and EPI are busy 88 % / 78 % of
+// the time at ~0.2 IPC per warp.  Tried and slower: 16 EPI warps of 16 channels (0.91-1.07 ms, with and without a
+// setmaxnreg register split), two BUILD groups (1.00 ms at 96 registers per thread).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -25,180 +38,205 @@ namespace {
 
 using namespace tc;
 
-constexpr int kPix1 = 128;                 // pooled pixels per tile == threads
+constexpr int kPix1 = 128;                 // pooled pixels per tile
 constexpr int kCh1 = 64;                   // output channels == UMMA N
+constexpr int kThreads1 = 32 * 13;         // 4 BUILD + 8 EPI + 1 MMA warps
+constexpr int kMmaWarp1 = 12;
 constexpr uint32_t kWinBytes = 4u * kPix1 * 16u;      // one window's P_d: [4 chunks][128 rows][16 B] = 8 KB
-constexpr uint32_t kBufBytes = 3u * kWinBytes;        // one window row: 24 KB
+constexpr uint32_t kTileBytes = 9u * kWinBytes;       // nine windows: 72 KB
 constexpr uint32_t kWBytes = 4u * kCh1 * 16u;         // Wf: [4 chunks][64 rows][16 B] = 4 KB
+constexpr uint32_t kAccCols = 3u * kCh1;              // one window row: three accumulators
+constexpr int kStagePitch = 36;                       // floats per staged pixel row (32 channels + 4: conflict-free)
+constexpr uint32_t kStageBytes = 32u * kStagePitch * 4u;  // per EPI warp
+constexpr uint32_t kTmemCols1 = 512;
 
 struct Conv1TcParams {
   float w[kCh1 * 9];  // folded weights [c][ky][kx]
   float shift[kCh1];
 };
 
-__global__ void __launch_bounds__(kPix1)
+enum { kAFull = 0, kAEmpty = 2, kAccFull = 4, kAccEmpty = 6, kBars1 = 8 };
+
+template <bool LEAKY>
+__global__ void __launch_bounds__(kThreads1, 1)
 conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, int PH, int PW, float slope,
                 float* __restrict__ out, const __grid_constant__ Conv1TcParams prm) {
-  extern __shared__ __align__(128) uint8_t s_buf[];  // [2][kBufBytes] im2col | [kWBytes] weights
-  __shared__ __align__(8) uint64_t s_bar;
+  extern __shared__ __align__(128) uint8_t s_buf[];  // [2][kTileBytes] im2col | [kWBytes] weights | [8][kStageBytes] output staging
+  __shared__ __align__(8) uint64_t s_bars[kBars1];
   __shared__ uint32_t s_tmem;
+  __shared__ float s_shift[kCh1];
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = tid >> 5, lane = tid & 31;
   const uint32_t a_base = smem_u32(s_buf);
-  const uint32_t w_base = a_base + 2u * kBufBytes;
+  const uint32_t w_base = a_base + 2u * kTileBytes;
+  if (tid < kCh1) s_shift[tid] = prm.shift[tid];
+  const uint32_t bars = smem_u32(s_bars);
+#define BAR1(id) (bars + 8u * static_cast<uint32_t>(id))
 
-  constexpr uint32_t kTmemCols1 = 256;  // 3 accumulators x 64 columns, power of two
   // folded weights -> K-major operand [chunk][channel][4 taps], TF32-rounded; taps 9..15 are zero
-  for (int i = tid; i < 4 * kCh1; i += kPix1) {
+  for (int i = tid; i < 4 * kCh1; i += kThreads1) {
     const int chunk = i / kCh1, c = i - chunk * kCh1;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (chunk == 0) v = make_float4(to_tf32(prm.w[c * 9 + 0]), to_tf32(prm.w[c * 9 + 1]), to_tf32(prm.w[c * 9 + 2]), to_tf32(prm.w[c * 9 + 3]));
     if (chunk == 1) v = make_float4(to_tf32(prm.w[c * 9 + 4]), to_tf32(prm.w[c * 9 + 5]), to_tf32(prm.w[c * 9 + 6]), to_tf32(prm.w[c * 9 + 7]));
     if (chunk == 2) v.x = to_tf32(prm.w[c * 9 + 8]);
-    reinterpret_cast<float4*>(s_buf + 2u * kBufBytes)[i] = v;
+    reinterpret_cast<float4*>(s_buf + 2u * kTileBytes)[i] = v;
   }
-  // the all-zero fourth chunk of every window tile never changes
-  for (int i = tid; i < 2 * 3 * kPix1; i += kPix1) {
+  // the all-zero fourth chunk of every window never changes
+  for (int i = tid; i < 2 * 9 * kPix1; i += kThreads1) {
     const int win = i / kPix1, r = i - win * kPix1;
     reinterpret_cast<float4*>(s_buf + win * kWinBytes)[3 * kPix1 + r] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (warp == 0) tmem_alloc(&s_tmem, kTmemCols1);
-  if (tid == 0) {
-    mbar_init(smem_u32(&s_bar), 1);
+  if (tid == 32) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR1(kAFull + s), kPix1);
+      mbar_init(BAR1(kAEmpty + s), 1);
+      mbar_init(BAR1(kAccFull + s), 1);
+      mbar_init(BAR1(kAccEmpty + s), 256);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  fence_async_smem();
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = s_tmem;
-  const uint32_t bar = smem_u32(&s_bar);
-  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  constexpr uint32_t kIdesc = idesc_tf32(kPix1, kCh1);
 
   const int64_t n_tiles = (total_pix + kPix1 - 1) / kPix1;
   const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t n_steps = 3 * my_tiles;
 
-  float p[5][5];   // this thread's input patch (tile being built)
-  float pn[5][5];  // patch of the NEXT tile, loaded two steps ahead so its global latency is off the critical path
-  float best[kCh1];
-
-  auto load_patch = [&](int64_t tile_iter) {
-    const int64_t tile = blockIdx.x + tile_iter * gridDim.x;
-    int64_t pix = tile * kPix1 + tid;
-    if (pix >= total_pix) pix = total_pix - 1;  // tail rows recompute the last pixel; never stored
-    const int per = PH * PW;
-    const int64_t n = pix / per;
-    const int r = static_cast<int>(pix - n * per);
-    const int ph = r / PW, pw = r - ph * PW;
-    const float* img = x + n * static_cast<int64_t>(H) * Wd;
-    const int y0 = 3 * ph - 1, x0 = 3 * pw - 1;
+  if (warp < 4) {
+    // =========================================================== BUILD
+    float pn[5][5];  // patch of the NEXT tile: its global latency hides behind the current tile's stores
+    const uint32_t per = static_cast<uint32_t>(PH * PW);
+    auto load_patch = [&](int64_t it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      int64_t pix = tile * kPix1 + tid;
+      if (pix >= total_pix) pix = total_pix - 1;  // tail rows recompute the last pixel; never stored
+      const int64_t n = pix / per;
+      const uint32_t r = static_cast<uint32_t>(pix - n * per);
+      const uint32_t ph = r / static_cast<uint32_t>(PW), pw = r - ph * static_cast<uint32_t>(PW);
+      const int y0 = 3 * static_cast<int>(ph) - 1, x0 = 3 * static_cast<int>(pw) - 1;
+      // validity of the five rows / columns as bit masks: only the first and the last can fall outside (H, Wd >= 3)
+      const uint32_t ym = (y0 >= 0 ? 1u : 0u) | 14u | (y0 + 4 < H ? 16u : 0u);
+      const uint32_t xm = (x0 >= 0 ? 1u : 0u) | 14u | (x0 + 4 < Wd ? 16u : 0u);
+      const float* rowp = x + (n * H + y0) * static_cast<int64_t>(Wd) + x0;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const int yy = y0 + i;
-      const bool yin = (yy >= 0) && (yy < H);
+      for (int i = 0; i < 5; ++i) {
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const int xx = x0 + j;
-        pn[i][j] = (yin && xx >= 0 && xx < Wd) ? __ldg(img + static_cast<int64_t>(yy) * Wd + xx) : 0.f;
+        for (int j = 0; j < 5; ++j) pn[i][j] = ((ym >> i) & (xm >> j) & 1u) ? __ldg(rowp + j) : 0.f;
+        rowp += Wd;
       }
-    }
-  };
-
-  // writes the three im2col rows of window row g (positions (g,0..2)) of this thread's pooled pixel
-  auto build = [&](int64_t step) {
-    const int g = static_cast<int>(step % 3);
-    if (g == 0) {  // the patch was requested two steps ago (or in the prologue)
+    };
+    if (my_tiles > 0) load_patch(0);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const uint32_t st = static_cast<uint32_t>(it & 1), par = static_cast<uint32_t>((it >> 1) & 1);
+      float p[5][5];
 #pragma unroll
       for (int i = 0; i < 5; ++i)
 #pragma unroll
         for (int j = 0; j < 5; ++j) p[i][j] = to_tf32(pn[i][j]);
-    }
-    if (g == 1 && step / 3 + 1 < my_tiles) load_patch(step / 3 + 1);
-    float4* dst = reinterpret_cast<float4*>(s_buf + (step & 1) * kBufBytes) + tid;
+      if (it + 1 < my_tiles) load_patch(it + 1);  // in flight while this tile is written
+      mbar_wait_warp_sleep(BAR1(kAEmpty + st), par ^ 1u, lane);  // the 18 MMAs that read this buffer have completed
+      float4* dst = reinterpret_cast<float4*>(s_buf + st * kTileBytes) + tid;
 #pragma unroll
-    for (int gg = 0; gg < 3; ++gg) {
-      if (gg == g) {  // resolved at compile time inside each unrolled copy: p[] keeps static indices
+      for (int g = 0; g < 3; ++g) {
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          float4* row = dst + dx * (4 * kPix1);
-          row[0 * kPix1] = make_float4(p[gg][dx], p[gg][dx + 1], p[gg][dx + 2], p[gg + 1][dx]);
-          row[1 * kPix1] = make_float4(p[gg + 1][dx + 1], p[gg + 1][dx + 2], p[gg + 2][dx], p[gg + 2][dx + 1]);
-          row[2 * kPix1] = make_float4(p[gg + 2][dx + 2], 0.f, 0.f, 0.f);
+          float4* row = dst + (3 * g + dx) * (4 * kPix1);
+          row[0 * kPix1] = make_float4(p[g][dx], p[g][dx + 1], p[g][dx + 2], p[g + 1][dx]);
+          row[1 * kPix1] = make_float4(p[g + 1][dx + 1], p[g + 1][dx + 2], p[g + 2][dx], p[g + 2][dx + 1]);
+          row[2 * kPix1] = make_float4(p[g + 2][dx + 2], 0.f, 0.f, 0.f);
         }
       }
+      fence_async_smem();
+      mbar_arrive(BAR1(kAFull + st));
     }
-  };
-
-  uint32_t phase = 0;
-  if (n_steps > 0) {
-    load_patch(0);
-    build(0);
+  } else if (warp == kMmaWarp1) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t kIdesc = idesc_tf32(kPix1, kCh1);
+      const uint64_t dA = desc_kmajor_noswizzle(a_base, 16u * kPix1, 128u);
+      const uint64_t dB = desc_kmajor_noswizzle(w_base, 16u * kCh1, 128u);
+      uint32_t r = 0;  // running window-row counter: accumulator set r & 1
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const uint32_t st = static_cast<uint32_t>(it & 1), par = static_cast<uint32_t>((it >> 1) & 1);
+        mbar_wait_sleep(BAR1(kAFull + st), par);
+#pragma unroll
+        for (int g = 0; g < 3; ++g, ++r) {
+          const uint32_t as = r & 1u;
+          mbar_wait_sleep(BAR1(kAccEmpty + as), ((r >> 1) & 1u) ^ 1u);
+          fence_after();
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+            for (int k8 = 0; k8 < 2; ++k8) {
+              const uint64_t da = dA + ((st * kTileBytes + (3u * g + dx) * kWinBytes + k8 * 2u * (16u * kPix1)) >> 4);
+              const uint64_t db = dB + ((k8 * 2u * (16u * kCh1)) >> 4);
+              mma_tf32(tmem_base + as * kAccCols + dx * kCh1, da, db, kIdesc, k8 > 0);
+            }
+          }
+          commit(BAR1(kAccFull + as));
+        }
+        commit(BAR1(kAEmpty + st));
+      }
+    }
+  } else {
+    // =========================================================== EPI: running max over nine windows, store
+    const int e = warp - 4;
+    const int half = e >> 2;  // channels 32 half .. 32 half + 31; TMEM lane quadrant = warp & 3 = e & 3
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 32u * half;
+    float* stage = reinterpret_cast<float*>(s_buf + 2u * kTileBytes + kWBytes + static_cast<uint32_t>(e) * kStageBytes);
+    uint32_t r = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      float best[32];
+#pragma unroll
+      for (int g = 0; g < 3; ++g, ++r) {
+        const uint32_t as = r & 1u;
+        mbar_wait_warp_sleep(BAR1(kAccFull + as), (r >> 1) & 1u, lane);
+        fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld32_nowait(t_row + as * kAccCols + 0 * kCh1, v0);
+        tmem_ld32_nowait(t_row + as * kAccCols + 1 * kCh1, v1);
+        tmem_wait_ld();
+        if (g == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) best[j] = fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) best[j] = fmaxf(fmaxf(best[j], __uint_as_float(v0[j])), __uint_as_float(v1[j]));
+        }
+        tmem_ld32(t_row + as * kAccCols + 2 * kCh1, v0);
+        fence_before();
+        mbar_arrive(BAR1(kAccEmpty + as));  // this thread's part of the accumulator set is in registers
+#pragma unroll
+        for (int j = 0; j < 32; ++j) best[j] = fmaxf(best[j], __uint_as_float(v0[j]));
+      }
+      __syncwarp();  // the previous tile's staging reads are done
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        float q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float v = best[4 * c4 + k] + s_shift[32 * half + 4 * c4 + k];
+          q[k] = LEAKY ? fmaxf(v, v * slope) : fmaxf(v, 0.f);  // 0 <= slope < 1: max(v, slope v) is LeakyReLU
+        }
+        *reinterpret_cast<float4*>(stage + lane * kStagePitch + 4 * c4) = make_float4(q[0], q[1], q[2], q[3]);
+      }
+      __syncwarp();
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t pix0 = tile * kPix1 + (warp & 3) * 32;  // first pixel of this warp's 32
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int q = 4 * i + (lane >> 3), c = lane & 7;  // pixel of the warp, 16-byte chunk of its 128-byte half-row
+        const float4 v = *reinterpret_cast<const float4*>(stage + q * kStagePitch + 4 * c);
+        if (pix0 + q < total_pix) *reinterpret_cast<float4*>(out + (pix0 + q) * kCh1 + 32 * half + 4 * c) = v;
+      }
+    }
   }
-  for (int64_t step = 0; step < n_steps; ++step) {
-    fence_async_smem();   // im2col rows of this step -> visible to the tensor core
-    fence_before();       // the previous step's TMEM reads are ordered before the barrier
-    __syncthreads();
-    if (tid == 0) {
-      fence_after();
-      const uint32_t buf = a_base + static_cast<uint32_t>(step & 1) * kBufBytes;
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-        for (int k8 = 0; k8 < 2; ++k8) {
-          const uint64_t da = desc_kmajor_noswizzle(buf + dx * kWinBytes + k8 * 2u * (16u * kPix1), 16u * kPix1, 128u);
-          const uint64_t db = desc_kmajor_noswizzle(w_base + k8 * 2u * (16u * kCh1), 16u * kCh1, 128u);
-          mma_tf32(tmem_base + dx * kCh1, da, db, kIdesc, k8 > 0);
-        }
-      }
-      commit(bar);
-    }
-    if (step + 1 < n_steps) build(step + 1);  // overlaps the MMAs just issued (other buffer)
-    mbar_wait(bar, phase);
-    phase ^= 1u;
-    fence_after();
-
-    const int g = static_cast<int>(step % 3);
-#pragma unroll
-    for (int half = 0; half < kCh1 / 32; ++half) {  // 32 channels at a time: three windows x 32 columns, loads batched
-      uint32_t v0[32], v1[32];
-      tmem_ld32_nowait(t_row + static_cast<uint32_t>(0 * kCh1 + half * 32), v0);
-      tmem_ld32_nowait(t_row + static_cast<uint32_t>(1 * kCh1 + half * 32), v1);
-      tmem_wait_ld();
-      if (g == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) best[half * 32 + j] = fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          best[half * 32 + j] = fmaxf(best[half * 32 + j], fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
-      }
-      tmem_ld32(t_row + static_cast<uint32_t>(2 * kCh1 + half * 32), v0);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) best[half * 32 + j] = fmaxf(best[half * 32 + j], __uint_as_float(v0[j]));
-    }
-    if (g == 2) {
-      const int64_t tile = blockIdx.x + (step / 3) * gridDim.x;
-      const int64_t pix = tile * kPix1 + tid;
-      if (pix < total_pix) {
-        float4* o = reinterpret_cast<float4*>(out + pix * kCh1);
-#pragma unroll
-        for (int c4 = 0; c4 < kCh1 / 4; ++c4) {
-          float4 r;
-          r.x = best[4 * c4 + 0] + prm.shift[4 * c4 + 0];
-          r.y = best[4 * c4 + 1] + prm.shift[4 * c4 + 1];
-          r.z = best[4 * c4 + 2] + prm.shift[4 * c4 + 2];
-          r.w = best[4 * c4 + 3] + prm.shift[4 * c4 + 3];
-          r.x = r.x > 0.f ? r.x : r.x * slope;
-          r.y = r.y > 0.f ? r.y : r.y * slope;
-          r.z = r.z > 0.f ? r.z : r.z * slope;
-          r.w = r.w > 0.f ? r.w : r.w * slope;
-          o[c4] = r;
-        }
-      }
-    }
-  }
+#undef BAR1
 
   fence_before();
   __syncthreads();
@@ -225,10 +263,16 @@ extern "C" int afs_conv1_bn_act_pool3_fwd_tf32(const float* x, int32_t N, int32_
   for (int i = 0; i < kCh1 * 9; ++i) prm.w[i] = w_folded_host[i];
   for (int i = 0; i < kCh1; ++i) prm.shift[i] = shift_host[i];
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const size_t smem = 2 * kBufBytes + kWBytes;
-  int64_t blocks = n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs;  // persistent: 2 CTAs per SM (256 TMEM columns each)
-  AFS_CUDA_TRY(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  conv1_tc_kernel<<<static_cast<unsigned>(blocks), kPix1, smem, stream>>>(x, total, H, Wd, PH, PW, negative_slope, out, prm);
+  const size_t smem = 2 * kTileBytes + kWBytes + 8 * kStageBytes;
+  int64_t blocks = n_tiles < kNumSMs ? n_tiles : kNumSMs;  // persistent: one CTA per SM
+  if (negative_slope >= 1.f) return AFS_ERR_UNSUPPORTED;  // the activation is max(v, slope v)
+  if (negative_slope > 0.f) {
+    AFS_CUDA_TRY(cudaFuncSetAttribute(conv1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    conv1_tc_kernel<true><<<static_cast<unsigned>(blocks), kThreads1, smem, stream>>>(x, total, H, Wd, PH, PW, negative_slope, out, prm);
+  } else {
+    AFS_CUDA_TRY(cudaFuncSetAttribute(conv1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    conv1_tc_kernel<false><<<static_cast<unsigned>(blocks), kThreads1, smem, stream>>>(x, total, H, Wd, PH, PW, negative_slope, out, prm);
+  }
   AFS_LAUNCH_CHECK();
   return AFS_OK;
 }
