@@ -20,6 +20,8 @@ from bench import bind_to_gpu_cpus
 
 
 def main():
+    real_stdout = os.fdopen(os.dup(1), "w")  # NCCL prints its banner on fd 1: keep the JSON line alone on stdout
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -69,7 +71,8 @@ def main():
             topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
         except Exception:
             pass
-        print(json.dumps({"n_gpus": world, "host_cpus": os.cpu_count(), "results": results, "topo": topo}))
+        real_stdout.write(json.dumps({"n_gpus": world, "host_cpus": os.cpu_count(), "results": results, "topo": topo}) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
