@@ -7,10 +7,14 @@
 //   cosine :  logit = <q, p> / (max(|q|,1e-12) max(|p|,1e-12))
 //   dot    :  logit = <q, p>
 // The reference materialises a [t,wq,w,c] temporary and launches one ATen op
-// per step and per episode; here one CTA per (episode, row split) keeps the
-// episode's prototypes in shared memory and streams every query row from HBM
-// exactly once with 128-bit loads.  HBM-bound: 4*W*(S+Q)*D + 4*WQ*W bytes per
-// episode.
+// per step and per episode.  Here a pre-kernel writes the E*W prototypes once
+// (support rows are read exactly once), and one CTA per (episode, row split)
+// streams every query row from HBM exactly once with 128-bit loads, eight in
+// flight per thread, against a SLICE of the prototypes held in shared memory:
+// wide features (D = 12 800 for flattened ResNet-12 maps) walk the slices in
+// ascending column order with the partial sums kept in registers, so the
+// summation order -- and therefore every logit bit -- is the same whatever the
+// slice size.  HBM-bound: 4*W*(S+Q)*D + 4*WQ*W bytes per episode.
 #include "common.cuh"
 
 namespace afs {
@@ -19,7 +23,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxWay = 32;
-constexpr size_t kSmemProtoLimit = 160 * 1024;
+constexpr int kSliceBytes = 40 * 1024;  // prototype slice in shared memory: W * DS * 4 bytes <= this (5 CTAs per SM)
 
 __global__ void __launch_bounds__(256) proto_mean_kernel(const float* __restrict__ feat,
                                                          int64_t ld,
@@ -42,14 +46,59 @@ __global__ void __launch_bounds__(256) proto_mean_kernel(const float* __restrict
   }
 }
 
-template <int MODE, int WT, int RW, bool SMEM_PROTO>
+// ||p||^-1 of every prototype (cosine mode), one warp per prototype
+__global__ void __launch_bounds__(256) proto_pinv_kernel(const float4* __restrict__ protos, int EW, int D4,
+                                                         float* __restrict__ pinv) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= EW) return;
+  float ss = 0.f;
+  for (int c = lane; c < D4; c += 32) {
+    const float4 p = protos[static_cast<int64_t>(g) * D4 + c];
+    ss = fmaf(p.x, p.x, ss); ss = fmaf(p.y, p.y, ss);
+    ss = fmaf(p.z, p.z, ss); ss = fmaf(p.w, p.w, ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) pinv[g] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+}
+
+template <int MODE, int WT, int RW>
+__device__ __forceinline__ void proto_accumulate(const float4 (&q)[RW], const float4* __restrict__ proto, int DS4, int c,
+                                                 int W, float (&acc)[RW][WT], float (&qq)[RW]) {
+  if (MODE == AFS_PROTO_COSINE) {
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      qq[r] = fmaf(q[r].x, q[r].x, qq[r]); qq[r] = fmaf(q[r].y, q[r].y, qq[r]);
+      qq[r] = fmaf(q[r].z, q[r].z, qq[r]); qq[r] = fmaf(q[r].w, q[r].w, qq[r]);
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < WT; ++w) {
+    if (w < W) {
+      const float4 p = proto[w * DS4 + c];
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        if (MODE == AFS_PROTO_EUCLIDEAN) {
+          const float dx = q[r].x - p.x, dy = q[r].y - p.y;
+          const float dz = q[r].z - p.z, dw = q[r].w - p.w;
+          acc[r][w] = fmaf(dx, dx, acc[r][w]); acc[r][w] = fmaf(dy, dy, acc[r][w]);
+          acc[r][w] = fmaf(dz, dz, acc[r][w]); acc[r][w] = fmaf(dw, dw, acc[r][w]);
+        } else {
+          acc[r][w] = fmaf(q[r].x, p.x, acc[r][w]); acc[r][w] = fmaf(q[r].y, p.y, acc[r][w]);
+          acc[r][w] = fmaf(q[r].z, p.z, acc[r][w]); acc[r][w] = fmaf(q[r].w, p.w, acc[r][w]);
+        }
+      }
+    }
+  }
+}
+
+template <int MODE, int WT, int RW>
 __global__ void __launch_bounds__(kThreads)
 proto_fwd_kernel(const float* __restrict__ feat, int64_t ld, const int32_t* __restrict__ cls_row,
-                 int W, int S, int D4, float* __restrict__ logits, int32_t* __restrict__ pred,
-                 const float4* __restrict__ protos_g) {
-  extern __shared__ float4 s_proto[];  // [W][D4] when SMEM_PROTO
+                 int W, int S, int D4, int DS4, float* __restrict__ logits, int32_t* __restrict__ pred,
+                 const float4* __restrict__ protos_g, const float* __restrict__ pinv_g) {
+  extern __shared__ float4 s_proto[];  // [W][DS4]: the current column slice of this episode's prototypes
   __shared__ int s_qbase[kMaxWay + 1];
-  __shared__ float s_pinv[kMaxWay];
 
   const int e = blockIdx.x;
   const int tid = threadIdx.x;
@@ -60,50 +109,23 @@ proto_fwd_kernel(const float* __restrict__ feat, int64_t ld, const int32_t* __re
     const int g = e * W + tid;
     s_qbase[tid] = cls_row[g] - g * S;
   }
-  const float4* proto;
-  if (SMEM_PROTO) {
-    const float fS = static_cast<float>(S);
-    for (int idx = tid; idx < W * D4; idx += kThreads) {
-      const int w = idx / D4;
-      const int c = idx - w * D4;
-      const float* base = feat + static_cast<int64_t>(cls_row[e * W + w]) * ld + 4 * c;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = 0; s < S; ++s) {
-        const float4 v = *reinterpret_cast<const float4*>(base + s * ld);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
-      s_proto[idx] = make_float4(acc.x / fS, acc.y / fS, acc.z / fS, acc.w / fS);
-    }
-    proto = s_proto;
-  } else {
-    proto = protos_g + static_cast<int64_t>(e) * W * D4;
-  }
   __syncthreads();
-
-  if (MODE == AFS_PROTO_COSINE) {
-    for (int w = warp; w < W; w += kWarps) {
-      float ss = 0.f;
-      for (int c = lane; c < D4; c += 32) {
-        const float4 p = proto[w * D4 + c];
-        ss = fmaf(p.x, p.x, ss); ss = fmaf(p.y, p.y, ss);
-        ss = fmaf(p.z, p.z, ss); ss = fmaf(p.w, p.w, ss);
-      }
-      ss = warp_sum(ss);
-      if (lane == 0) s_pinv[w] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-    }
-    __syncthreads();
-  }
-
+  const float4* pe = protos_g + static_cast<int64_t>(e) * W * D4;
   const int out0 = s_qbase[0];
   const int out1 = s_qbase[W];
   const int ngroups = (out1 - out0 + RW - 1) / RW;
+  const int n_slices = (D4 + DS4 - 1) / DS4;
+  bool filled = false;
 
-  for (int grp = blockIdx.y * kWarps + warp; grp < ngroups; grp += gridDim.y * kWarps) {
+  // every warp of the CTA makes the same number of trips (the slice loop synchronises the CTA)
+  for (int g0 = blockIdx.y * kWarps; g0 < ngroups; g0 += gridDim.y * kWarps) {
+    const int grp = g0 + warp;
+    const bool active = grp < ngroups;
     const int o_base = out0 + grp * RW;
     const float* qptr[RW];
 #pragma unroll
     for (int r = 0; r < RW; ++r) {
-      int o = o_base + r;
+      int o = active ? o_base + r : out0;
       if (o >= out1) o = out1 - 1;  // tail rows recompute the last row; never stored
       int w = 0;
       while (s_qbase[w + 1] <= o) ++w;
@@ -119,36 +141,38 @@ proto_fwd_kernel(const float* __restrict__ feat, int64_t ld, const int32_t* __re
       for (int w = 0; w < WT; ++w) acc[r][w] = 0.f;
     }
 
-    for (int c = lane; c < D4; c += 32) {
-      float4 q[RW];
-#pragma unroll
-      for (int r = 0; r < RW; ++r) q[r] = ldg_stream4(qptr[r] + 4 * c);
-      if (MODE == AFS_PROTO_COSINE) {
-#pragma unroll
-        for (int r = 0; r < RW; ++r) {
-          qq[r] = fmaf(q[r].x, q[r].x, qq[r]); qq[r] = fmaf(q[r].y, q[r].y, qq[r]);
-          qq[r] = fmaf(q[r].z, q[r].z, qq[r]); qq[r] = fmaf(q[r].w, q[r].w, qq[r]);
+    for (int sl = 0; sl < n_slices; ++sl) {
+      const int c0 = sl * DS4;
+      const int cn = min(DS4, D4 - c0);
+      if (n_slices > 1 || !filled) {
+        __syncthreads();  // the previous slice has been consumed
+        for (int idx = tid; idx < W * cn; idx += kThreads) {
+          const int w = idx / cn, c = idx - w * cn;
+          s_proto[w * DS4 + c] = __ldg(pe + static_cast<int64_t>(w) * D4 + c0 + c);
         }
+        __syncthreads();
+        filled = true;
       }
+      if (active) {
+        int c = lane;
+        for (; c + 32 < cn; c += 64) {  // two column chunks per trip: 2 * RW 128-bit loads in flight per thread
+          float4 qa[RW], qb[RW];
 #pragma unroll
-      for (int w = 0; w < WT; ++w) {
-        if (w < W) {
-          const float4 p = proto[w * D4 + c];
+          for (int r = 0; r < RW; ++r) qa[r] = ldg_stream4(qptr[r] + 4 * (c0 + c));
 #pragma unroll
-          for (int r = 0; r < RW; ++r) {
-            if (MODE == AFS_PROTO_EUCLIDEAN) {
-              const float dx = q[r].x - p.x, dy = q[r].y - p.y;
-              const float dz = q[r].z - p.z, dw = q[r].w - p.w;
-              acc[r][w] = fmaf(dx, dx, acc[r][w]); acc[r][w] = fmaf(dy, dy, acc[r][w]);
-              acc[r][w] = fmaf(dz, dz, acc[r][w]); acc[r][w] = fmaf(dw, dw, acc[r][w]);
-            } else {
-              acc[r][w] = fmaf(q[r].x, p.x, acc[r][w]); acc[r][w] = fmaf(q[r].y, p.y, acc[r][w]);
-              acc[r][w] = fmaf(q[r].z, p.z, acc[r][w]); acc[r][w] = fmaf(q[r].w, p.w, acc[r][w]);
-            }
-          }
+          for (int r = 0; r < RW; ++r) qb[r] = ldg_stream4(qptr[r] + 4 * (c0 + c + 32));
+          proto_accumulate<MODE, WT, RW>(qa, s_proto, DS4, c, W, acc, qq);
+          proto_accumulate<MODE, WT, RW>(qb, s_proto, DS4, c + 32, W, acc, qq);
+        }
+        if (c < cn) {
+          float4 qa[RW];
+#pragma unroll
+          for (int r = 0; r < RW; ++r) qa[r] = ldg_stream4(qptr[r] + 4 * (c0 + c));
+          proto_accumulate<MODE, WT, RW>(qa, s_proto, DS4, c, W, acc, qq);
         }
       }
     }
+    if (!active) continue;
 
 #pragma unroll
     for (int r = 0; r < RW; ++r) {
@@ -169,7 +193,7 @@ proto_fwd_kernel(const float* __restrict__ feat, int64_t ld, const int32_t* __re
           if (w < W) {
             float v;
             if (MODE == AFS_PROTO_EUCLIDEAN) v = -acc[r][w];
-            else if (MODE == AFS_PROTO_COSINE) v = acc[r][w] * qinv * s_pinv[w];
+            else if (MODE == AFS_PROTO_COSINE) v = acc[r][w] * qinv * pinv_g[e * W + w];
             else v = acc[r][w];
             logits[static_cast<int64_t>(o) * W + w] = v;
             if (v > best) { best = v; best_w = w; }
@@ -181,53 +205,56 @@ proto_fwd_kernel(const float* __restrict__ feat, int64_t ld, const int32_t* __re
   }
 }
 
-template <int MODE, int WT, int RW, bool SMEM_PROTO>
+template <int MODE, int WT, int RW>
 int launch_fwd(const float* feat, int64_t ld, const int32_t* cls_row, int N, int E, int W, int S,
-               int D, float* logits, int32_t* pred, const float4* protos_g,
+               int D, float* logits, int32_t* pred, const float4* protos_g, const float* pinv_g,
                cudaStream_t stream) {
-  auto kern = proto_fwd_kernel<MODE, WT, RW, SMEM_PROTO>;
-  const size_t smem = SMEM_PROTO ? static_cast<size_t>(W) * D * sizeof(float) : 0;
+  auto kern = proto_fwd_kernel<MODE, WT, RW>;
+  const int D4 = D / 4;
+  int DS4 = kSliceBytes / (16 * W);  // float4 columns of a slice
+  DS4 -= DS4 % 64;                   // whole double-chunk trips
+  if (DS4 < 64) DS4 = 64;
+  if (DS4 > D4) DS4 = D4;
+  const size_t smem = static_cast<size_t>(W) * DS4 * sizeof(float4);
   if (smem > 48 * 1024) {
-    AFS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
+    AFS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
   const int nq = N - E * W * S;
   const int avg_groups = (nq / (E > 0 ? E : 1) + RW - 1) / RW;
   int max_split = (avg_groups + kWarps - 1) / kWarps;
   if (max_split < 1) max_split = 1;
-  int want = (2 * kNumSMs + E - 1) / E;
+  int want = (4 * kNumSMs + E - 1) / E;  // enough CTAs for four per SM
   int nsplit = want < max_split ? want : max_split;
   if (nsplit < 1) nsplit = 1;
   dim3 grid(E, nsplit);
-  kern<<<grid, kThreads, smem, stream>>>(feat, ld, cls_row, W, S, D / 4, logits, pred, protos_g);
+  kern<<<grid, kThreads, smem, stream>>>(feat, ld, cls_row, W, S, D4, DS4, logits, pred, protos_g, pinv_g);
   AFS_LAUNCH_CHECK();
   return AFS_OK;
 }
 
-template <int MODE, bool SMEM_PROTO>
+template <int MODE>
 int dispatch_way(const float* feat, int64_t ld, const int32_t* cls_row, int N, int E, int W,
-                 int S, int D, float* logits, int32_t* pred, const float4* protos_g,
+                 int S, int D, float* logits, int32_t* pred, const float4* protos_g, const float* pinv_g,
                  cudaStream_t stream) {
   if (W <= 5)
-    return launch_fwd<MODE, 5, 4, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+    return launch_fwd<MODE, 5, 4>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, pinv_g, stream);
   if (W <= 8)
-    return launch_fwd<MODE, 8, 2, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+    return launch_fwd<MODE, 8, 2>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, pinv_g, stream);
   if (W <= 16)
-    return launch_fwd<MODE, 16, 1, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
-  return launch_fwd<MODE, 32, 1, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+    return launch_fwd<MODE, 16, 1>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, pinv_g, stream);
+  return launch_fwd<MODE, 32, 1>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, pinv_g, stream);
 }
 
-template <bool SMEM_PROTO>
 int dispatch_mode(int mode, const float* feat, int64_t ld, const int32_t* cls_row, int N, int E,
-                  int W, int S, int D, float* logits, int32_t* pred, const float4* protos_g,
+                  int W, int S, int D, float* logits, int32_t* pred, const float4* protos_g, const float* pinv_g,
                   cudaStream_t stream) {
   switch (mode) {
     case AFS_PROTO_EUCLIDEAN:
-      return dispatch_way<AFS_PROTO_EUCLIDEAN, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+      return dispatch_way<AFS_PROTO_EUCLIDEAN>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, pinv_g, stream);
     case AFS_PROTO_COSINE:
-      return dispatch_way<AFS_PROTO_COSINE, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+      return dispatch_way<AFS_PROTO_COSINE>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, pinv_g, stream);
     case AFS_PROTO_DOT:
-      return dispatch_way<AFS_PROTO_DOT, SMEM_PROTO>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, stream);
+      return dispatch_way<AFS_PROTO_DOT>(feat, ld, cls_row, N, E, W, S, D, logits, pred, protos_g, pinv_g, stream);
     default:
       return AFS_ERR_INVALID_ARG;
   }
@@ -420,8 +447,9 @@ bool args_ok(const void* feat, int64_t ld, const void* cls_row, int N, int E, in
 extern "C" size_t afs_proto_workspace_bytes(int32_t E, int32_t W, int32_t S, int32_t D) {
   (void)S;
   if (E <= 0 || W <= 0 || D <= 0) return 0;
-  const size_t per_episode = static_cast<size_t>(W) * D * sizeof(float);
-  return per_episode <= afs::kSmemProtoLimit ? 0 : per_episode * static_cast<size_t>(E);
+  // the E*W prototypes [D] and their inverse norms (cosine mode), 16-byte aligned
+  const size_t protos = static_cast<size_t>(E) * W * D * sizeof(float);
+  return protos + ((static_cast<size_t>(E) * W * sizeof(float) + 15) & ~static_cast<size_t>(15));
 }
 
 extern "C" int afs_proto_fwd(const float* feat, int64_t ld_feat, const int32_t* cls_row, int32_t N,
@@ -433,18 +461,20 @@ extern "C" int afs_proto_fwd(const float* feat, int64_t ld_feat, const int32_t* 
   if (E == 0 || N == E * W * S) return AFS_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t need = afs_proto_workspace_bytes(E, W, S, D);
-  if (need == 0) {
-    return dispatch_mode<true>(mode, feat, ld_feat, cls_row, N, E, W, S, D, logits, pred, nullptr, stream);
-  }
   if (ws == nullptr || ws_bytes < need) return AFS_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(ws) % 16 != 0) return AFS_ERR_INVALID_ARG;
   float4* protos = static_cast<float4*>(ws);
+  float* pinv = reinterpret_cast<float*>(static_cast<char*>(ws) + static_cast<size_t>(E) * W * D * sizeof(float));
   const int64_t total = static_cast<int64_t>(E) * W * (D / 4);
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   proto_mean_kernel<<<blocks, 256, 0, stream>>>(feat, ld_feat, cls_row, E * W, S, D / 4, protos);
   AFS_LAUNCH_CHECK();
-  return dispatch_mode<false>(mode, feat, ld_feat, cls_row, N, E, W, S, D, logits, pred, protos, stream);
+  if (mode == AFS_PROTO_COSINE) {
+    proto_pinv_kernel<<<(E * W * 32 + 255) / 256, 256, 0, stream>>>(protos, E * W, D / 4, pinv);
+    AFS_LAUNCH_CHECK();
+  }
+  return dispatch_mode(mode, feat, ld_feat, cls_row, N, E, W, S, D, logits, pred, protos, pinv, stream);
 }
 
 extern "C" size_t afs_proto_bwd_cos_workspace_bytes(int32_t N, int32_t E, int32_t W, int32_t S) {

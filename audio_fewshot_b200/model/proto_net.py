@@ -30,9 +30,13 @@ def accuracy_percent(output, target, as_tensor=False):
 
 
 class ProtoNet(MetricModel):
-    def __init__(self, distance="euclidean", **kwargs):
+    def __init__(self, distance="euclidean", precision="fp32", **kwargs):
+        """precision (not a reference kwarg): "fp32" is the parity path; "tf32" evaluates the logits as
+        -(|q|^2 - 2 q.p + |p|^2) with q.p on the tcgen05 tensor cores (euclidean, evaluation only; a separate
+        precision class, see csrc/proto_tc.cu)."""
         super().__init__(**kwargs)
         self.distance = distance
+        self.precision = precision
         self.loss_func = nn.CrossEntropyLoss()
         self.is_clap = kwargs.get("is_clap", False)
 
@@ -40,7 +44,7 @@ class ProtoNet(MetricModel):
         image, repeats, support_size = self._unpack(batch)
         feat = self.emb_func(image)
         tab = self._table(feat.shape[0], repeats, support_size)
-        output = ops.proto_logits(feat, tab.cls_row, tab.E, tab.W, tab.S, self.distance)
+        output = ops.proto_logits(feat, tab.cls_row, tab.E, tab.W, tab.S, self.distance, precision=self.precision)
         _, acc, _ = ops.vote_acc(output, tab.q_start, tab.q_target)
         return output, acc
 

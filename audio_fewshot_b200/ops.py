@@ -353,11 +353,43 @@ class _ProtoFn(torch.autograd.Function):
         return grad_feat, None, None, None, None, None
 
 
-def proto_logits(feat, cls_row, E, W, S, mode="euclidean", want_pred=False):
-    """Prototype head.  Differentiable w.r.t. feat (modes euclidean, dot) when feat requires grad."""
+def _proto_tc_call(feat, cls_row, E, W, S, want_pred):
+    """Prototype head in the "tf32" precision class (csrc/proto_tc.cu): -(|q|^2 - 2 q.p + |p|^2) with q.p on the
+    tcgen05 tensor cores.  Euclidean mode, W <= 8, D % 32 == 0."""
+    _need_cuda(feat, "feat")
+    _need_cuda(cls_row, "cls_row", torch.int32)
+    if feat.dim() != 2:
+        raise ValueError("feat must be [N, D]")
+    if feat.stride(1) != 1 or feat.stride(0) % 4 != 0 or feat.data_ptr() % 16 != 0:
+        feat = feat.contiguous()
+    N, D = feat.shape
+    NQ = N - E * W * S
+    logits = torch.empty((NQ, W), dtype=torch.float32, device=feat.device)
+    pred = torch.empty((NQ,), dtype=torch.int32, device=feat.device) if want_pred else None
+    h = _lib.lib()
+    ws_bytes = int(h.afs_proto_tc_workspace_bytes(E, W, D))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=feat.device)
+    _lib.check(h.afs_proto_fwd_tc(_ptr(feat), feat.stride(0), _ptr(cls_row), N, E, W, S, D, _ptr(logits), _ptr(pred),
+                                  _ptr(ws), ws_bytes, _stream()), "afs_proto_fwd_tc")
+    return logits, pred
+
+
+def proto_logits(feat, cls_row, E, W, S, mode="euclidean", want_pred=False, precision="fp32"):
+    """Prototype head.  Differentiable w.r.t. feat (modes euclidean, dot) when feat requires grad.
+    precision="tf32" (evaluation, euclidean only): the tensor-core GEMM-epilogue formulation, a separate precision
+    class -- absolute logit error ~1e-3 |q| |p|, near-tie predictions may differ from the fp32 kernel."""
+    if precision not in ("fp32", "tf32"):
+        raise ValueError("precision must be 'fp32' or 'tf32'")
     if torch.is_grad_enabled() and feat.requires_grad:
+        if precision != "fp32":
+            raise ValueError("the tf32 prototype head has no backward: use precision='fp32' for training")
         logits = _ProtoFn.apply(feat, cls_row, E, W, S, mode)
         return (logits, None) if want_pred else logits
+    if precision == "tf32":
+        if mode != "euclidean":
+            raise ValueError("the tf32 prototype head implements the euclidean mode only")
+        logits, pred = _proto_tc_call(feat, cls_row, E, W, S, want_pred)
+        return (logits, pred) if want_pred else logits
     _, logits, pred = _proto_call(feat, cls_row, E, W, S, mode, want_pred)
     return (logits, pred) if want_pred else logits
 

@@ -215,8 +215,9 @@ int afs_add_bias_act_pool_nhwc_fwd(const float* a, const float* b, const float* 
  * mode: 0 = -sum_d (q-p)^2, 1 = cosine(q, p) with eps 1e-12, 2 = raw dot q.p.
  * feat [N, D] (row stride ld_feat floats), logits [NQ, W], pred [NQ] nullable
  * (argmax over W, lowest index on ties), NQ = N - E*W*S.  W <= 32.  D % 4 == 0
- * and 16-byte aligned rows.  ws: scratch of afs_proto_workspace_bytes() (0 when
- * the prototypes of one episode fit in shared memory; then ws may be NULL).   */
+ * and 16-byte aligned rows.  ws: scratch of afs_proto_workspace_bytes() bytes,
+ * 16-byte aligned: the E*W prototypes (written once by a pre-kernel, so that
+ * support rows are read exactly once) and their inverse norms.               */
 #define AFS_PROTO_EUCLIDEAN 0
 #define AFS_PROTO_COSINE 1
 #define AFS_PROTO_DOT 2
@@ -224,6 +225,17 @@ size_t afs_proto_workspace_bytes(int32_t E, int32_t W, int32_t S, int32_t D);
 int afs_proto_fwd(const float* feat, int64_t ld_feat, const int32_t* cls_row, int32_t N,
                   int32_t E, int32_t W, int32_t S, int32_t D, int32_t mode, float* logits,
                   int32_t* pred, void* ws, size_t ws_bytes, afs_stream_t stream);
+
+/* (2a') The same head in the "tf32" precision class, stated apart from the parity path above (north star: "one
+ * tensor-core GEMM epilogue"): logit = -(|q|^2 - 2 q.p + |p|^2) with q.p as a tcgen05 TF32 GEMM fed by TMA and the
+ * norms in fp32 (csrc/proto_tc.cu).  Euclidean mode only.  The expansion cancels and the MMA truncates its operands
+ * to TF32: absolute logit error ~1e-3 |q| |p|, so near-tie predictions may differ from afs_proto_fwd.
+ * Requirements: W <= 8, D % 32 == 0, ld_feat % 4 == 0, 16-byte aligned feat, and every run of 128 consecutive
+ * feature rows must touch at most 32 / W episodes (logits of rows that break this come back as NaN).
+ * ws: afs_proto_tc_workspace_bytes(E, W, D) bytes, 16-byte aligned.                                          */
+size_t afs_proto_tc_workspace_bytes(int32_t E, int32_t W, int32_t D);
+int afs_proto_fwd_tc(const float* feat, int64_t ld_feat, const int32_t* cls_row, int32_t N, int32_t E, int32_t W,
+                     int32_t S, int32_t D, float* logits, int32_t* pred, void* ws, size_t ws_bytes, afs_stream_t stream);
 
 /* Backward of (2a) for set_forward_loss (proto_net.py:148-154 under autograd):
  * grad_feat [N, D] (row stride ld_grad) is fully overwritten.  Modes 0 and 2. */

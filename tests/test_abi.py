@@ -32,8 +32,8 @@ def test_binding_covers_header():
     from audio_fewshot_b200 import _lib
     assert sorted(_lib.SIGNATURES.keys()) == declared_symbols()
     h = _lib.lib()  # loads and type-checks every symbol
-    assert h.afs_proto_workspace_bytes(1, 5, 5, 1600) == 0
-    assert h.afs_proto_workspace_bytes(2, 5, 1, 12800) == 2 * 5 * 12800 * 4
+    assert h.afs_proto_workspace_bytes(1, 5, 5, 1600) == 5 * 1600 * 4 + 32  # prototypes + 5 inverse norms, 16-byte padded
+    assert h.afs_proto_workspace_bytes(2, 5, 1, 12800) == 2 * 5 * 12800 * 4 + 48
     assert h.afs_dn4_workspace_bytes(100, 1, 5, 5, 64, 20) > 100 * 64 * 20 * 4
 
 
