@@ -118,6 +118,7 @@ SIGNATURES = {
                               C.c_void_p]),
     "afs_bdc_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "afs_bdc_set_tensor_core": (C.c_int, [C.c_int32]),
     "afs_bdc_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                               C.c_void_p, C.c_void_p]),
     "afs_spec_augment": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,

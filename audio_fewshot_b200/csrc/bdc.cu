@@ -343,6 +343,17 @@ extern "C" int afs_bdc_bwd(const float* x, int32_t B, int32_t C, int32_t M, cons
   return AFS_OK;
 }
 
+namespace afs {
+int bdc_fwd_tc(const float* x, int32_t B, int32_t C, int32_t M, const float* log_temp, int32_t triu, float* out,
+               cudaStream_t stream);  // bdc_tc.cu
+static bool g_bdc_tensor_core = true;
+}  // namespace afs
+
+extern "C" int afs_bdc_set_tensor_core(int32_t enable) {
+  afs::g_bdc_tensor_core = enable != 0;
+  return AFS_OK;
+}
+
 extern "C" int afs_bdc_fwd(const float* x, int32_t B, int32_t C, int32_t M, const float* log_temp,
                            int32_t triu, float* out, afs_stream_t stream_) {
   using namespace afs;
@@ -351,6 +362,10 @@ extern "C" int afs_bdc_fwd(const float* x, int32_t B, int32_t C, int32_t M, cons
   if (C > kC) return AFS_ERR_UNSUPPORTED;
   if (B == 0) return AFS_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (g_bdc_tensor_core) {  // C == 64, M % 4 == 0: Gram on tcgen05 (3 x TF32), same epilogue arithmetic
+    const int r = bdc_fwd_tc(x, B, C, M, log_temp, triu, out, stream);
+    if (r != AFS_ERR_UNSUPPORTED) return r;
+  }
   bdc_kernel<<<B, kThreads, 0, stream>>>(x, C, M, log_temp, triu, out);
   AFS_LAUNCH_CHECK();
   return AFS_OK;

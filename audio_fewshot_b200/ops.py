@@ -524,6 +524,12 @@ def bdc_pool(x, log_temp, triu=True):
     return _bdc_call(x, log_temp, triu)[1]
 
 
+def bdc_set_tensor_core(enable):
+    """Process-wide switch of afs_bdc_fwd: True (default) runs the Gram on tcgen05 where the shape allows
+    (C == 64, M % 4 == 0), False always the fp32 FMA kernel."""
+    _lib.check(_lib.lib().afs_bdc_set_tensor_core(1 if enable else 0), "afs_bdc_set_tensor_core")
+
+
 VOTE_TIE_RULES = {"smallest": 0, "torch_cuda": 1}
 
 

@@ -295,7 +295,11 @@ int afs_dn4_bwd(const float* feat, const int32_t* cls_row, int32_t N, int32_t E,
  * scale, sqrt, double centring, row-major upper triangle.  Replaces
  * BDCovpool + Triuvec (libfewshot_core/model/backbone/utils/bdc_pool.py:69-93).
  * x [B, C, M]; log_temp: device pointer to the scalar `temperature`;
- * out [B, C*(C+1)/2] if triu else [B, C*C].  C <= 64 built.                 */
+ * out [B, C*(C+1)/2] if triu else [B, C*C].  C <= 64 built.  For C == 64 and
+ * M % 4 == 0 (16-byte aligned x) the Gram runs on the tcgen05 tensor cores with 3 x TF32
+ * operand splitting (csrc/bdc_tc.cu, within the same 1e-4 tolerance); other shapes, or
+ * after afs_bdc_set_tensor_core(0), the fp32 FMA kernel of csrc/bdc.cu.           */
+int afs_bdc_set_tensor_core(int32_t enable);
 int afs_bdc_fwd(const float* x, int32_t B, int32_t C, int32_t M, const float* log_temp,
                 int32_t triu, float* out, afs_stream_t stream);
 
