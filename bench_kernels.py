@@ -59,13 +59,16 @@ def main():
     flush = torch.empty(160 * 2 ** 20 // 4, dtype=torch.float32, device=dev)  # 160 MB > 126 MB L2
 
     # ---- fused log-mel, shapes S5 and S1
-    for tag, L, hop, B in (("S5 L=80000 hop=512", 80000, 512, 800), ("S1 L=16000 hop=102", 16000, 102, 800)):
-        fr = LogMelFrontEnd(hop_length=hop, n_mels=128, mean=-15.0, std=26.0).to(dev).eval()
-        wav = torch.randn(B, L, device=dev) * 0.1
-        T = 1 + L // hop
-        out = torch.empty(B, 1, 128, T, device=dev)
-        ms, mn = timeit(lambda: fr(wav, out=out), flush=flush)
-        report("logmel_kernel<false> " + tag, "clip", B, 4 * L + 4 * 128 * T, ms, mn, note="T=%d" % T)
+    for tag, L, hop, B in (("S5 L=80000 hop=512", 80000, 512, 800), ("S5 L=80000 hop=512", 80000, 512, 3200),
+                           ("S1 L=16000 hop=102", 16000, 102, 800)):
+        for engine, kname in (("fft", "logmel_kernel<false> (FFT engine)"), ("tc", "logmel_tc_kernel<false> (tcgen05 DFT engine)")):
+            fr = LogMelFrontEnd(hop_length=hop, n_mels=128, mean=-15.0, std=26.0, engine=engine).to(dev).eval()
+            wav = torch.randn(B, L, device=dev) * 0.1
+            T = 1 + L // hop
+            out = torch.empty(B, 1, 128, T, device=dev)
+            ms, mn = timeit(lambda: fr(wav, out=out), flush=flush)
+            report("%s %s B=%d" % (kname, tag, B), "clip", B, 4 * L + 4 * 128 * T, ms, mn, note="T=%d" % T)
+            del wav, out
     fr = LogMelFrontEnd(hop_length=512, n_mels=128, mean=-15.0, std=26.0, seed=7,
                         aug={"gain_db": (-6.0, 6.0), "max_shift": 1600, "noise_std": (0.0, 0.02)}).to(dev).train()
     wav = torch.randn(800, 80000, device=dev) * 0.1
@@ -107,15 +110,23 @@ def main():
 
     # ---- prototype head: C1 (D=1600, 5w5s15q), C2 (D=12800, 5w1s15q), C4 vectors (D=2080, 5w5s10q)
     for tag, E, W, S, Q, D, mode in (("C1 D=1600 5w5s15q", 256, 5, 5, 15, 1600, "euclidean"),
+                                     ("C1 D=1600 5w5s15q", 2048, 5, 5, 15, 1600, "euclidean"),
                                      ("C2 D=12800 5w1s15q", 64, 5, 1, 15, 12800, "euclidean"),
+                                     ("C2 D=12800 5w1s15q", 512, 5, 1, 15, 12800, "euclidean"),
                                      ("C4 D=2080 5w5s10q", 256, 5, 5, 10, 2080, "euclidean"),
                                      ("C1 cosine", 256, 5, 5, 15, 1600, "cos_sim")):
         N = E * W * (S + Q)
         feat = torch.randn(N, D, device=dev)
         tab = EpisodeTable(E, W, S, Q, np.ones(E * W * Q, dtype=np.int64), dev)
         ms, mn = timeit(lambda: ops.proto_logits(feat, tab.cls_row, E, W, S, mode), flush=flush)
-        report("proto_fwd_kernel " + tag, "episode", E, 4 * W * (S + Q) * D + 4 * W * Q * W, ms, mn,
-               flops_per_unit=3 * W * Q * W * D + W * S * D)
+        report("proto_mean_kernel + proto_fwd_kernel %s E=%d" % (tag, E), "episode", E, 4 * W * (S + Q) * D + 4 * W * Q * W, ms, mn,
+               flops_per_unit=3 * W * Q * W * D + W * S * D, note="two launches; small batches are launch-bound")
+        if mode == "euclidean" and D % 32 == 0:
+            ms, mn = timeit(lambda: ops.proto_logits(feat, tab.cls_row, E, W, S, mode, precision="tf32"), flush=flush)
+            report("proto_tc_kernel (TMA + tcgen05 TF32 GEMM epilogue) %s E=%d" % (tag, E), "episode", E,
+                   4 * W * (S + Q) * D + 4 * W * Q * W, ms, mn, flops_per_unit=2 * W * (S + Q) * 32 * D,
+                   note="precision class tf32; flops = executed MMA flops (N = 32 columns)")
+        del feat
 
     # ---- DN4: C3 Conv64F maps [64,4,5], 5w5s15q n_k=3; ResNet-12 maps [640,8,9] 5w5s10q
     for tag, E, W, S, Q, C, H, Wd in (("C3 map 64x4x5 5w5s15q", 128, 5, 5, 15, 64, 4, 5),
@@ -135,8 +146,14 @@ def main():
     # ---- BDC matrix: C4 map [64,16,19]
     x = torch.relu(torch.randn(2000, 64, 16, 19, device=dev))
     t = torch.full((1, 1), float(np.log(1 / 200.0)), device=dev)
-    ms, mn = timeit(lambda: ops.bdc_pool(x, t), flush=flush)
-    report("bdc_kernel C4 map 64x16x19", "clip", 2000, 4 * 64 * 304 + 4 * 2080, ms, mn, flops_per_unit=2 * 64 * 64 * 304)
+    for B_ in (2000, 8000):
+        x = torch.relu(torch.randn(B_, 64, 16, 19, device=dev))
+        for tc in (False, True):
+            ops.bdc_set_tensor_core(tc)
+            ms, mn = timeit(lambda: ops.bdc_pool(x, t), flush=flush)
+            report("%s C4 map 64x16x19 B=%d" % ("bdc_tc_kernel (tcgen05, 3xTF32)" if tc else "bdc_kernel (fp32 FMA)", B_), "clip", B_,
+                   4 * 64 * 304 + 4 * 2080, ms, mn, flops_per_unit=2 * 64 * 64 * 304)
+        ops.bdc_set_tensor_core(True)
 
     # ---- vote + accuracy, 5-way, one window per query
     nq = 75 * 4096
