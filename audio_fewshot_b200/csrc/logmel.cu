@@ -248,6 +248,10 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   pack_mel_ell(fb_host, cfg->n_mels, band, weights);
   if (weights.size() > static_cast<size_t>(kMaxNnz)) return AFS_ERR_UNSUPPORTED;
   if (weights.empty()) weights.push_back(0.f);
+  std::vector<int> band64;
+  std::vector<float> weights64;
+  pack_mel_ell(fb_host, cfg->n_mels, band64, weights64, logmel::kBanks64);
+  weights64.resize(weights.size(), 0.f);  // same rows per warp-pass, only the start shifts differ
 
   std::vector<float2> tw(kNfft);
   const double two_pi = 6.283185307179586476925286766559;
@@ -262,8 +266,13 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   plan->device = device;
   plan->nnz = static_cast<int>(weights.size());
   plan->d_window = nullptr; plan->d_tw1024 = nullptr; plan->d_band = nullptr; plan->d_weights = nullptr;
+  plan->d_band64 = nullptr; plan->d_weights64 = nullptr;
   plan->d_tc = nullptr;
   plan->engine = AFS_LOGMEL_ENGINE_FFT;
+  {
+    const char* v = getenv("AFS_PAIR_VARIANT");
+    plan->pair_variant = v != nullptr ? atoi(v) : 0;
+  }
 
   int prev = 0;
   cudaError_t e = cudaGetDevice(&prev);
@@ -276,11 +285,16 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   if (e == cudaSuccess) e = cudaMemcpy(plan->d_tw1024, tw.data(), kNfft * sizeof(float2), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(plan->d_band, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(plan->d_weights, weights.data(), weights.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&plan->d_band64, band64.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&plan->d_weights64, weights64.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(plan->d_band64, band64.data(), band64.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(plan->d_weights64, weights64.data(), weights64.size() * sizeof(float), cudaMemcpyHostToDevice);
   const int smem = static_cast<int>(kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<false, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_kernel<true, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = logmel::pair_prepare();
   if (e == cudaSuccess && logmel::tc_tables_create(plan, fb_host) != AFS_OK) e = cudaErrorMemoryAllocation;
   cudaSetDevice(prev);
   if (e != cudaSuccess) {
@@ -297,13 +311,15 @@ extern "C" int afs_logmel_plan_destroy(afs_logmel_plan* plan) {
   cudaFree(plan->d_tw1024);
   cudaFree(plan->d_band);
   cudaFree(plan->d_weights);
+  cudaFree(plan->d_band64);
+  cudaFree(plan->d_weights64);
   afs::logmel::tc_tables_destroy(plan);
   delete plan;
   return AFS_OK;
 }
 
 extern "C" int afs_logmel_plan_set_engine(afs_logmel_plan* plan, int32_t engine) {
-  if (plan == nullptr || (engine != AFS_LOGMEL_ENGINE_FFT && engine != AFS_LOGMEL_ENGINE_TC)) return AFS_ERR_INVALID_ARG;
+  if (plan == nullptr || (engine != AFS_LOGMEL_ENGINE_FFT && engine != AFS_LOGMEL_ENGINE_TC && engine != AFS_LOGMEL_ENGINE_PAIR)) return AFS_ERR_INVALID_ARG;
   if (engine == AFS_LOGMEL_ENGINE_TC && plan->d_tc == nullptr) return AFS_ERR_UNSUPPORTED;
   plan->engine = engine;
   return AFS_OK;
@@ -354,6 +370,7 @@ int logmel_launch(const afs_logmel_plan* plan, const S* wav, float pcm_scale, in
     p.max_shift = aug->max_shift;
   }
   if (plan->engine == AFS_LOGMEL_ENGINE_TC) return logmel::tc_launch<S>(plan, p, aug != nullptr, stream);
+  if (plan->engine == AFS_LOGMEL_ENGINE_PAIR) return logmel::pair_launch<S>(plan, p, aug != nullptr, stream);
   if (aug != nullptr) {
     logmel_kernel<true, S><<<g, kThreads, kSmemBytes, stream>>>(p);
   } else {

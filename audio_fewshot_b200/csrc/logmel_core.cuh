@@ -114,24 +114,31 @@ inline int pack_mel_bands(const float* fb, int n_mels, IntVec& band, FloatVec& w
 }
 
 // Shared-memory wavefronts of one warp-pass of the mel projection for one frame: in iteration i lane l reads power
-// bin start[l] + i when i < n[l] (all lanes execute iteration i in the same instruction); an instruction costs as
-// many wavefronts as the largest number of DISTINCT words that fall on one of the 32 banks.
-inline int mel_read_wavefronts(const int (&start)[32], const int (&n)[32]) {
+// bin start[l] + i when i < n[l] (all lanes execute iteration i in the same instruction).
+//   kBanks32: one 32-bit word per bin (radix-8 engine) -- an instruction costs as many wavefronts as the largest
+//             number of DISTINCT words that fall on one of the 32 banks;
+//   kBanks64: one 64-bit word per bin, the powers of a frame PAIR side by side (pair engine) -- the access is served
+//             per half-warp on 16 eight-byte banks, the cost is the sum over the two half-warps.
+enum MelBankModel { kBanks32 = 0, kBanks64 = 1 };
+inline int mel_read_wavefronts(const int (&start)[32], const int (&n)[32], MelBankModel model = kBanks32) {
+  const int group = model == kBanks32 ? 32 : 16;
   int total = 0;
   for (int i = 0;; ++i) {
-    int words[32][32], cnt[32] = {0}, worst = 0;
     bool any = false;
-    for (int l = 0; l < 32; ++l) {
-      if (i >= n[l]) continue;
-      any = true;
-      const int a = start[l] + i, b = a & 31;
-      bool seen = false;
-      for (int j = 0; j < cnt[b]; ++j) seen = seen || words[b][j] == a;
-      if (!seen) words[b][cnt[b]++] = a;
-      if (cnt[b] > worst) worst = cnt[b];
+    for (int g0 = 0; g0 < 32; g0 += group) {
+      int words[32][32], cnt[32] = {0}, worst = 0;
+      for (int l = g0; l < g0 + group; ++l) {
+        if (i >= n[l]) continue;
+        any = true;
+        const int a = start[l] + i, b = a & (group - 1);
+        bool seen = false;
+        for (int j = 0; j < cnt[b]; ++j) seen = seen || words[b][j] == a;
+        if (!seen) words[b][cnt[b]++] = a;
+        if (cnt[b] > worst) worst = cnt[b];
+      }
+      total += worst;
     }
     if (!any) break;
-    total += worst;
   }
   return total;
 }
@@ -150,7 +157,7 @@ inline int mel_read_wavefronts(const int (&start)[32], const int (&n)[32]) {
 //   band[2*kMaxMels+m] = index of the filter's table entry 0; consecutive entries are kEllStride apart.
 constexpr int kEllStride = 32;
 template <typename IntVec, typename FloatVec>
-inline int pack_mel_ell(const float* fb, int n_mels, IntVec& band, FloatVec& weights) {
+inline int pack_mel_ell(const float* fb, int n_mels, IntVec& band, FloatVec& weights, MelBankModel model = kBanks32) {
   IntVec b0;
   FloatVec w0;
   pack_mel_bands(fb, n_mels, b0, w0);
@@ -170,9 +177,10 @@ inline int pack_mel_ell(const float* fb, int n_mels, IntVec& band, FloatVec& wei
       // start shifts: r <= maxlen - len (the table does not grow) and r <= lo (the first bin read exists)
       int shift[32] = {0}, start[32], n[32];
       for (int lane = 0; lane < 32; ++lane) { start[lane] = lo[lane]; n[lane] = len[lane]; }
-      int best = mel_read_wavefronts(start, n);
+      int best = mel_read_wavefronts(start, n, model);
+      const int floor_cost = model == kBanks32 ? maxlen : 2 * maxlen;
       uint32_t rng = 0x9E3779B9u + static_cast<uint32_t>(pass * 2 + warp);
-      for (int it = 0; it < 6000 && best > maxlen; ++it) {
+      for (int it = 0; it < 6000 && best > floor_cost; ++it) {
         rng = rng * 1664525u + 1013904223u;
         const int lane = static_cast<int>((rng >> 8) & 31u);
         if (len[lane] == 0) continue;
@@ -184,7 +192,7 @@ inline int pack_mel_ell(const float* fb, int n_mels, IntVec& band, FloatVec& wei
         const int old = shift[lane];
         if (cand == old) continue;
         start[lane] = lo[lane] - cand; n[lane] = len[lane] + cand;
-        const int c = mel_read_wavefronts(start, n);
+        const int c = mel_read_wavefronts(start, n, model);
         if (c <= best) {  // sideways moves are accepted: the landscape is full of plateaus
           best = c; shift[lane] = cand;
         } else {

@@ -17,6 +17,9 @@ struct afs_logmel_plan {
   float2* d_tw1024;  // [1024]
   int* d_band;       // [3][128]: lo, len, off
   float* d_weights;  // [nnz]
+  int* d_band64;     // the same table with start shifts chosen for 64-bit power reads (pair engine)
+  float* d_weights64;
+  int pair_variant;  // pair engine: 0 = samples fetched one pair ahead before the transform, 1 = after it (development)
   void* d_tc;        // tensor-core engine: DFT operand images + twiddle table (logmel_tc.cu); null when unsupported
 };
 
@@ -133,6 +136,11 @@ int tc_tables_create(afs_logmel_plan* plan, const float* fb_host);  // sets plan
 void tc_tables_destroy(afs_logmel_plan* plan);
 template <typename S>
 int tc_launch(const afs_logmel_plan* plan, const Params& p, bool aug, cudaStream_t stream);
+
+// logmel_pair.cu
+cudaError_t pair_prepare();
+template <typename S>
+int pair_launch(const afs_logmel_plan* plan, const Params& p, bool aug, cudaStream_t stream);
 
 }  // namespace logmel
 }  // namespace afs

@@ -45,7 +45,7 @@ def _need_cuda(t, name, dtype=torch.float32):
 class LogMelPlan:
     """Owns an afs_logmel_plan (device tables: window, twiddles, packed mel bands)."""
 
-    ENGINES = {"fft": 0, "tc": 1}
+    ENGINES = {"fft": 0, "tc": 1, "pair": 2}
 
     def __init__(self, fb, window, hop, n_mels, center=True, log_mult=10.0, log_eps=2.220446049250313e-16,
                  device=None, engine=None):

@@ -96,6 +96,7 @@ int afs_logmel_plan_destroy(afs_logmel_plan* plan);
  * AFS_ERR_UNSUPPORTED when the plan cannot run the requested engine.                                       */
 #define AFS_LOGMEL_ENGINE_FFT 0
 #define AFS_LOGMEL_ENGINE_TC 1
+#define AFS_LOGMEL_ENGINE_PAIR 2
 int afs_logmel_plan_set_engine(afs_logmel_plan* plan, int32_t engine);
 /* number of output frames for clips of L samples */
 int afs_logmel_num_frames(const afs_logmel_plan* plan, int64_t L);

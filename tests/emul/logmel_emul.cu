@@ -11,6 +11,7 @@
 
 #include "logmel_core.cuh"
 #include "logmel_fft.cuh"
+#include "logmel_pair.cuh"
 
 using namespace afs::logmel;
 
@@ -165,6 +166,139 @@ extern "C" int emul_mel_read_wavefronts(const float* fb, int n_mels, int shifted
       *iterations += longest;
       total += mel_read_wavefronts(start, n);
     }
+  }
+  return total;
+}
+
+// ---- warp-per-frame-pair engine (logmel_pair.cuh): 32 'lanes' looped per phase; the shuffle of the split is a read of
+// the partner lane's register array; power planes and mel batches exactly as logmel_pair.cu lays them out. ----
+extern "C" int emul_logmel_pair(const float* wav, int64_t L, int hop, int center, const float* fb,
+                                const float* window, int n_mels, const float* mean, const float* stdv,
+                                float log_mult, float log_eps, float* out, float* power_out) {
+  std::vector<int> band;
+  std::vector<float> weights;
+  pack_mel_ell(fb, n_mels, band, weights, kBanks64);
+  const int pad = center ? kNfft / 2 : 0;
+  const int T = center ? static_cast<int>(1 + L / hop) : static_cast<int>(1 + (L - kNfft) / hop);
+  std::vector<float2> exch(kPairExch);
+  std::vector<float2> planeA(kPStride, make_float2(0.f, 0.f)), planeB(kPStride, make_float2(0.f, 0.f));
+  std::vector<float2> regs(32 * 32);
+  auto sample = [&](int f, int n) -> float {
+    if (f >= T) return 0.f;
+    int64_t i = static_cast<int64_t>(f) * hop - pad + n;
+    i = reflect_index(i, L);
+    return wav[i];
+  };
+  const int chunk_frames = 8;
+  for (int t0 = 0; t0 < T; t0 += chunk_frames) {
+    const int nfr = T - t0 < chunk_frames ? T - t0 : chunk_frames;
+    const int npairs = (nfr + 1) / 2;
+    for (int j = 0; j < npairs; ++j) {
+      const int fa = t0 + 2 * j;
+      for (int lane = 0; lane < 32; ++lane) {
+        float2 z[32];
+        for (int n2 = 0; n2 < 32; ++n2) {
+          const int n = lane + 32 * n2;
+          const float wv = 0.5f * window[n];  // the kernel stages the window halved (logmel_pair.cuh)
+          z[n2] = make_float2(sample(fa, n) * wv, sample(fa + 1, n) * wv);
+        }
+        const double a = 6.283185307179586476925286766559 * lane / kNfft;
+        pair_pass1(lane, z, make_float2(static_cast<float>(cos(a)), static_cast<float>(-sin(a))), exch.data());
+      }
+      for (int lane = 0; lane < 32; ++lane) {
+        float2 x[32];
+        pair_pass2(lane, exch.data(), x);
+        for (int i = 0; i < 32; ++i) regs[lane * 32 + i] = x[i];
+      }
+      float2* plane = (j & 1) ? planeB.data() : planeA.data();
+      for (int lane = 0; lane < 32; ++lane) {
+        const int partner = pair_partner(lane);
+        float2 xs[32], xp[32];
+        for (int i = 0; i < 32; ++i) { xs[i] = regs[lane * 32 + i]; xp[i] = regs[partner * 32 + i]; }
+        for (int k2 = 0; k2 < 16; ++k2) {
+          const float2 b = pair_split_src(partner, xp, k2);
+          plane[lane + 32 * k2] = pair_power(xs[k2], b);
+        }
+        if (lane == 0) plane[512] = pair_power(xs[16], xs[16]);
+      }
+      if (power_out) {
+        for (int h = 0; h < 2; ++h)
+          if (fa + h < T)
+            for (int k = 0; k < kBins; ++k) power_out[static_cast<size_t>(fa + h) * kBins + k] = h ? plane[k].y : plane[k].x;
+      }
+      const bool last = j + 1 >= npairs;
+      if (!((j & 1) || last)) continue;
+      const int c0 = (j & ~1) * 2;
+      for (int lane = 0; lane < 32; ++lane)
+        for (int vp = 0; vp < 4; ++vp) {
+          const int m = pair_mel_id(lane, vp & 1, vp >> 1, n_mels);
+          if (m < 0) continue;
+          if (band[2 * kMaxMels + m] % kEllStride != lane) return -1;
+          float acc[4];
+          mel_dot_pairs(planeA.data(), planeB.data(), weights.data() + band[2 * kMaxMels + m], band[m], band[kMaxMels + m], acc);
+          const float scale = log_mult * 0.30102999566398120f / stdv[m];
+          const float shift = -mean[m] / stdv[m];
+          for (int f = 0; f < 4; ++f)
+            if (c0 + f < nfr) out[static_cast<size_t>(m) * T + t0 + c0 + f] = norm_db(acc[f], log_eps, scale, shift);
+        }
+    }
+  }
+  return T;
+}
+
+// Worst number of distinct 64-bit words one half-warp puts on one of the 16 eight-byte banks over the exchange's
+// access patterns (1 = conflict-free), and -1 unless every (n1, k1) has its own slot inside the buffer.
+extern "C" int emul_pair_bank_check() {
+  std::vector<char> seen(kPairExch, 0);
+  for (int n1 = 0; n1 < 32; ++n1)
+    for (int k1 = 0; k1 < 32; ++k1) {
+      const int s = n1 * kPairStride + k1;
+      if (s >= kPairExch || seen[s]) return -1;
+      seen[s] = 1;
+    }
+  int worst = 0;
+  // group = 16 lanes on 16 eight-byte banks (64-bit access) or 8 lanes on 8 sixteen-byte banks (128-bit access)
+  auto access = [&](int group, auto word_of_lane) {
+    for (int g0 = 0; g0 < 32; g0 += group) {
+      int words[16][16], cnt[16] = {0};
+      for (int l = g0; l < g0 + group; ++l) {
+        const int a = word_of_lane(l), b = a & (group - 1);
+        bool dup = false;
+        for (int i = 0; i < cnt[b]; ++i) dup = dup || words[b][i] == a;
+        if (!dup) words[b][cnt[b]++] = a;
+        if (cnt[b] > worst) worst = cnt[b];
+      }
+    }
+  };
+  if (kPairStride % 2 != 0) return -1;  // 128-bit stores need 16-byte aligned rows
+  for (int r = 0; r < 32; ++r) {
+    if (r % 2 == 0) access(8, [&](int lane) { return (lane * kPairStride + r) / 2; });  // pass 1 writes (k1, k1 + 1) = (r, r + 1)
+    access(16, [&](int lane) { return r * kPairStride + lane; });                        // pass 2 reads n1 = r
+  }
+  for (int q = 0; q < 8; ++q) access(8, [&](int lane) { return (lane * 36 + 4 * q) / 4; });  // window reads (kPWinStride = 36)
+  return worst;
+}
+
+// Shared-memory wavefronts per frame PAIR of the pair engine's mel power reads (64-bit word per bin, served per
+// half-warp), replayed from the table packed for that bank model; *iterations = read instructions per pair.
+extern "C" int emul_mel_read_wavefronts64(const float* fb, int n_mels, int shifted, int* iterations) {
+  std::vector<int> band, b0;
+  std::vector<float> weights, w0;
+  pack_mel_ell(fb, n_mels, band, weights, kBanks64);
+  pack_mel_bands(fb, n_mels, b0, w0);
+  int total = 0;
+  *iterations = 0;
+  for (int vp = 0; vp < 4; ++vp) {
+    int start[32], n[32], longest = 0;
+    for (int lane = 0; lane < 32; ++lane) {
+      const int m = pair_mel_id(lane, vp & 1, vp >> 1, n_mels);
+      start[lane] = m < 0 ? 0 : (shifted ? band[m] : b0[m]);
+      n[lane] = m < 0 ? 0 : (shifted ? band[kMaxMels + m] : b0[kMaxMels + m]);
+      if (start[lane] < 0 || start[lane] + n[lane] > kBins) return -1;
+      if (n[lane] > longest) longest = n[lane];
+    }
+    *iterations += longest;
+    total += mel_read_wavefronts(start, n, kBanks64);
   }
   return total;
 }

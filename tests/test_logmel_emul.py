@@ -19,7 +19,8 @@ LIB = os.path.join(OUT_DIR, "liblogmel_emul.so")
 def emul():
     os.makedirs(OUT_DIR, exist_ok=True)
     deps = [SRC, os.path.join(ROOT, "audio_fewshot_b200", "csrc", "logmel_core.cuh"),
-            os.path.join(ROOT, "audio_fewshot_b200", "csrc", "logmel_fft.cuh")]
+            os.path.join(ROOT, "audio_fewshot_b200", "csrc", "logmel_fft.cuh"),
+            os.path.join(ROOT, "audio_fewshot_b200", "csrc", "logmel_pair.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-x", "cu",
                                "-Wno-deprecated-gpu-targets",
@@ -27,10 +28,11 @@ def emul():
                                "-I", os.path.join(ROOT, "include"), SRC, "-o", LIB])
     lib = C.CDLL(LIB)
     lib.emul_logmel.restype = C.c_int
+    lib.emul_logmel_pair.restype = C.c_int
     return lib
 
 
-def run(lib, x, hop, n_mels=128, mean=-15.1, std=26.2):
+def run(lib, x, hop, n_mels=128, mean=-15.1, std=26.2, engine="fft"):
     L = x.shape[0]
     fb = fe.mel_filterbank(n_mels=n_mels)
     win = fe.hann_periodic()
@@ -40,7 +42,8 @@ def run(lib, x, hop, n_mels=128, mean=-15.1, std=26.2):
     m = np.full(n_mels, mean, np.float32)
     s = np.full(n_mels, std, np.float32)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    got_T = lib.emul_logmel(vp(x), C.c_int64(L), hop, 1, vp(fb), vp(win), n_mels, vp(m), vp(s), C.c_float(10.0),
+    fn = lib.emul_logmel_pair if engine == "pair" else lib.emul_logmel
+    got_T = fn(vp(x), C.c_int64(L), hop, 1, vp(fb), vp(win), n_mels, vp(m), vp(s), C.c_float(10.0),
                C.c_float(fe.LOG_EPS), vp(out), vp(power))
     assert got_T == T
     return out, power, m, s
@@ -48,10 +51,11 @@ def run(lib, x, hop, n_mels=128, mean=-15.1, std=26.2):
 
 @pytest.mark.parametrize("L,hop,n_mels", [(8000, 512, 128), (3000, 102, 128), (2049, 511, 128), (4096, 256, 80),
                                           (1500, 512, 64)])
-def test_phases_match_float64_spec(emul, L, hop, n_mels):
+@pytest.mark.parametrize("engine", ["fft", "pair"])
+def test_phases_match_float64_spec(emul, L, hop, n_mels, engine):
     rng = np.random.default_rng(L + hop)
     x = (rng.standard_normal(L) * 0.1).astype(np.float32)
-    out, power, m, s = run(emul, x, hop, n_mels)
+    out, power, m, s = run(emul, x, hop, n_mels, engine=engine)
     fr = fe.frames(x[None].astype(np.float64), hop)[0] * fe.hann_periodic().astype(np.float64)
     pref = np.abs(np.fft.rfft(fr, axis=-1)) ** 2
     assert np.abs(power - pref).max() / pref.max() < 2e-6
@@ -64,6 +68,26 @@ def test_exchange_layouts_are_bijective_and_conflict_free(emul):
     """Every 64-bit shared-memory access pattern of the FFT phases puts the 16 words of a half-warp on 16 different
     8-byte banks, and the exchange-2 slot function is a bijection onto [0, 512)."""
     assert emul.emul_packed_bank_check() == 1
+
+
+def test_pair_exchange_layout_is_bijective_and_conflict_free(emul):
+    """The one exchange of the warp-per-frame-pair engine: every (n1, k1) has its own slot and both access patterns
+    put the 16 words of a half-warp on 16 different 8-byte banks."""
+    assert emul.emul_pair_bank_check() == 1
+
+
+def test_pair_engine_separates_a_loud_and_a_quiet_frame(emul):
+    """Two frames share one complex transform; the split must not leak a loud frame into its 60 dB quieter
+    neighbour beyond fp32 rounding of the louder one (the same bound any fp32 FFT has on weak bins)."""
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(512 * 12) * 1e-3).astype(np.float32)
+    x[1024:1536] *= 1000.0
+    out, power, m, s = run(emul, x, 512, engine="pair")
+    fr = fe.frames(x[None].astype(np.float64), 512)[0] * fe.hann_periodic().astype(np.float64)
+    pref = np.abs(np.fft.rfft(fr, axis=-1)) ** 2
+    ref = fe.logmel_f64(x[None], hop=512, mean=m, std=s)[0, 0]
+    assert np.abs(out - ref).max() * 26.2 < 1e-4
+    assert np.abs(power - pref).max() / pref.max() < 2e-6
 
 
 def test_pure_tone_lands_in_the_right_mel_bin(emul):
@@ -103,6 +127,20 @@ def test_mel_power_reads_are_nearly_conflict_free(emul, n_mels):
     assert plain > 0 and shifted > 0
     assert it1.value == it0.value  # no extra iterations: shifts live in the slack of shorter filters
     assert shifted <= 1.2 * it1.value and shifted < plain, (n_mels, it1.value, plain, shifted)
+
+
+@pytest.mark.parametrize("n_mels", [128, 80, 64, 40])
+def test_pair_engine_mel_reads_are_nearly_conflict_free(emul, n_mels):
+    """The pair engine reads one 64-bit word (two frames) per bin, served per half-warp on 16 eight-byte banks: its
+    table is packed for that bank model; the conflict-free count is 2 wavefronts per read instruction."""
+    fb = fe.mel_filterbank(n_mels=n_mels)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    it0, it1 = C.c_int(0), C.c_int(0)
+    plain = emul.emul_mel_read_wavefronts64(vp(fb), n_mels, 0, C.byref(it0))
+    shifted = emul.emul_mel_read_wavefronts64(vp(fb), n_mels, 1, C.byref(it1))
+    assert plain > 0 and shifted > 0 and it1.value == it0.value
+    assert shifted <= plain and shifted <= 1.25 * 2 * it1.value, (n_mels, it1.value, plain, shifted)
+    print(n_mels, it1.value, plain, shifted)
 
 
 def test_phase_d_power_writes_are_conflict_free():
