@@ -269,10 +269,6 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   plan->d_band64 = nullptr; plan->d_weights64 = nullptr;
   plan->d_tc = nullptr;
   plan->engine = AFS_LOGMEL_ENGINE_FFT;
-  {
-    const char* v = getenv("AFS_PAIR_VARIANT");
-    plan->pair_variant = v != nullptr ? atoi(v) : 0;
-  }
 
   int prev = 0;
   cudaError_t e = cudaGetDevice(&prev);

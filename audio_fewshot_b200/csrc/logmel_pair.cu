@@ -2,14 +2,19 @@
 //
 // Same stage and same contract as logmel.cu (augmentation -> reflect padding -> framing -> window -> 1024-point real
 // DFT -> power -> banded mel projection -> log -> normalise -> [B, 1, n_mels, T]; algorithmic bytes per clip
-// 4 L + 4 n_mels T), different decomposition: a WARP owns 8 consecutive frames of one clip and transforms them two at
-// a time as one 1024-point complex FFT (logmel_pair.cuh) -- one shared-memory exchange per frame PAIR and an in-warp
-// shuffle split instead of three exchanges per frame.  Everything a warp touches is private to it (exchange buffer,
-// power planes, output tile), so after the tables are staged there is no CTA-wide or group barrier at all.
+// 4 L + 4 n_mels T), different decomposition: a WARP transforms two frames at a time as one 1024-point complex FFT
+// (logmel_pair.cuh) -- one shared-memory exchange per frame PAIR and an in-warp shuffle split instead of three
+// exchanges per frame.  Everything a warp touches is private to it (exchange buffer, power planes, output tile), so
+// after the tables are staged there is no CTA-wide or group barrier at all.
 //
-// One persistent CTA of 12 warps per SM; warp-items (clip, 8-frame chunk) are dealt round-robin so that the 12 warps
-// of a CTA work on neighbouring chunks (frame overlap is served by L1, neighbouring 32-byte output pieces are
-// written by the same SM).  Samples are fetched one pair ahead into registers.
+// One persistent CTA of 12 warps per SM (168 registers per thread: the register file is split per SM sub-partition,
+// three warps of 168 x 32 registers fill one).  The frame pairs of the whole batch form one sequence (clip-major);
+// every warp owns a contiguous run of it, equal to within one pair, so there is no tail.  Within a clip the pairs are
+// grouped in chunks of 8 frames: the mel projection runs once per 4 frames (one weight load feeds four frames) and the
+// chunk's [n_mels x 8] tile is staged in shared memory so that every global store instruction writes four 32-byte row
+// pieces.  The samples of the next pair are fetched half-way through the split loop, when half of the transform's 64
+// registers have retired (fetching before the transform spills at 168 registers; fetching register by register as
+// the split loop retires values was measured and is slower: 0.69 against 0.58 ms per 3 200 clips).
 #include <math.h>
 
 #include "common.cuh"
@@ -25,14 +30,14 @@ using namespace logmel;
 
 constexpr int kPWarps = 12;
 constexpr int kPThreads = 32 * kPWarps;
-constexpr int kPFrames = 8;          // frames per warp-item
+constexpr int kPFrames = 8;          // frames per chunk (output tile)
 constexpr int kPTileStride = 132;    // floats per tile column (frame): 132 = 4 mod 32 -> conflict-free 4-row x 8-frame reads
 constexpr int kPWinStride = 36;      // floats per lane of the staged window: 128-bit reads of 8 lanes hit 8 different 16-byte banks
 constexpr int kPExchFloats = 2 * kPairExch;
 constexpr int kPPlaneFloats = 2 * kPStride;  // one power plane: a 64-bit word (frame pair) per bin
 constexpr int kPWarpFloats = kPExchFloats + kPPlaneFloats + kPFrames * kPTileStride;
 static_assert(kPExchFloats >= kPPlaneFloats, "the second pair's power plane aliases the exchange buffer");
-static_assert(kPWarpFloats % 4 == 0 && kPExchFloats % 4 == 0, "16-byte alignment of the per-warp buffers");
+static_assert(kPExchFloats % 2 == 0 && kPWarpFloats % 2 == 0, "8-byte alignment of the per-warp buffers");
 
 inline size_t pair_smem_bytes(int nnz) {
   const size_t nnz_pad = (static_cast<size_t>(nnz) + 3) & ~static_cast<size_t>(3);
@@ -45,29 +50,26 @@ struct RawN {
   static constexpr int boff = HALF ? 16 : 32;
 };
 
+// Interior pair without augmentation: value m of the fetch list straight from memory.
+template <typename S, bool HALF>
+__device__ __forceinline__ float ld_fast(const S* xa, int hop, int m, float pcm_scale) {
+  if (HALF || m < 32) return ld_sample(xa + 32 * m, pcm_scale);
+  return ld_sample(xa + hop + 32 * (m - 32), pcm_scale);
+}
+
 // Raw (augmented, reflect-padded, not yet windowed) samples of the frame pair (fa, fa + 1) of one clip: lane l holds
 // sample l + 32 m of frame a in raw[m] and of frame b in raw[boff + m].  M0 = 16 (HALF only): raw[0..15] were carried
-// over from the previous pair.
+// over from the previous pair.  The general path: clip edges (reflection), missing second frame, augmentation.
 template <bool AUG, typename S, bool HALF, int M0>
 __device__ __forceinline__ void load_pair(const S* __restrict__ x, int64_t L, int64_t s0, int hop, bool b_exists, int lane,
                                           const AugState& aug, float (&raw)[RawN<HALF>::n]) {
-  const int64_t span = HALF ? 1536 : static_cast<int64_t>(hop) + kNfft;
-  if (!AUG && s0 >= 0 && s0 + span <= L) {
+  constexpr int n = RawN<HALF>::n;
+  if (!AUG && s0 >= 0 && s0 + (HALF ? 1536 : static_cast<int64_t>(hop) + kNfft) <= L) {  // interior pair
     const S* xa = x + s0 + lane;
-    if (HALF) {
 #pragma unroll
-      for (int m = M0; m < 48; ++m) raw[m] = ld_sample(xa + 32 * m, aug.pcm_scale);
-    } else {
-      const S* xb = xa + hop;
-#pragma unroll
-      for (int m = 0; m < 32; ++m) {
-        raw[m] = ld_sample(xa + 32 * m, aug.pcm_scale);
-        raw[32 + m] = ld_sample(xb + 32 * m, aug.pcm_scale);
-      }
-    }
+    for (int m = M0; m < n; ++m) raw[m] = ld_fast<S, HALF>(xa, hop, m, aug.pcm_scale);
     return;
   }
-  constexpr int n = RawN<HALF>::n;
 #pragma unroll
   for (int m = M0; m < n; ++m) {
     const bool of_b_only = m >= 32;
@@ -81,7 +83,7 @@ __device__ __forceinline__ void load_pair(const S* __restrict__ x, int64_t L, in
   }
 }
 
-template <bool AUG, typename S, bool HALF, bool EARLY>
+template <bool AUG, typename S, bool HALF>
 __global__ void __launch_bounds__(kPThreads, 1) logmel_pair_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
   const int nnz_pad = (p.nnz + 3) & ~3;
@@ -116,65 +118,54 @@ __global__ void __launch_bounds__(kPThreads, 1) logmel_pair_kernel(const Params 
 
   constexpr int NR = RawN<HALF>::n;
   constexpr int BOFF = RawN<HALF>::boff;
-  const int chunks = p.chunks;
-  const int n_items = p.B * chunks;
-  const int item_stride = gridDim.x * kPWarps;
+
+  // this warp's run of the pair sequence: pair g = clip * ppc + q covers frames 2q, 2q + 1 of `clip`
+  const int ppc = (p.T + 1) >> 1;
+  const int64_t n_pairs = static_cast<int64_t>(p.B) * ppc;
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * kPWarps;
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * kPWarps + warp;
+  const int64_t g_begin = gw * n_pairs / n_warps;
+  const int64_t g_end = (gw + 1) * n_pairs / n_warps;
+  int left = static_cast<int>(g_end - g_begin);
+  if (left <= 0) return;
+  int clip = static_cast<int>(g_begin / ppc);
+  int q = static_cast<int>(g_begin - static_cast<int64_t>(clip) * ppc);
+  int col_lo = 2 * (q & 3);  // first tile column this warp owns in its current chunk
 
   AugState aug;
   aug.pcm_scale = p.pcm_scale;
   float raw[NR];
-
-  // current pair: frames t0 + 2 j, t0 + 2 j + 1 of `clip`
-  int item = blockIdx.x * kPWarps + warp;
-  int j = 0, clip = 0, t0 = 0;
-  if (item < n_items) {
-    clip = item / chunks;
-    t0 = (item - clip * chunks) * kPFrames;
+  {
     if (AUG) init_clip_aug(aug, p, clip);
     const S* x = static_cast<const S*>(p.wav) + static_cast<int64_t>(clip) * p.L;
-    load_pair<AUG, S, HALF, 0>(x, p.L, static_cast<int64_t>(t0) * p.hop - p.pad, p.hop, t0 + 1 < p.T, lane, aug, raw);
+    load_pair<AUG, S, HALF, 0>(x, p.L, static_cast<int64_t>(2 * q) * p.hop - p.pad, p.hop, 2 * q + 1 < p.T, lane, aug, raw);
   }
 
-  while (item < n_items) {
-    const int nfr = min(kPFrames, p.T - t0);
-    const bool last = 2 * j + 2 >= nfr;  // last pair of this warp-item
+  while (left > 0) {
+    const int j = q & 3;                   // pair within the 8-frame chunk
+    const int t0 = (q & ~3) * 2;           // first frame of the chunk
+    const bool clip_end = q + 1 >= ppc;
+    const bool last = j == 3 || clip_end || left == 1;  // last pair this warp transforms in this chunk
 
     float2 z[32];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 wv = win4[q];
-      z[4 * q + 0] = make_float2(raw[4 * q + 0] * wv.x, raw[BOFF + 4 * q + 0] * wv.x);
-      z[4 * q + 1] = make_float2(raw[4 * q + 1] * wv.y, raw[BOFF + 4 * q + 1] * wv.y);
-      z[4 * q + 2] = make_float2(raw[4 * q + 2] * wv.z, raw[BOFF + 4 * q + 2] * wv.z);
-      z[4 * q + 3] = make_float2(raw[4 * q + 3] * wv.w, raw[BOFF + 4 * q + 3] * wv.w);
+    for (int i = 0; i < 8; ++i) {
+      const float4 wv = win4[i];
+      z[4 * i + 0] = make_float2(raw[4 * i + 0] * wv.x, raw[BOFF + 4 * i + 0] * wv.x);
+      z[4 * i + 1] = make_float2(raw[4 * i + 1] * wv.y, raw[BOFF + 4 * i + 1] * wv.y);
+      z[4 * i + 2] = make_float2(raw[4 * i + 2] * wv.z, raw[BOFF + 4 * i + 2] * wv.z);
+      z[4 * i + 3] = make_float2(raw[4 * i + 3] * wv.w, raw[BOFF + 4 * i + 3] * wv.w);
     }
 
-    // the pair after this one (this warp's next item when the chunk is finished); its samples are fetched now
-    // (EARLY: the loads fly during the whole transform) or after the power spectra are written.
-    int nitem = item, nj = j + 1, nclip = clip, nt0 = t0;
-    if (last) {
-      nitem = item + item_stride;
-      nj = 0;
-      nclip = nitem / chunks;
-      nt0 = (nitem - nclip * chunks) * kPFrames;
-    }
-    auto fetch_next = [&]() {
-      if (nitem >= n_items) return;
-      const int fa = nt0 + 2 * nj;
-      if (AUG && nclip != clip) init_clip_aug(aug, p, nclip);
-      const S* nx = static_cast<const S*>(p.wav) + static_cast<int64_t>(nclip) * p.L;
-      const int64_t s0 = static_cast<int64_t>(fa) * p.hop - p.pad;
-      if (HALF && !last) {
-        load_pair<AUG, S, HALF, HALF ? 16 : 0>(nx, p.L, s0, p.hop, fa + 1 < p.T, lane, aug, raw);
-      } else {
-        load_pair<AUG, S, HALF, 0>(nx, p.L, s0, p.hop, fa + 1 < p.T, lane, aug, raw);
-      }
-    };
-    if (HALF && !last) {
+    // the next pair of this warp's run
+    const bool have_next = left > 1;
+    const int nclip = clip_end ? clip + 1 : clip;
+    const int nq = clip_end ? 0 : q + 1;
+    const bool carry = HALF && !clip_end;  // its first 16 values per lane are this pair's last 16
+    if (carry) {
 #pragma unroll
       for (int m = 0; m < 16; ++m) raw[m] = raw[32 + m];
     }
-    if (EARLY) fetch_next();
 
     pair_pass1(lane, z, w, exch);
     __syncwarp();
@@ -185,6 +176,16 @@ __global__ void __launch_bounds__(kPThreads, 1) logmel_pair_kernel(const Params 
     const int partner = pair_partner(lane);
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {
+      if (k2 == 8 && have_next) {  // z[0..7] and z[24..31] have retired: room for the next pair's samples
+        if (AUG && nclip != clip) init_clip_aug(aug, p, nclip);
+        const S* nx = static_cast<const S*>(p.wav) + static_cast<int64_t>(nclip) * p.L;
+        const int64_t ns0 = static_cast<int64_t>(2 * nq) * p.hop - p.pad;
+        if (carry) {
+          load_pair<AUG, S, HALF, HALF ? 16 : 0>(nx, p.L, ns0, p.hop, 2 * nq + 1 < p.T, lane, aug, raw);
+        } else {
+          load_pair<AUG, S, HALF, 0>(nx, p.L, ns0, p.hop, 2 * nq + 1 < p.T, lane, aug, raw);
+        }
+      }
       const float2 src = pair_split_src(lane, z, k2);
       float2 b;
       b.x = __shfl_sync(0xffffffffu, src.x, partner);
@@ -192,7 +193,6 @@ __global__ void __launch_bounds__(kPThreads, 1) logmel_pair_kernel(const Params 
       plane[lane + 32 * k2] = pair_power(z[k2], b);
     }
     if (lane == 0) plane[512] = pair_power(z[16], z[16]);  // bin 512 is its own mirror
-    if (!EARLY) fetch_next();
     __syncwarp();
 
     if ((j & 1) || last) {
@@ -211,9 +211,10 @@ __global__ void __launch_bounds__(kPThreads, 1) logmel_pair_kernel(const Params 
       __syncwarp();
     }
 
-    if (last) {
+    if (last) {  // store the columns [col_lo, col_hi) of the chunk's tile: the frames this warp transformed
+      const int col_hi = min(2 * j + 2, p.T - t0);
       const int col = lane & 7, r0 = lane >> 3;
-      if (col < nfr) {
+      if (col >= col_lo && col < col_hi) {
         const float* tp = tile + col * kPTileStride + r0;
         float* o = p.out + (static_cast<int64_t>(clip) * p.n_mels + r0) * p.T + t0 + col;
         const int64_t step = 4 * static_cast<int64_t>(p.T);
@@ -230,9 +231,10 @@ __global__ void __launch_bounds__(kPThreads, 1) logmel_pair_kernel(const Params 
           tp += 4;
         }
       }
+      col_lo = 0;
       __syncwarp();
     }
-    item = nitem; j = nj; clip = nclip; t0 = nt0;
+    clip = nclip; q = nq; --left;
   }
 }
 
@@ -245,24 +247,20 @@ int pair_launch(const afs_logmel_plan* plan, const Params& p_in, bool aug, cudaS
   Params p = p_in;
   p.band = plan->d_band64;
   p.weights = plan->d_weights64;
-  p.chunks = (p.T + kPFrames - 1) / kPFrames;
-  const int64_t items = static_cast<int64_t>(p.B) * p.chunks;
-  if (items > 0x7fffffffLL) return AFS_ERR_UNSUPPORTED;
+  const int64_t n_pairs = static_cast<int64_t>(p.B) * ((p.T + 1) / 2);
+  if (n_pairs > 0x7fffffffLL) return AFS_ERR_UNSUPPORTED;
   const size_t smem = pair_smem_bytes(p.nnz);
   if (smem > 227 * 1024) return AFS_ERR_UNSUPPORTED;
-  const int64_t ctas = (items + kPWarps - 1) / kPWarps;
+  const int64_t ctas = (n_pairs + kPWarps - 1) / kPWarps;
   const unsigned grid = static_cast<unsigned>(ctas < kNumSMs ? ctas : kNumSMs);
   const bool half = p.hop * 2 == kNfft;
-  const bool late = plan->pair_variant == 1;
-#define AFS_PAIR_LAUNCH(AUGV, HALFV, EARLYV) logmel_pair_kernel<AUGV, S, HALFV, EARLYV><<<grid, kPThreads, smem, stream>>>(p)
   if (aug) {
-    if (half) AFS_PAIR_LAUNCH(true, true, false); else AFS_PAIR_LAUNCH(true, false, false);
-  } else if (late) {
-    if (half) AFS_PAIR_LAUNCH(false, true, false); else AFS_PAIR_LAUNCH(false, false, false);
+    if (half) logmel_pair_kernel<true, S, true><<<grid, kPThreads, smem, stream>>>(p);
+    else logmel_pair_kernel<true, S, false><<<grid, kPThreads, smem, stream>>>(p);
   } else {
-    if (half) AFS_PAIR_LAUNCH(false, true, true); else AFS_PAIR_LAUNCH(false, false, true);
+    if (half) logmel_pair_kernel<false, S, true><<<grid, kPThreads, smem, stream>>>(p);
+    else logmel_pair_kernel<false, S, false><<<grid, kPThreads, smem, stream>>>(p);
   }
-#undef AFS_PAIR_LAUNCH
   AFS_LAUNCH_CHECK();
   return AFS_OK;
 }
@@ -270,12 +268,10 @@ int pair_launch(const afs_logmel_plan* plan, const Params& p_in, bool aug, cudaS
 template <typename S>
 static cudaError_t pair_prepare_t() {
   const int smem = 227 * 1024;
-  cudaError_t e = cudaFuncSetAttribute(logmel_pair_kernel<true, S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_pair_kernel<true, S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_pair_kernel<false, S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_pair_kernel<false, S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_pair_kernel<false, S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_pair_kernel<false, S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(logmel_pair_kernel<true, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_pair_kernel<true, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_pair_kernel<false, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_pair_kernel<false, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   return e;
 }
 

@@ -3,7 +3,7 @@
 // z[n] = w[n] (x_f[n] + i x_{f+1}[n]), n = 0..1023, is transformed by one 1024-point complex FFT held as 32 values
 // per lane, decomposed 32 x 32 (n = n1 + 32 n2, k = k1 + 32 k2, W_n = exp(-2 pi i / n)):
 //   pass 1, lane n1: Y[n1,k1] = sum_n2 z[n1 + 32 n2] W_32^{n2 k1}   (32-point DFT in registers)
-//                    U[n1,k1] = Y[n1,k1] W_1024^{n1 k1}             -> shared memory, slot n1 * 34 + k1
+//                    U[n1,k1] = Y[n1,k1] W_1024^{n1 k1}             -> shared memory, slot n1 * 33 + k1
 //   pass 2, lane k1: X[k1 + 32 k2] = sum_n1 U[n1,k1] W_32^{n1 k2}   (32-point DFT in registers)
 //   split:           x_f, x_{f+1} real  =>  2 F_f[k] = X[k] + conj X[1024-k],  2i F_{f+1}[k] = X[k] - conj X[1024-k];
 //                    X[1024 - (k1 + 32 k2)] is value 31 - k2 of lane 32 - k1 (lane 0: value (32 - k2) & 31 of itself),
@@ -12,10 +12,10 @@
 // this is ONE exchange of 1024 complex values per TWO frames: a third of the exchange traffic per frame, no
 // group barriers (a warp only ever synchronises with itself), and 32 independent values per thread for the FMA pipe.
 //
-// Shared-memory bank model: pass 1 writes TWO neighbouring values (k1, k1 + 1) as one 128-bit store, served per
-// quarter-warp on 8 sixteen-byte banks -- slot pairs n1 * 17 + k1 / 2 over lanes n1 are distinct mod 8; pass-2 reads are
-// 64-bit, served per half-warp, slots n1 * 34 + k1 over lanes k1 -- contiguous.  Checked by tests/emul
-// (emul_pair_bank_check).
+// Shared-memory bank model (64-bit accesses are served per half-warp on 16 eight-byte banks): pass-1 writes of one
+// instruction are slots n1 * 33 + k1 over lanes n1 -- (n1 + k1) mod 16 distinct; pass-2 reads are n1 * 33 + k1 over lanes
+// k1 -- contiguous.  Checked by tests/emul (emul_pair_bank_check).  (128-bit stores of value pairs were measured and
+// dropped: ptxas needs four MOVs per store to line the registers up.)
 //
 // Scaling: the kernel stages the window multiplied by 1/2 (exact), so X is half the textbook transform and
 // |X[k] +- conj X[1024-k]|^2 IS the power of the frame -- the 1/4 of the split costs nothing.
@@ -25,7 +25,7 @@
 namespace afs {
 namespace logmel {
 
-constexpr int kPairStride = 34;                // float2 slots per exchange row (even: rows stay 16-byte aligned)
+constexpr int kPairStride = 33;                // float2 slots per exchange row
 constexpr int kPairExch = 32 * kPairStride;    // float2 slots of one warp's exchange buffer
 
 // s * (c + i d) with c, d compile-time constants: both enter as broadcast immediates (no constant register pairs).
@@ -77,9 +77,6 @@ AFS_HD void dft32_p(float2 (&a)[32]) {
 // Pass 1.  in: z[n2] = windowed (x_f[n], x_{f+1}[n]) as (re, im), n = lane + 32 n2; w = W_1024^lane.
 // The 31 twiddles W_1024^{lane k1} are rebuilt per pair from w (7 powers held, advanced by w^8 per group of eight):
 // 30 complex multiplications, at most 6 roundings deep.
-AFS_HD void pair_store2(float2* row, int k1, float2 u0, float2 u1) {
-  *reinterpret_cast<float4*>(row + k1) = make_float4(u0.x, u0.y, u1.x, u1.y);
-}
 AFS_HD void pair_pass1(int lane, float2 (&z)[32], float2 w, float2* exch) {
   dft32_p(z);
   float2* row = exch + lane * kPairStride;
@@ -89,15 +86,12 @@ AFS_HD void pair_pass1(int lane, float2 (&z)[32], float2 w, float2* exch) {
   float2 wa = w8;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    float2 u[8];
-    u[0] = a == 0 ? z[0] : c_mul(z[8 * a], wa);
+    row[8 * a] = a == 0 ? z[0] : c_mul(z[8 * a], wa);
 #pragma unroll
     for (int b = 1; b < 8; ++b) {
       if (a > 0) pw[b] = c_mul(pw[b], w8);
-      u[b] = c_mul(z[8 * a + b], pw[b]);
+      row[8 * a + b] = c_mul(z[8 * a + b], pw[b]);
     }
-#pragma unroll
-    for (int b = 0; b < 8; b += 2) pair_store2(row, 8 * a + b, u[b], u[b + 1]);
     if (a > 0 && a < 3) wa = c_mul(wa, w8);
   }
 }
@@ -138,6 +132,16 @@ AFS_HD void mel_dot_pairs(const float2* pA, const float2* pB, const float* weigh
     a23 = p_fma(ww, b[i], a23);
   }
   acc[0] = a01.x; acc[1] = a01.y; acc[2] = a23.x; acc[3] = a23.y;
+}
+// The same for one frame pair.
+AFS_HD float2 mel_dot_pair(const float2* pA, const float* weights, int lo, int len) {
+  float2 a01 = make_float2(0.f, 0.f);
+  const float2* a = pA + lo;
+  for (int i = 0; i < len; ++i) {
+    const float w = weights[i * kEllStride];
+    a01 = p_fma(make_float2(w, w), a[i], a01);
+  }
+  return a01;
 }
 
 // Filter owned by (lane, virtual warp vw, pass) in the ELL table of pack_mel_ell (a warp of this engine walks the four

@@ -19,7 +19,6 @@ struct afs_logmel_plan {
   float* d_weights;  // [nnz]
   int* d_band64;     // the same table with start shifts chosen for 64-bit power reads (pair engine)
   float* d_weights64;
-  int pair_variant;  // pair engine: 0 = samples fetched one pair ahead before the transform, 1 = after it (development)
   void* d_tc;        // tensor-core engine: DFT operand images + twiddle table (logmel_tc.cu); null when unsupported
 };
 

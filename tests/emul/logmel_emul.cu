@@ -270,10 +270,9 @@ extern "C" int emul_pair_bank_check() {
       }
     }
   };
-  if (kPairStride % 2 != 0) return -1;  // 128-bit stores need 16-byte aligned rows
   for (int r = 0; r < 32; ++r) {
-    if (r % 2 == 0) access(8, [&](int lane) { return (lane * kPairStride + r) / 2; });  // pass 1 writes (k1, k1 + 1) = (r, r + 1)
-    access(16, [&](int lane) { return r * kPairStride + lane; });                        // pass 2 reads n1 = r
+    access(16, [&](int lane) { return lane * kPairStride + r; });  // pass 1 writes k1 = r
+    access(16, [&](int lane) { return r * kPairStride + lane; });  // pass 2 reads n1 = r
   }
   for (int q = 0; q < 8; ++q) access(8, [&](int lane) { return (lane * 36 + 4 * q) / 4; });  // window reads (kPWinStride = 36)
   return worst;
