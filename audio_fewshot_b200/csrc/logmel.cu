@@ -268,7 +268,7 @@ extern "C" int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb
   plan->d_window = nullptr; plan->d_tw1024 = nullptr; plan->d_band = nullptr; plan->d_weights = nullptr;
   plan->d_band64 = nullptr; plan->d_weights64 = nullptr;
   plan->d_tc = nullptr;
-  plan->engine = AFS_LOGMEL_ENGINE_FFT;
+  plan->engine = AFS_LOGMEL_ENGINE_AUTO;
 
   int prev = 0;
   cudaError_t e = cudaGetDevice(&prev);
@@ -315,7 +315,7 @@ extern "C" int afs_logmel_plan_destroy(afs_logmel_plan* plan) {
 }
 
 extern "C" int afs_logmel_plan_set_engine(afs_logmel_plan* plan, int32_t engine) {
-  if (plan == nullptr || (engine != AFS_LOGMEL_ENGINE_FFT && engine != AFS_LOGMEL_ENGINE_TC && engine != AFS_LOGMEL_ENGINE_PAIR)) return AFS_ERR_INVALID_ARG;
+  if (plan == nullptr || (engine < AFS_LOGMEL_ENGINE_FFT || engine > AFS_LOGMEL_ENGINE_AUTO)) return AFS_ERR_INVALID_ARG;
   if (engine == AFS_LOGMEL_ENGINE_TC && plan->d_tc == nullptr) return AFS_ERR_UNSUPPORTED;
   plan->engine = engine;
   return AFS_OK;
@@ -366,7 +366,8 @@ int logmel_launch(const afs_logmel_plan* plan, const S* wav, float pcm_scale, in
     p.max_shift = aug->max_shift;
   }
   if (plan->engine == AFS_LOGMEL_ENGINE_TC) return logmel::tc_launch<S>(plan, p, aug != nullptr, stream);
-  if (plan->engine == AFS_LOGMEL_ENGINE_PAIR) return logmel::pair_launch<S>(plan, p, aug != nullptr, stream);
+  if (plan->engine == AFS_LOGMEL_ENGINE_PAIR || (plan->engine == AFS_LOGMEL_ENGINE_AUTO && aug == nullptr))
+    return logmel::pair_launch<S>(plan, p, aug != nullptr, stream);
   if (aug != nullptr) {
     logmel_kernel<true, S><<<g, kThreads, kSmemBytes, stream>>>(p);
   } else {

@@ -45,7 +45,7 @@ def _need_cuda(t, name, dtype=torch.float32):
 class LogMelPlan:
     """Owns an afs_logmel_plan (device tables: window, twiddles, packed mel bands)."""
 
-    ENGINES = {"fft": 0, "tc": 1, "pair": 2}
+    ENGINES = {"fft": 0, "tc": 1, "pair": 2, "auto": 3}
 
     def __init__(self, fb, window, hop, n_mels, center=True, log_mult=10.0, log_eps=2.220446049250313e-16,
                  device=None, engine=None):
@@ -67,12 +67,13 @@ class LogMelPlan:
         _lib.check(h.afs_logmel_plan_create(C.byref(self.cfg), fb.ctypes.data_as(C.c_void_p),
                                             window.ctypes.data_as(C.c_void_p), device.index,
                                             C.byref(self._handle)), "afs_logmel_plan_create")
-        self.engine = "fft"
+        self.engine = "auto"
         if engine is not None:
             self.set_engine(engine)
 
     def set_engine(self, engine):
-        """"fft": radix-8 FFT on the FMA pipe; "tc": four-step DFT on the tcgen05 tensor cores."""
+        """"pair": two frames per warp as one 1024-point complex FFT; "fft": one frame per 64 threads, radix-8; "tc":
+        four-step DFT on the tcgen05 tensor cores; "auto" (default): "pair", "fft" for augmented launches."""
         _lib.check(_lib.lib().afs_logmel_plan_set_engine(self._handle, self.ENGINES[engine]), "afs_logmel_plan_set_engine")
         self.engine = engine
 

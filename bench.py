@@ -594,7 +594,8 @@ def run_eval(args, rank, world, local_rank):
                     "logmel": {"ms_per_launch": lm1, "achieved": ach1, "unit": "GB/s", "frac": ach1 / hbm_peak,
                                "bytes_per_launch": LOGMEL_BYTES_PER_CLIP_S1 * n_clips,
                                "note": "10x frame overlap: 2.8x fewer algorithmic bytes per frame than S5, the same "
-                                       "FFT work -- the kernel is instruction-bound, the HBM fraction follows"}}
+                                       "FFT work per frame -- the kernel is bound by the FMA pipe / shared-memory data "
+                                       "path, the HBM fraction follows"}}
 
     total_eps = args.steps * E * world
     if rank != 0:
@@ -618,7 +619,7 @@ def run_eval(args, rank, world, local_rank):
         "backbone": "Conv64F eval path: tcgen05 TF32 kernels for block 1 (conv+BN+ReLU+pool) and blocks 2-3 "
                     "(implicit GEMM+BN+ReLU+pool), cuDNN conv+bias+ReLU for block 4 (TF32 allowed, the "
                     "reference's PyTorch default)",
-        "logmel_engine": front.plan().engine,
+        "logmel_engine": "pair" if front.plan().engine == "auto" else front.plan().engine,
         "e2e_path": "EpisodePipeline.stream: H2D on a copy stream overlapped with compute, 3 device buffers",
         "l2_policy": "inputs larger than L2: %d MB of waveform per step, two rotating batches" % (wav_bytes // 2 ** 20),
         "parallelism": "episodes sharded over %d rank(s), no data-path collective; timing: barrier + 1-double MAX "
@@ -637,7 +638,8 @@ def run_eval(args, rank, world, local_rank):
                 "note": "h2d_probe = plain pinned cudaMemcpyAsync of the same buffers by all %d rank(s) at once "
                         "(slowest rank); the e2e leg is bound by that copy, not by the 3.2 ms of device work" % world},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "logmel_kernel<false, float> (fused waveform->log-mel, FFT engine)", "bound": "hbm",
+        "roofline": {"kernel": "logmel_pair_kernel<false, float, true> (fused waveform->log-mel, warp-per-frame-pair engine)",
+                     "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "traffic_source": traffic_src, "co_limits": colimit,
                      "peak_source": peak_src, "bytes_per_launch": LOGMEL_BYTES_PER_CLIP * n_clips,

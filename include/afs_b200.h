@@ -89,14 +89,20 @@ typedef struct afs_logmel_plan afs_logmel_plan; /* opaque; owns device tables */
 int afs_logmel_plan_create(const afs_logmel_cfg* cfg, const float* fb_host,
                            const float* window_host, int device, afs_logmel_plan** plan_out);
 int afs_logmel_plan_destroy(afs_logmel_plan* plan);
-/* Two engines compute the same features (both within the 1e-4 dB tolerance of the float64 spec):
- *   AFS_LOGMEL_ENGINE_FFT  radix-8 FFT in registers on the FMA pipe (packed-f32x2 arithmetic), csrc/logmel.cu
- *   AFS_LOGMEL_ENGINE_TC   four-step 32x32 DFT as tcgen05 GEMMs (fp16 hi/lo operand pairs, fp32 accumulators in
- *                          tensor memory), csrc/logmel_tc.cu
+/* Three engines compute the same features (each within the 1e-4 dB tolerance of the float64 spec):
+ *   AFS_LOGMEL_ENGINE_FFT   one frame per 64 threads: 512-point complex radix-8 FFT in registers on the FMA pipe
+ *                           (packed-f32x2 arithmetic), three shared-memory exchanges per frame, csrc/logmel.cu
+ *   AFS_LOGMEL_ENGINE_TC    four-step 32x32 DFT as tcgen05 GEMMs (fp16 hi/lo operand pairs, fp32 accumulators in
+ *                           tensor memory), csrc/logmel_tc.cu
+ *   AFS_LOGMEL_ENGINE_PAIR  two frames per warp as ONE 1024-point complex FFT (32 x 32 in registers): one exchange per
+ *                           frame pair, in-warp shuffle split, csrc/logmel_pair.cu -- the fastest for plain launches
+ *   AFS_LOGMEL_ENGINE_AUTO  (default) PAIR, except FFT when waveform augmentation is requested (its Philox draws are
+ *                           shared by sample pairs there)
  * AFS_ERR_UNSUPPORTED when the plan cannot run the requested engine.                                       */
 #define AFS_LOGMEL_ENGINE_FFT 0
 #define AFS_LOGMEL_ENGINE_TC 1
 #define AFS_LOGMEL_ENGINE_PAIR 2
+#define AFS_LOGMEL_ENGINE_AUTO 3
 int afs_logmel_plan_set_engine(afs_logmel_plan* plan, int32_t engine);
 /* number of output frames for clips of L samples */
 int afs_logmel_num_frames(const afs_logmel_plan* plan, int64_t L);
