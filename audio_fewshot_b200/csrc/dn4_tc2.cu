@@ -18,9 +18,13 @@
 // Two operand schedules, one kernel (template flag KSTREAM):
 //   C <= 128 (Conv64F maps): the 128 query rows of a tile stay resident for all C channels while the support
 //            tiles stream through two whole-K stages;
-//   C  > 128 (ResNet-12 maps, C = 640: a 12.4 GFLOP GEMM per 5w5s episode): a 6-stage ring of
-//            [A slice | B slice] pairs of 32 channels each (32 KB per stage) feeds the K loop; the accumulator is
-//            committed to the epilogue after the last slice.
+//   C  > 128 (ResNet-12 maps, C = 640: an 8.3 GFLOP GEMM per 5w5s10q episode): a 3-stage ring of
+//            [A slice | B slice x 3] groups of 32 channels (64 KB per stage) feeds the K loop: ONE query slice serves the
+//            (up to) three column tiles of a class, which accumulate side by side in three of FOUR 128-column TMEM
+//            accumulators (the fourth lets the next item start while the epilogue drains) -- 16 KB of operands per MMA
+//            quartet instead of 32 KB: the round-1 schedule re-streamed both operands per 128 x 128 tile and sat at the
+//            per-SM L2 bandwidth (157 clk per M128 N128 K8 MMA against 65 for the MMA itself).  Work items are
+//            (row tile, class) pairs dealt over a persistent grid of ~148 CTAs.
 // Built for C % 32 == 0 (one 128-byte swizzle atom per 32 channels); other widths use dn4_tc.cu (C % 8 == 0) or
 // the fp32 path dn4.cu.
 #include <cuda.h>
@@ -73,14 +77,46 @@ bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint32_t C) {
 
 constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((kCols2 >> 3) << 17) | ((kRows2 >> 4) << 24);
 
-// ---- pre-pass: normalise, round to TF32, write K-major; queries compacted in output-row order
-__global__ void __launch_bounds__(128)
-dn4_tc_prep_kernel(const float* __restrict__ feat, const int32_t* __restrict__ cls_row, int64_t n_desc, int EW, int S,
-                   int C, int HW, float* __restrict__ nfq, float* __restrict__ nfs) {
-  const int64_t gid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (gid >= n_desc) return;
-  const int64_t row = gid / HW;
-  const int m = static_cast<int>(gid - row * HW);
+// ---- pre-pass: normalise, round to TF32, write K-major; queries compacted in output-row order.
+// A transpose through shared memory: a CTA owns kPrepPos positions of one image, warp w reads channels w, w + 8, ...
+// (a lane = a position: 128-byte coalesced reads of the NCHW map), keeps the tile [C][33] on chip while the per-position
+// sums of squares are reduced, then writes each position's C channels as one contiguous run (the round-1 kernel had a
+// thread per descriptor writing 16-byte pieces C floats apart: 169 us for 300 maps of [640, 8, 9]; this one ~25 us).
+constexpr int kPrepPos = 32;
+constexpr int kPrepThreads = 256;
+constexpr int kPrepPitch = kPrepPos + 1;
+
+__global__ void __launch_bounds__(kPrepThreads)
+dn4_tc_prep_kernel(const float* __restrict__ feat, const int32_t* __restrict__ cls_row, int EW, int S, int C, int HW,
+                   float* __restrict__ nfq, float* __restrict__ nfs) {
+  extern __shared__ float s_tile[];            // [C][kPrepPitch]
+  __shared__ float s_part[kPrepThreads / 32][kPrepPos];
+  __shared__ float s_inv[kPrepPos];
+  const int64_t row = blockIdx.x;
+  const int per = (HW + gridDim.y - 1) / gridDim.y;  // positions per CTA (<= kPrepPos): HW = 72 -> 3 x 24
+  const int m0 = blockIdx.y * per;
+  const int np = min(per, HW - m0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kPrepThreads / 32;
+
+  const float* src = feat + row * static_cast<int64_t>(C) * HW + m0;
+  float ss = 0.f;
+#pragma unroll 8
+  for (int c = warp; c < C; c += kWarps) {
+    const float v = lane < np ? __ldg(src + static_cast<int64_t>(c) * HW + lane) : 0.f;
+    s_tile[c * kPrepPitch + lane] = v;
+    ss = fmaf(v, v, ss);
+  }
+  s_part[warp][lane] = ss;
+  __syncthreads();
+  if (tid < kPrepPos) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += s_part[w][tid];
+    s_inv[tid] = 1.0f / fmaxf(sqrtf(t), 1e-12f);  // F.normalize: x / max(||x||, eps)
+  }
+  __syncthreads();
+
   int lo = 0, hi = EW - 1;  // block g with cls_row[g] <= row < cls_row[g+1]
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -88,32 +124,27 @@ dn4_tc_prep_kernel(const float* __restrict__ feat, const int32_t* __restrict__ c
   }
   const int g = lo;
   const int pos = static_cast<int>(row - cls_row[g]);
-  float* dst = pos < S ? nfs + ((static_cast<int64_t>(g) * S + pos) * HW + m) * C
-                       : nfq + ((row - static_cast<int64_t>(g + 1) * S) * HW + m) * C;
-  const float* src = feat + row * C * HW + m;
-  float ss = 0.f;
-  for (int c = 0; c < C; ++c) {
-    const float v = __ldg(src + static_cast<int64_t>(c) * HW);
-    ss = fmaf(v, v, ss);
-  }
-  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
-  for (int c = 0; c < C; c += 4) {
-    float4 v;
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(__ldg(src + static_cast<int64_t>(c + 0) * HW) * inv)); v.x = __uint_as_float(r);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(__ldg(src + static_cast<int64_t>(c + 1) * HW) * inv)); v.y = __uint_as_float(r);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(__ldg(src + static_cast<int64_t>(c + 2) * HW) * inv)); v.z = __uint_as_float(r);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(__ldg(src + static_cast<int64_t>(c + 3) * HW) * inv)); v.w = __uint_as_float(r);
-    *reinterpret_cast<float4*>(dst + c) = v;
+  float* dst = pos < S ? nfs + ((static_cast<int64_t>(g) * S + pos) * HW + m0) * C
+                       : nfq + ((row - static_cast<int64_t>(g + 1) * S) * HW + m0) * C;
+  for (int p = warp; p < np; p += kWarps) {
+    const float inv = s_inv[p];
+    float* d = dst + static_cast<int64_t>(p) * C;
+    for (int c = lane; c < C; c += 32) {
+      uint32_t r;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(s_tile[c * kPrepPitch + p] * inv));
+      d[c] = __uint_as_float(r);
+    }
   }
 }
 
-constexpr int kStgK = 6;  // ring stages of the K-streaming schedule
+constexpr int kStgK = 3;   // ring stages of the K-streaming schedule
+constexpr int kGrpK = 3;   // column tiles (accumulators) that share one query slice
+constexpr uint32_t kStageK = (1u + kGrpK) * kAtomBytes;
 
 struct Bars {
   uint64_t full_a, empty_a;
   uint64_t full_b[2], empty_b[2];
-  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t tmem_full[4], tmem_empty[4];
   uint64_t full_k[kStgK], empty_k[kStgK];
 };
 
@@ -147,6 +178,8 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bars.full_b[s]), 1);
       mbar_init(smem_u32(&bars.empty_b[s]), 1);
+    }
+    for (int s = 0; s < 4; ++s) {
       mbar_init(smem_u32(&bars.tmem_full[s]), 1);
       mbar_init(smem_u32(&bars.tmem_empty[s]), 4);  // one arrival per epilogue warp
     }
@@ -156,8 +189,11 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {  // two 128-column accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(256u));
+  constexpr uint32_t kTmemCols = KSTREAM ? 512u : 256u;  // four / two 128-column accumulators
+  constexpr uint32_t kAccMask = KSTREAM ? 3u : 1u;
+  constexpr uint32_t kAccShift = KSTREAM ? 2u : 1u;
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -171,24 +207,26 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   const int n_rows = (out1 - out0) * HW;
   const int n_tiles = (n_rows + kRows2 - 1) / kRows2;
   const int n_ctiles = (NS + kCols2 - 1) / kCols2;
+  const int n_items = n_tiles * W;  // K-streaming schedule: (row tile, class) work items
 
   if (warp == 4) {
     // ================= TMA producer (one thread) =================
     if (KSTREAM && lane == 0) {
       uint32_t ks = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = item / W, w = item - tile * W;
         const int qrow0 = out0 * HW + tile * kRows2;
-        for (int w = 0; w < W; ++w) {
-          const int srow_base = (e * W + w) * S * HW;
-          for (int ct = 0; ct < n_ctiles; ++ct) {
-            for (int kh = 0; kh < KH; ++kh, ++ks) {
-              const uint32_t st = ks % kStgK, ph = (ks / kStgK) & 1u;
-              mbar_wait(smem_u32(&bars.empty_k[st]), ph ^ 1u);
-              mbar_expect_tx(smem_u32(&bars.full_k[st]), 2u * kAtomBytes);
-              const uint32_t sa = base + st * (2u * kAtomBytes);
-              tma_load_2d(sa, &map_q, kh * 32, qrow0, smem_u32(&bars.full_k[st]));
-              tma_load_2d(sa + kAtomBytes, &map_s, kh * 32, srow_base + ct * kCols2, smem_u32(&bars.full_k[st]));
-            }
+        const int srow_base = (e * W + w) * S * HW;
+        for (int cg0 = 0; cg0 < n_ctiles; cg0 += kGrpK) {
+          const int g = min(kGrpK, n_ctiles - cg0);
+          for (int kh = 0; kh < KH; ++kh, ++ks) {
+            const uint32_t st = ks % kStgK, ph = (ks / kStgK) & 1u;
+            mbar_wait(smem_u32(&bars.empty_k[st]), ph ^ 1u);
+            mbar_expect_tx(smem_u32(&bars.full_k[st]), (1u + static_cast<uint32_t>(g)) * kAtomBytes);
+            const uint32_t sa = base + st * kStageK;
+            tma_load_2d(sa, &map_q, kh * 32, qrow0, smem_u32(&bars.full_k[st]));
+            for (int c = 0; c < g; ++c)
+              tma_load_2d(sa + (1u + c) * kAtomBytes, &map_s, kh * 32, srow_base + (cg0 + c) * kCols2, smem_u32(&bars.full_k[st]));
           }
         }
       }
@@ -217,25 +255,30 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // ================= MMA issuer (one thread) =================
     if (KSTREAM && lane == 0) {
       uint32_t ks = 0, it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int w = 0; w < W; ++w) {
-          for (int ct = 0; ct < n_ctiles; ++ct, ++it) {
-            const uint32_t acc_st = it & 1u, aph = (it >> 1) & 1u;
-            mbar_wait(smem_u32(&bars.tmem_empty[acc_st]), aph ^ 1u);  // epilogue has drained this accumulator
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int cg0 = 0; cg0 < n_ctiles; cg0 += kGrpK) {
+          const int g = min(kGrpK, n_ctiles - cg0);
+          for (int kh = 0; kh < KH; ++kh, ++ks) {
+            const uint32_t st = ks % kStgK, ph = (ks / kStgK) & 1u;
+            mbar_wait(smem_u32(&bars.full_k[st]), ph);
             fence_after();
-            const uint32_t d_tmem = tmem_base + acc_st * kCols2;
-            for (int kh = 0; kh < KH; ++kh, ++ks) {
-              const uint32_t st = ks % kStgK, ph = (ks / kStgK) & 1u;
-              mbar_wait(smem_u32(&bars.full_k[st]), ph);
-              fence_after();
-              const uint32_t sa = base + st * (2u * kAtomBytes);
+            const uint32_t sa = base + st * kStageK;
+            for (int c = 0; c < g; ++c) {
+              const uint32_t acc = (it + c) & 3u;
+              if (kh == 0) {  // first touch of this accumulator: the epilogue must have drained its previous use
+                mbar_wait(smem_u32(&bars.tmem_empty[acc]), (((it + c) >> 2) & 1u) ^ 1u);
+                fence_after();
+              }
+              const uint32_t d_tmem = tmem_base + acc * kCols2;
+              const uint32_t sb = sa + (1u + c) * kAtomBytes;
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4)
-                mma_tf32(d_tmem, desc_sw128(sa + k4 * 32u), desc_sw128(sa + kAtomBytes + k4 * 32u), kIdesc2, (kh | k4) != 0);
-              commit(smem_u32(&bars.empty_k[st]));  // slice reusable once these MMAs have read it
+                mma_tf32(d_tmem, desc_sw128(sa + k4 * 32u), desc_sw128(sb + k4 * 32u), kIdesc2, (kh | k4) != 0);
             }
-            commit(smem_u32(&bars.tmem_full[acc_st]));  // all C channels accumulated: hand over to the epilogue
+            commit(smem_u32(&bars.empty_k[st]));  // slice group reusable once these MMAs have read it
           }
+          for (int c = 0; c < g; ++c) commit(smem_u32(&bars.tmem_full[(it + c) & 3u]));  // all C channels accumulated
+          it += g;
         }
       }
     } else if (lane == 0) {
@@ -275,87 +318,96 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // ================= epilogue warps 0..3: accumulator row == TMEM lane == tid =================
     uint32_t it = 0;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // one (row tile, class): running top-n_k of this thread's accumulator row over the class's column tiles
+    auto do_class = [&](int tile, int w) {
       const int dr = tile * kRows2 + tid;
       const bool live = dr < n_rows;
       const int o = out0 + dr / HW;
       const int m = dr - (dr / HW) * HW;
-      for (int w = 0; w < W; ++w) {
-        float tv[NK];
-        int ti[NK];
+      float tv[NK];
+      int ti[NK];
 #pragma unroll
-        for (int k = 0; k < NK; ++k) { tv[k] = -INFINITY; ti[k] = INT_MAX; }
-        for (int ct = 0; ct < n_ctiles; ++ct, ++it) {
-          const uint32_t st = it & 1u, ph = (it >> 1) & 1u;
-          mbar_wait(smem_u32(&bars.tmem_full[st]), ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          uint32_t tk[NK];
+      for (int k = 0; k < NK; ++k) { tv[k] = -INFINITY; ti[k] = INT_MAX; }
+      for (int ct = 0; ct < n_ctiles; ++ct, ++it) {
+        const uint32_t st = it & kAccMask, ph = (it >> kAccShift) & 1u;
+        mbar_wait(smem_u32(&bars.tmem_full[st]), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t tk[NK];
 #pragma unroll
-          for (int k = 0; k < NK; ++k) tk[k] = 0u;  // below every real key (keys of finite values are > 0)
-          const int valid = NS - ct * kCols2;   // columns of this tile that exist (>= kCols2 for full tiles)
+        for (int k = 0; k < NK; ++k) tk[k] = 0u;  // below every real key (keys of finite values are > 0)
+        const int valid = NS - ct * kCols2;   // columns of this tile that exist (>= kCols2 for full tiles)
 #pragma unroll 1
-          for (int c0 = 0; c0 < kCols2; c0 += 32) {
-            uint32_t v[32];
-            if (c0 >= valid) break;  // tile-uniform: nothing left in this column tile
-            tmem_ld32(t_row + st * kCols2 + static_cast<uint32_t>(c0), v);
-            if (c0 + 32 <= valid) {
+        for (int c0 = 0; c0 < kCols2; c0 += 32) {
+          uint32_t v[32];
+          if (c0 >= valid) break;  // tile-uniform: nothing left in this column tile
+          tmem_ld32(t_row + st * kCols2 + static_cast<uint32_t>(c0), v);
+          if (c0 + 32 <= valid) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) topk_push<NK>(tk, topk_key(v[j], c0 + j));
-            } else {
+            for (int j = 0; j < 32; ++j) topk_push<NK>(tk, topk_key(v[j], c0 + j));
+          } else {
 #pragma unroll
-              for (int g8 = 0; g8 < 4; ++g8) {  // boundary chunk: whole groups of 8 are skipped by a uniform branch
-                if (c0 + 8 * g8 < valid) {
+            for (int g8 = 0; g8 < 4; ++g8) {  // boundary chunk: whole groups of 8 are skipped by a uniform branch
+              if (c0 + 8 * g8 < valid) {
 #pragma unroll
-                  for (int j = 8 * g8; j < 8 * g8 + 8; ++j)
-                    if (c0 + j < valid) topk_push<NK>(tk, topk_key(v[j], c0 + j));
-                }
+                for (int j = 8 * g8; j < 8 * g8 + 8; ++j)
+                  if (c0 + j < valid) topk_push<NK>(tk, topk_key(v[j], c0 + j));
               }
             }
           }
-#pragma unroll
-          for (int k = 0; k < NK; ++k)
-            if (tk[k] != 0u) topk_merge<NK>(tv, ti, topk_key_value(tk[k]), ct * kCols2 + 127 - static_cast<int>(tk[k] & 127u));
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bars.tmem_empty[st]));
         }
-        if (live) {
-          float sum = 0.f;
 #pragma unroll
-          for (int k = 0; k < NK; ++k) sum += tv[k];
-          const int64_t rb = (static_cast<int64_t>(o) * W + w) * HW + m;
-          rowsum[rb] = sum;
-          if (topk_idx != nullptr) {
+        for (int k = 0; k < NK; ++k)
+          if (tk[k] != 0u) topk_merge<NK>(tv, ti, topk_key_value(tk[k]), ct * kCols2 + 127 - static_cast<int>(tk[k] & 127u));
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars.tmem_empty[st]));
+      }
+      if (live) {
+        float sum = 0.f;
 #pragma unroll
-            for (int k = 0; k < NK; ++k) topk_idx[rb * NK + k] = ti[k];
-          }
+        for (int k = 0; k < NK; ++k) sum += tv[k];
+        const int64_t rb = (static_cast<int64_t>(o) * W + w) * HW + m;
+        rowsum[rb] = sum;
+        if (topk_idx != nullptr) {
+#pragma unroll
+          for (int k = 0; k < NK; ++k) topk_idx[rb * NK + k] = ti[k];
         }
       }
+    };
+    if (KSTREAM) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) do_class(item / W, item % W);
+    } else {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int w = 0; w < W; ++w) do_class(tile, w);
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 5) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
 }
 
+// score[o, w] = sum over the HW descriptors of query o of their top-k sums: one warp per query, lanes stride the
+// positions, fixed-order shuffle reduction (deterministic); lane 0 takes the argmax over the classes.
 __global__ void __launch_bounds__(128)
 dn4_tc2_reduce_kernel(const float* __restrict__ rowsum, int NQ, int W, int HW, float* __restrict__ score,
                       int32_t* __restrict__ pred) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (o >= NQ) return;
   float best = -INFINITY;
   int best_w = 0;
   for (int w = 0; w < W; ++w) {
     const float* p = rowsum + (static_cast<int64_t>(o) * W + w) * HW;
     float s = 0.f;
-    for (int m = 0; m < HW; ++m) s += p[m];
-    score[static_cast<int64_t>(o) * W + w] = s;
+    for (int m = lane; m < HW; m += 32) s += p[m];
+    s = warp_sum(s);
+    if (lane == 0) score[static_cast<int64_t>(o) * W + w] = s;
     if (s > best) { best = s; best_w = w; }
   }
-  if (pred != nullptr) pred[o] = best_w;
+  if (pred != nullptr && lane == 0) pred[o] = best_w;
 }
 
 template <int NK, bool KSTREAM>
@@ -412,16 +464,28 @@ extern "C" int afs_dn4_fwd_tc2(const float* feat, const int32_t* cls_row, int32_
   CUtensorMap mq, ms;
   if (!make_map(&mq, nfq, q_rows, C) || !make_map(&ms, nfs, s_rows, C)) return AFS_ERR_UNSUPPORTED;
 
-  const int64_t n_desc = static_cast<int64_t>(N) * HW;
-  dn4_tc_prep_kernel<<<static_cast<unsigned>((n_desc + 127) / 128), 128, 0, stream>>>(feat, cls_row, n_desc, E * W, S, C,
-                                                                                     HW, nfq, nfs);
-  AFS_LAUNCH_CHECK();
+  {
+    const size_t prep_smem = static_cast<size_t>(C) * kPrepPitch * sizeof(float);
+    if (prep_smem > 200 * 1024 || (HW + kPrepPos - 1) / kPrepPos > 65535) return AFS_ERR_UNSUPPORTED;
+    if (prep_smem > 48 * 1024)
+      AFS_CUDA_TRY(cudaFuncSetAttribute(dn4_tc_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(prep_smem)));
+    const dim3 pgrid(N, (HW + kPrepPos - 1) / kPrepPos);
+    dn4_tc_prep_kernel<<<pgrid, kPrepThreads, prep_smem, stream>>>(feat, cls_row, E * W, S, C, HW, nfq, nfs);
+    AFS_LAUNCH_CHECK();
+  }
 
   const int64_t avg_rows = static_cast<int64_t>(NQ) * HW / E;
   int tiles = static_cast<int>((avg_rows + kRows2 - 1) / kRows2);
   if (tiles < 1) tiles = 1;
+  if (C > 128) {  // K-streaming: persistent CTAs over the (row tile, class) items of their episode, ~one CTA per SM in all
+    int per_episode = kNumSMs / E;
+    if (per_episode < 1) per_episode = 1;
+    if (per_episode > tiles * W) per_episode = tiles * W;
+    tiles = per_episode;
+  }
   const dim3 grid(tiles, 1, E);
-  const size_t smem = (C > 128 ? static_cast<size_t>(kStgK) * 2 : 3 * static_cast<size_t>(C / 32)) * kAtomBytes + 1024;
+  const size_t smem = (C > 128 ? static_cast<size_t>(kStgK) * (1 + kGrpK) : 3 * static_cast<size_t>(C / 32)) * kAtomBytes + 1024;
   cudaError_t err = cudaSuccess;
   switch (n_k) {
     case 1: err = launch_tc2<1>(grid, smem, stream, mq, ms, cls_row, W, S, C, HW, rowsum, topk_idx); break;
@@ -435,7 +499,7 @@ extern "C" int afs_dn4_fwd_tc2(const float* feat, const int32_t* cls_row, int32_
   }
   if (err != cudaSuccess) return cuda_fail(err);
   AFS_LAUNCH_CHECK();
-  dn4_tc2_reduce_kernel<<<(NQ + 127) / 128, 128, 0, stream>>>(rowsum, NQ, W, HW, score, pred);
+  dn4_tc2_reduce_kernel<<<(NQ + 3) / 4, 128, 0, stream>>>(rowsum, NQ, W, HW, score, pred);
   AFS_LAUNCH_CHECK();
   return AFS_OK;
 }
