@@ -15,8 +15,8 @@ Two execution paths with the same parameters:
     the [N,64,128,157] activation never reaches HBM); blocks 2-3 are ONE tcgen05 kernel each
     (csrc/conv3_tc.cu: TF32 implicit GEMM over shifted shared-memory views + folded BatchNorm + activation
     + max-pool) when TF32 convolutions are allowed, otherwise -- and block 4 always -- cuDNN's fused
-    conv+bias+ReLU on channels-last tensors with BatchNorm folded into the weights; BatchNorm1d is folded
-    into the final Linear.  In the reference's
+    conv+bias+ReLU on channels-last tensors with BatchNorm folded into the weights; the last max-pool, the
+    flatten and the final Linear (BatchNorm1d folded in) are ONE kernel (csrc/tail.cu).  In the reference's
     eager sequence those elementwise and layout kernels are 88 % of an evaluation step on B200
     (profiles/r01_bench_launches.csv).
 """
@@ -129,6 +129,8 @@ class Conv64F(nn.Module):
             if self.maxpool_last2:
                 h = ops.maxpool3_channels_last(h)
         h = self._conv_act(h, c["w4"], c["b4"], c["slope"])
+        if self.last_pool and self.is_flatten and ops.pool3_linear_supported(h, c["wl"].shape[0]):
+            return ops.pool3_linear(h, c["wl"], c["bl"])  # last max-pool + flatten + BatchNorm1d + Linear: one kernel
         if self.last_pool:
             h = ops.maxpool3_channels_last(h)
         if self.is_flatten:

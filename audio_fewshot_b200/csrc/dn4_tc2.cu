@@ -8,7 +8,9 @@
 //            boxes (128-byte rows, hardware 128B swizzle) and arms the stage's mbarrier with expect_tx;
 //   warp 5   MMA issuer: one thread waits for the operands, issues C/8 tcgen05.mma.kind::tf32 into one of
 //            two 128-column TMEM accumulators and commits to the "operands free" / "accumulator full"
-//            mbarriers; it also owns the TMEM allocation (256 columns);
+//            mbarriers; it also owns the TMEM allocation.  In the K-streaming schedule warps 5, 6, 7 each issue for
+//            ONE of the three accumulators of a class: a single thread needs ~180 clk per tcgen05.mma (descriptor
+//            arithmetic, predicate, issue latency) against 65 clk for the M128 N128 K8 MMA itself;
 //   warps 0-3 epilogue: thread i owns accumulator row i (TMEM lane i): tcgen05.ld, running top-n_k,
 //            then releases the accumulator stage.
 // Operands come from a small pre-pass (dn4_tc_prep_kernel) that writes the L2-normalised, TF32-rounded
@@ -40,7 +42,7 @@ namespace {
 using namespace tc;
 using namespace topk;
 
-constexpr int kThreads2 = 192;
+constexpr int kThreads2 = 256;  // warps 0-3 epilogue, 4 TMA producer, 5-7 MMA issuers (6, 7: K-streaming schedule only)
 constexpr int kRows2 = 128;   // UMMA M
 constexpr int kCols2 = 128;   // UMMA N
 constexpr int kMaxWay2 = 32;
@@ -100,14 +102,49 @@ dn4_tc_prep_kernel(const float* __restrict__ feat, const int32_t* __restrict__ c
   constexpr int kWarps = kPrepThreads / 32;
 
   const float* src = feat + row * static_cast<int64_t>(C) * HW + m0;
-  float ss = 0.f;
+  if ((np & 3) == 0 && (HW & 3) == 0 && (m0 & 3) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0) {
+    // 128-bit loads, all of a thread's loads in flight at once (a [640 x 24] slab is 15 per thread), then the sums of
+    // squares from shared memory: 8 partial sums per position
+    const int nq = np >> 2;
+    const int total = C * nq;
+    for (int i0 = tid; i0 < total; i0 += 8 * kPrepThreads) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * kPrepThreads;
+        if (i < total) {
+          const int c = i / nq, q = i - c * nq;
+          v[u] = __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(c) * HW) + q);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * kPrepThreads;
+        if (i < total) {
+          const int c = i / nq, q = i - c * nq;
+          float* d = s_tile + c * kPrepPitch + 4 * q;
+          d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+        }
+      }
+    }
+    __syncthreads();
+    float ss = 0.f;
+    if (lane < np)
+      for (int c = warp; c < C; c += kWarps) {
+        const float v = s_tile[c * kPrepPitch + lane];
+        ss = fmaf(v, v, ss);
+      }
+    s_part[warp][lane] = ss;
+  } else {
+    float ss = 0.f;
 #pragma unroll 8
-  for (int c = warp; c < C; c += kWarps) {
-    const float v = lane < np ? __ldg(src + static_cast<int64_t>(c) * HW + lane) : 0.f;
-    s_tile[c * kPrepPitch + lane] = v;
-    ss = fmaf(v, v, ss);
+    for (int c = warp; c < C; c += kWarps) {
+      const float v = lane < np ? __ldg(src + static_cast<int64_t>(c) * HW + lane) : 0.f;
+      s_tile[c * kPrepPitch + lane] = v;
+      ss = fmaf(v, v, ss);
+    }
+    s_part[warp][lane] = ss;
   }
-  s_part[warp][lane] = ss;
   __syncthreads();
   if (tid < kPrepPos) {
     float t = 0.f;
@@ -185,7 +222,7 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
     for (int s = 0; s < kStgK; ++s) {
       mbar_init(smem_u32(&bars.full_k[s]), 1);
-      mbar_init(smem_u32(&bars.empty_k[s]), 1);
+      mbar_init(smem_u32(&bars.empty_k[s]), kGrpK);  // one arrival per MMA-issuing warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -251,9 +288,10 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
       }
     }
-  } else if (warp == 5) {
-    // ================= MMA issuer (one thread) =================
+  } else if (warp >= 5) {
+    // ================= MMA issuers (one thread per warp) =================
     if (KSTREAM && lane == 0) {
+      const int c = warp - 5;  // this warp's accumulator within a group of column tiles
       uint32_t ks = 0, it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         for (int cg0 = 0; cg0 < n_ctiles; cg0 += kGrpK) {
@@ -262,26 +300,28 @@ dn4_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             const uint32_t st = ks % kStgK, ph = (ks / kStgK) & 1u;
             mbar_wait(smem_u32(&bars.full_k[st]), ph);
             fence_after();
-            const uint32_t sa = base + st * kStageK;
-            for (int c = 0; c < g; ++c) {
+            if (c < g) {
               const uint32_t acc = (it + c) & 3u;
               if (kh == 0) {  // first touch of this accumulator: the epilogue must have drained its previous use
                 mbar_wait(smem_u32(&bars.tmem_empty[acc]), (((it + c) >> 2) & 1u) ^ 1u);
                 fence_after();
               }
               const uint32_t d_tmem = tmem_base + acc * kCols2;
-              const uint32_t sb = sa + (1u + c) * kAtomBytes;
+              const uint32_t sa = base + st * kStageK;
+              const uint64_t da = desc_sw128(sa), db = desc_sw128(sa + (1u + c) * kAtomBytes);
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                mma_tf32(d_tmem, desc_sw128(sa + k4 * 32u), desc_sw128(sb + k4 * 32u), kIdesc2, (kh | k4) != 0);
+              for (int k4 = 0; k4 < 4; ++k4)  // +32 bytes inside the swizzle atom = +2 in the descriptor's address field
+                mma_tf32(d_tmem, da + 2u * k4, db + 2u * k4, kIdesc2, (kh | k4) != 0);
+              commit(smem_u32(&bars.empty_k[st]));  // slice group reusable once these MMAs have read it
+            } else {
+              mbar_arrive(smem_u32(&bars.empty_k[st]));
             }
-            commit(smem_u32(&bars.empty_k[st]));  // slice group reusable once these MMAs have read it
           }
-          for (int c = 0; c < g; ++c) commit(smem_u32(&bars.tmem_full[(it + c) & 3u]));  // all C channels accumulated
+          if (c < g) commit(smem_u32(&bars.tmem_full[(it + c) & 3u]));  // all C channels accumulated
           it += g;
         }
       }
-    } else if (lane == 0) {
+    } else if (warp == 5 && lane == 0) {
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
         mbar_wait(smem_u32(&bars.full_a), tcount & 1u);

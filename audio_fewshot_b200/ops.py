@@ -272,6 +272,28 @@ def maxpool3_channels_last(x):
     return out
 
 
+def pool3_linear_supported(x, out_features):
+    """The fused tail needs 64 channels, a pooled map of one pixel and a multiple of 8 outputs."""
+    return (x.dim() == 4 and x.shape[1] == 64 and x.shape[2] // 3 == 1 and x.shape[3] // 3 == 1 and out_features % 8 == 0)
+
+
+def pool3_linear(x, weight, bias):
+    """MaxPool2d(3, 3) -> flatten -> Linear of a channels_last [N, 64, H, W] CUDA tensor with 3 <= H, W < 6:
+    out [N, J] = bias + pooled @ weight.T, weight [J, 64] (BatchNorm1d folded in by the caller)."""
+    _need_cuda(x, "x")
+    _need_cuda(weight, "weight")
+    _need_cuda(bias, "bias")
+    if not pool3_linear_supported(x, weight.shape[0]) or tuple(weight.shape[1:]) != (64,) or bias.numel() != weight.shape[0]:
+        raise ValueError("pool3_linear: x must be [N, 64, H, W] with H // 3 == W // 3 == 1, weight [J, 64], J % 8 == 0")
+    x = x.contiguous(memory_format=torch.channels_last)
+    N, _, H, Wd = x.shape
+    J = weight.shape[0]
+    out = torch.empty((N, J), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().afs_pool3_linear_fwd(_ptr(x), N, H, Wd, 64, _ptr(weight.contiguous()), _ptr(bias.contiguous()),
+                                               J, _ptr(out), _stream()), "afs_pool3_linear_fwd")
+    return out
+
+
 def add_bias_act_pool(a, b=None, bias=None, negative_slope=0.0, k=1, inplace=False):
     """MaxPool2d(k)(LeakyReLU(a + b + bias[c])) on channels_last [N, C, H, W] CUDA tensors (b, bias optional;
     k in {1, 2, 3}).  inplace=True (k == 1 only) writes into `a`."""

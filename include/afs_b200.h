@@ -196,6 +196,15 @@ int afs_conv3x3_c64_bn_act_fwd_tf32(const float* x, int32_t N, int32_t H, int32_
 int afs_maxpool3_nhwc_fwd(const float* x, int32_t N, int32_t H, int32_t W, int32_t C, float* out,
                           afs_stream_t stream);
 
+/* (1c') The last max-pool of Conv64F fused with its linear head, inference path: x [N, H, W, C = 64] channels-last
+ * (the output of block 4), 3 <= H, W < 6 so that MaxPool2d(3, 3) leaves one pixel; out[n, j] = bl[j] + sum_c
+ * max_{3x3}(x[n, :, :, c]) * wl[j, c], wl [J, 64] row-major and bl [J] with BatchNorm1d already folded in, J % 8 == 0,
+ * all pointers device, 16-byte aligned; fp32 FMA, channels summed in ascending order.  Replaces layer4_pool, the
+ * flatten and `logits` (BatchNorm1d + Linear) of libfewshot_core/model/backbone/conv_four.py:84,89-92,120-123 in
+ * eval mode.  AFS_ERR_UNSUPPORTED for other shapes (the caller keeps the pool + GEMM sequence).                  */
+int afs_pool3_linear_fwd(const float* x, int32_t N, int32_t H, int32_t W, int32_t C, const float* wl, const float* bl,
+                         int32_t J, float* out, afs_stream_t stream);
+
 /* (1d) Tail of a ResNet-12 BasicBlock on the inference path, channels-last, BatchNorms folded into the
  * convolutions: out = MaxPool2d(k)( LeakyReLU_slope( a + b + bias[c] ) ), k in {1,2,3} (floor mode).
  * a, b [N, H, W, C] (b nullable), bias [C] (nullable), out [N, H/k, W/k, C]; fp32, C % 4 == 0, 16-byte aligned.

@@ -705,3 +705,23 @@ def test_tcgen05_kernels_repeat_bit_identically(cuda):
     ref3 = ops.conv3x3_c64_bn_act(a, packed, b3, 0.0, pool=True)
     for _ in range(4):
         assert torch.equal(ops.conv3x3_c64_bn_act(a, packed, b3, 0.0, pool=True), ref3)
+
+
+@pytest.mark.parametrize("N,H,W,J", [(3200, 4, 5, 1600), (70, 3, 3, 8), (1, 5, 5, 136)])
+def test_pool3_linear_matches_pool_and_addmm(cuda, N, H, W, J):
+    """csrc/tail.cu: last max-pool + flatten + Linear of Conv64F (conv_four.py:84,89-92) in one kernel, against
+    F.max_pool2d + an fp64 matmul (fp32 FMA over 64 channels: 1e-5 of the output range)."""
+    from audio_fewshot_b200 import ops
+    g = torch.Generator().manual_seed(N + J)
+    x = torch.randn(N, 64, H, W, generator=g).to(cuda).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(J, 64, generator=g) * 0.1).to(cuda)
+    b = torch.randn(J, generator=g).to(cuda)
+    got = ops.pool3_linear(x, w, b)
+    pooled = torch.nn.functional.max_pool2d(x, 3, 3).reshape(N, 64).double()
+    want = pooled @ w.double().t() + b.double()
+    assert got.shape == (N, J)
+    assert (got.double() - want).abs().max().item() < 1e-5 * want.abs().max().item()
+    assert torch.equal(got, ops.pool3_linear(x, w, b))
+    assert not ops.pool3_linear_supported(torch.empty(1, 64, 6, 5), 1600)  # pooled map larger than one pixel
+    with pytest.raises(ValueError):
+        ops.pool3_linear(torch.zeros(2, 32, 4, 5, device=cuda), w, b)
