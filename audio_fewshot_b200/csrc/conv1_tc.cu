@@ -42,10 +42,11 @@ constexpr int kPix1 = 128;                 // pooled pixels per tile
 constexpr int kCh1 = 64;                   // output channels == UMMA N
 constexpr int kThreads1 = 32 * 13;         // 4 BUILD + 8 EPI + 1 MMA warps
 constexpr int kMmaWarp1 = 12;
-constexpr uint32_t kWinBytes = 4u * kPix1 * 16u;      // one window's P_d: [4 chunks][128 rows][16 B] = 8 KB
-constexpr uint32_t kTileBytes = 9u * kWinBytes;       // nine windows: 72 KB
-constexpr uint32_t kWBytes = 4u * kCh1 * 16u;         // Wf: [4 chunks][64 rows][16 B] = 4 KB
-constexpr uint32_t kAccCols = 3u * kCh1;              // one window row: three accumulators
+constexpr int kNBuf1 = 4;                             // operand buffers (tiles BUILD may run ahead of the tensor core)
+constexpr uint32_t kWinBytes = 4u * kPix1 * 16u;      // one window ROW's P_g: [4 chunks][128 rows][16 B] = 8 KB
+constexpr uint32_t kTileBytes = 3u * kWinBytes;       // three window rows: 24 KB
+constexpr uint32_t kAccCols = 3u * kCh1;              // one window row: three accumulators side by side = UMMA N
+constexpr uint32_t kWBytes = 4u * kAccCols * 16u;     // Wf: [4 chunks][192 rows][16 B] = 12 KB
 constexpr int kStagePitch = 36;                       // floats per staged pixel row (32 channels + 4: conflict-free)
 constexpr uint32_t kStageBytes = 32u * kStagePitch * 4u;  // per EPI warp
 constexpr uint32_t kTmemCols1 = 512;
@@ -55,13 +56,13 @@ struct Conv1TcParams {
   float shift[kCh1];
 };
 
-enum { kAFull = 0, kAEmpty = 2, kAccFull = 4, kAccEmpty = 6, kBars1 = 8 };
+enum { kAFull = 0, kAEmpty = kNBuf1, kAccFull = 2 * kNBuf1, kAccEmpty = 2 * kNBuf1 + 2, kBars1 = 2 * kNBuf1 + 4 };
 
 template <bool LEAKY>
 __global__ void __launch_bounds__(kThreads1, 1)
 conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, int PH, int PW, float slope,
                 float* __restrict__ out, const __grid_constant__ Conv1TcParams prm) {
-  extern __shared__ __align__(128) uint8_t s_buf[];  // [2][kTileBytes] im2col | [kWBytes] weights | [8][kStageBytes] output staging
+  extern __shared__ __align__(128) uint8_t s_buf[];  // [kNBuf1][kTileBytes] patches | [kWBytes] weights | [8][kStageBytes] output staging
   __shared__ __align__(8) uint64_t s_bars[kBars1];
   __shared__ uint32_t s_tmem;
   __shared__ float s_shift[kCh1];
@@ -69,30 +70,31 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const uint32_t a_base = smem_u32(s_buf);
-  const uint32_t w_base = a_base + 2u * kTileBytes;
+  const uint32_t w_base = a_base + kNBuf1 * kTileBytes;
   if (tid < kCh1) s_shift[tid] = prm.shift[tid];
   const uint32_t bars = smem_u32(s_bars);
 #define BAR1(id) (bars + 8u * static_cast<uint32_t>(id))
 
-  // folded weights -> K-major operand [chunk][channel][4 taps], TF32-rounded; taps 9..15 are zero
-  for (int i = tid; i < 4 * kCh1; i += kThreads1) {
-    const int chunk = i / kCh1, c = i - chunk * kCh1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (chunk == 0) v = make_float4(to_tf32(prm.w[c * 9 + 0]), to_tf32(prm.w[c * 9 + 1]), to_tf32(prm.w[c * 9 + 2]), to_tf32(prm.w[c * 9 + 3]));
-    if (chunk == 1) v = make_float4(to_tf32(prm.w[c * 9 + 4]), to_tf32(prm.w[c * 9 + 5]), to_tf32(prm.w[c * 9 + 6]), to_tf32(prm.w[c * 9 + 7]));
-    if (chunk == 2) v.x = to_tf32(prm.w[c * 9 + 8]);
-    reinterpret_cast<float4*>(s_buf + 2u * kTileBytes)[i] = v;
-  }
-  // the all-zero fourth chunk of every window never changes
-  for (int i = tid; i < 2 * 9 * kPix1; i += kThreads1) {
-    const int win = i / kPix1, r = i - win * kPix1;
-    reinterpret_cast<float4*>(s_buf + win * kWinBytes)[3 * kPix1 + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // folded weights -> K-major operand [chunk][n = 64 dx + channel][4 K values], TF32-rounded.  K index 5 r + c is
+  // patch row r (0..2, relative to the window row) and patch column c (0..4); window column dx sees tap (r, c - dx).
+  for (int i = tid; i < 4 * static_cast<int>(kAccCols); i += kThreads1) {
+    const int chunk = i / static_cast<int>(kAccCols), n = i - chunk * static_cast<int>(kAccCols);
+    const int dx = n / kCh1, c = n - dx * kCh1;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 4 * chunk + j, r = k / 5, kx = k - 5 * r - dx;
+      v[j] = (k < 15 && kx >= 0 && kx < 3) ? to_tf32(prm.w[c * 9 + r * 3 + kx]) : 0.f;
+    }
+    reinterpret_cast<float4*>(s_buf + kNBuf1 * kTileBytes)[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
   if (warp == 0) tmem_alloc(&s_tmem, kTmemCols1);
   if (tid == 32) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kNBuf1; ++s) {
       mbar_init(BAR1(kAFull + s), kPix1);
       mbar_init(BAR1(kAEmpty + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(BAR1(kAccFull + s), 1);
       mbar_init(BAR1(kAccEmpty + s), 256);
     }
@@ -115,8 +117,16 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
       const int64_t tile = blockIdx.x + it * gridDim.x;
       int64_t pix = tile * kPix1 + tid;
       if (pix >= total_pix) pix = total_pix - 1;  // tail rows recompute the last pixel; never stored
-      const int64_t n = pix / per;
-      const uint32_t r = static_cast<uint32_t>(pix - n * per);
+      int64_t n;
+      uint32_t r;
+      if (total_pix <= 0x7fffffffLL) {  // the usual case: 32-bit division
+        const uint32_t n32 = static_cast<uint32_t>(pix) / per;
+        n = n32;
+        r = static_cast<uint32_t>(pix) - n32 * per;
+      } else {
+        n = pix / per;
+        r = static_cast<uint32_t>(pix - n * per);
+      }
       const uint32_t ph = r / static_cast<uint32_t>(PW), pw = r - ph * static_cast<uint32_t>(PW);
       const int y0 = 3 * static_cast<int>(ph) - 1, x0 = 3 * static_cast<int>(pw) - 1;
       // validity of the five rows / columns as bit masks: only the first and the last can fall outside (H, Wd >= 3)
@@ -132,24 +142,22 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
     };
     if (my_tiles > 0) load_patch(0);
     for (int64_t it = 0; it < my_tiles; ++it) {
-      const uint32_t st = static_cast<uint32_t>(it & 1), par = static_cast<uint32_t>((it >> 1) & 1);
+      const uint32_t st = static_cast<uint32_t>(it % kNBuf1), par = static_cast<uint32_t>((it / kNBuf1) & 1);
       float p[5][5];
 #pragma unroll
       for (int i = 0; i < 5; ++i)
 #pragma unroll
         for (int j = 0; j < 5; ++j) p[i][j] = to_tf32(pn[i][j]);
       if (it + 1 < my_tiles) load_patch(it + 1);  // in flight while this tile is written
-      mbar_wait_warp_sleep(BAR1(kAEmpty + st), par ^ 1u, lane);  // the 18 MMAs that read this buffer have completed
+      mbar_wait_warp_sleep(BAR1(kAEmpty + st), par ^ 1u, lane);  // the 6 MMAs that read this buffer have completed
       float4* dst = reinterpret_cast<float4*>(s_buf + st * kTileBytes) + tid;
 #pragma unroll
-      for (int g = 0; g < 3; ++g) {
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          float4* row = dst + (3 * g + dx) * (4 * kPix1);
-          row[0 * kPix1] = make_float4(p[g][dx], p[g][dx + 1], p[g][dx + 2], p[g + 1][dx]);
-          row[1 * kPix1] = make_float4(p[g + 1][dx + 1], p[g + 1][dx + 2], p[g + 2][dx], p[g + 2][dx + 1]);
-          row[2 * kPix1] = make_float4(p[g + 2][dx + 2], 0.f, 0.f, 0.f);
-        }
+      for (int g = 0; g < 3; ++g) {  // window row g: patch rows g..g+2, all five columns, K index 5 r + c, K 15 = 0
+        float4* row = dst + g * (4 * kPix1);
+        row[0 * kPix1] = make_float4(p[g][0], p[g][1], p[g][2], p[g][3]);
+        row[1 * kPix1] = make_float4(p[g][4], p[g + 1][0], p[g + 1][1], p[g + 1][2]);
+        row[2 * kPix1] = make_float4(p[g + 1][3], p[g + 1][4], p[g + 2][0], p[g + 2][1]);
+        row[3 * kPix1] = make_float4(p[g + 2][2], p[g + 2][3], p[g + 2][4], 0.f);
       }
       fence_async_smem();
       mbar_arrive(BAR1(kAFull + st));
@@ -157,12 +165,12 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
   } else if (warp == kMmaWarp1) {
     // =========================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t kIdesc = idesc_tf32(kPix1, kCh1);
+      constexpr uint32_t kIdesc = idesc_tf32(kPix1, static_cast<int>(kAccCols));
       const uint64_t dA = desc_kmajor_noswizzle(a_base, 16u * kPix1, 128u);
-      const uint64_t dB = desc_kmajor_noswizzle(w_base, 16u * kCh1, 128u);
+      const uint64_t dB = desc_kmajor_noswizzle(w_base, 16u * kAccCols, 128u);
       uint32_t r = 0;  // running window-row counter: accumulator set r & 1
       for (int64_t it = 0; it < my_tiles; ++it) {
-        const uint32_t st = static_cast<uint32_t>(it & 1), par = static_cast<uint32_t>((it >> 1) & 1);
+        const uint32_t st = static_cast<uint32_t>(it % kNBuf1), par = static_cast<uint32_t>((it / kNBuf1) & 1);
         mbar_wait_sleep(BAR1(kAFull + st), par);
 #pragma unroll
         for (int g = 0; g < 3; ++g, ++r) {
@@ -170,13 +178,10 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
           mbar_wait_sleep(BAR1(kAccEmpty + as), ((r >> 1) & 1u) ^ 1u);
           fence_after();
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-            for (int k8 = 0; k8 < 2; ++k8) {
-              const uint64_t da = dA + ((st * kTileBytes + (3u * g + dx) * kWinBytes + k8 * 2u * (16u * kPix1)) >> 4);
-              const uint64_t db = dB + ((k8 * 2u * (16u * kCh1)) >> 4);
-              mma_tf32(tmem_base + as * kAccCols + dx * kCh1, da, db, kIdesc, k8 > 0);
-            }
+          for (int k8 = 0; k8 < 2; ++k8) {
+            const uint64_t da = dA + ((st * kTileBytes + g * kWinBytes + k8 * 2u * (16u * kPix1)) >> 4);
+            const uint64_t db = dB + ((k8 * 2u * (16u * kAccCols)) >> 4);
+            mma_tf32(tmem_base + as * kAccCols, da, db, kIdesc, k8 > 0);
           }
           commit(BAR1(kAccFull + as));
         }
@@ -188,7 +193,7 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
     const int e = warp - 4;
     const int half = e >> 2;  // channels 32 half .. 32 half + 31; TMEM lane quadrant = warp & 3 = e & 3
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 32u * half;
-    float* stage = reinterpret_cast<float*>(s_buf + 2u * kTileBytes + kWBytes + static_cast<uint32_t>(e) * kStageBytes);
+    float* stage = reinterpret_cast<float*>(s_buf + kNBuf1 * kTileBytes + kWBytes + static_cast<uint32_t>(e) * kStageBytes);
     uint32_t r = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
       float best[32];
@@ -263,7 +268,7 @@ extern "C" int afs_conv1_bn_act_pool3_fwd_tf32(const float* x, int32_t N, int32_
   for (int i = 0; i < kCh1 * 9; ++i) prm.w[i] = w_folded_host[i];
   for (int i = 0; i < kCh1; ++i) prm.shift[i] = shift_host[i];
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const size_t smem = 2 * kTileBytes + kWBytes + 8 * kStageBytes;
+  const size_t smem = kNBuf1 * kTileBytes + kWBytes + 8 * kStageBytes;
   int64_t blocks = n_tiles < kNumSMs ? n_tiles : kNumSMs;  // persistent: one CTA per SM
   if (negative_slope >= 1.f) return AFS_ERR_UNSUPPORTED;  // the activation is max(v, slope v)
   if (negative_slope > 0.f) {
