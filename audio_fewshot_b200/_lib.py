@@ -82,6 +82,12 @@ SIGNATURES = {
     "afs_conv3x3_c64_pack_weights": (C.c_int, [C.c_void_p, C.c_void_p]),
     "afs_conv3x3_c64_bn_act_fwd_tf32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                                   C.c_float, C.c_int32, C.c_void_p, C.c_void_p]),
+    "afs_conv3x3_c64_packed_bf16_elems": (C.c_size_t, []),
+    "afs_conv3x3_c64_pack_weights_bf16": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "afs_conv3x3_c64_bn_act_fwd_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                                  C.c_float, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "afs_conv1_bn_act_pool3_fwd_tf32_bf16out": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                                          C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "afs_pool3_linear_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_int32, C.c_void_p, C.c_void_p]),
     "afs_maxpool3_nhwc_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

@@ -52,6 +52,10 @@ class Conv64F(nn.Module):
         self.last_pool, self.maxpool_last2 = last_pool, maxpool_last2
         self.stem_tf32 = None  # None: follow torch.backends.cudnn.allow_tf32
         self.block_tc = None   # tcgen05 kernel for blocks 2-3; None: follow torch.backends.cudnn.allow_tf32
+        # "bf16": the separately stated reduced-precision inference path -- the stem writes bf16, blocks 2-3 run as
+        # bf16 tcgen05 MMAs (K = 16) with fp32 accumulation; block 4, the Linear and the head stay as they are.
+        # Not the parity path (logits move by ~1e-2 relative); None / "tf32": the reference's precision class.
+        self.precision = None
         self.fused_train_stem = True  # training: block 1 forward + backward as fused kernels (csrc/conv1_train.cu)
         act = nn.LeakyReLU(negative_slope=negative_slope, inplace=True) if leaky_relu else nn.ReLU(inplace=False)
         trk = use_running_statistics
@@ -115,6 +119,12 @@ class Conv64F(nn.Module):
         # tcgen05 TF32 stem (csrc/conv1_tc.cu, 0.28 ms per 800 clips) when the caller allows TF32 convolutions --
         # PyTorch's and the reference's default, and the switch that governs the cuDNN blocks below -- otherwise
         # the exact-fp32 SIMT stem (csrc/conv1.cu, 0.36 ms).  stem_tf32 = True/False forces one of them.
+        if self.precision == "bf16" and "p2" in c and "p3" in c:
+            h = self._forward_blocks_bf16(x, c)
+            if h is not None:
+                return self._forward_tail(h, c)
+        elif self.precision not in (None, "tf32", "bf16"):
+            raise ValueError("Conv64F.precision must be None, 'tf32' or 'bf16'")
         tf32 = torch.backends.cudnn.allow_tf32 if self.stem_tf32 is None else self.stem_tf32
         h = ops.conv1_bn_act_pool3(x, c["w1"], c["b1"], c["slope"], tf32=tf32)  # [N,64,H/3,W/3] channels_last
         tc = torch.backends.cudnn.allow_tf32 if self.block_tc is None else self.block_tc
@@ -128,6 +138,23 @@ class Conv64F(nn.Module):
             h = self._conv_act(h, c["w3"], c["b3"], c["slope"])
             if self.maxpool_last2:
                 h = ops.maxpool3_channels_last(h)
+        return self._forward_tail(h, c)
+
+    def _forward_blocks_bf16(self, x, c):
+        """Blocks 1-3 with bf16 activations between them (csrc/conv1_tc.cu bf16 output, csrc/conv3_tc.cu bf16 MMAs);
+        returns the fp32 channels_last input of block 4, or None when a shape is outside what the kernels are built for."""
+        need = 27 if self.maxpool_last2 else 9  # every pooled block needs a 3x3 input at least
+        if x.shape[2] < need or x.shape[3] < need or x.shape[3] // 3 > 61:
+            return None
+        for i in (2, 3):
+            if "q%d" % i not in c:
+                w = c["w%d" % i]
+                c["q%d" % i] = torch.from_numpy(ops.conv3x3_c64_pack_weights_bf16(w)).to(w.device).view(torch.bfloat16)
+        h = ops.conv1_bn_act_pool3(x, c["w1"], c["b1"], c["slope"], tf32=True, out_dtype=torch.bfloat16)
+        h = ops.conv3x3_c64_bn_act_bf16(h, c["q2"], c["b2"], c["slope"], pool=True, out_dtype=torch.bfloat16)
+        return ops.conv3x3_c64_bn_act_bf16(h, c["q3"], c["b3"], c["slope"], pool=self.maxpool_last2, out_dtype=torch.float32)
+
+    def _forward_tail(self, h, c):
         h = self._conv_act(h, c["w4"], c["b4"], c["slope"])
         if self.last_pool and self.is_flatten and ops.pool3_linear_supported(h, c["wl"].shape[0]):
             return ops.pool3_linear(h, c["wl"], c["bl"])  # last max-pool + flatten + BatchNorm1d + Linear: one kernel

@@ -28,6 +28,7 @@
 // busy (im2col stores 55 KB + operand reads 108 KB + staging 64 KB per tile) and BUILD and EPI are busy 88 % / 78 % of
 // the time at ~0.2 IPC per warp.  Tried and slower: 16 EPI warps of 16 channels (0.91-1.07 ms, with and without a
 // setmaxnreg register split), two BUILD groups (1.00 ms at 96 registers per thread).
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -58,10 +59,11 @@ struct Conv1TcParams {
 
 enum { kAFull = 0, kAEmpty = kNBuf1, kAccFull = 2 * kNBuf1, kAccEmpty = 2 * kNBuf1 + 2, kBars1 = 2 * kNBuf1 + 4 };
 
-template <bool LEAKY>
+// OBF16: the channels-last output is written as bf16 (the input of the bf16 blocks of csrc/conv3_tc.cu) instead of fp32
+template <bool LEAKY, bool OBF16>
 __global__ void __launch_bounds__(kThreads1, 1)
 conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, int PH, int PW, float slope,
-                float* __restrict__ out, const __grid_constant__ Conv1TcParams prm) {
+                void* __restrict__ out_, const __grid_constant__ Conv1TcParams prm) {
   extern __shared__ __align__(128) uint8_t s_buf[];  // [kNBuf1][kTileBytes] patches | [kWBytes] weights | [8][kStageBytes] output staging
   __shared__ __align__(8) uint64_t s_bars[kBars1];
   __shared__ uint32_t s_tmem;
@@ -202,10 +204,11 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
         const uint32_t as = r & 1u;
         mbar_wait_warp_sleep(BAR1(kAccFull + as), (r >> 1) & 1u, lane);
         fence_after();
-        uint32_t v0[32], v1[32];
+        uint32_t v0[32], v1[32], v2[32];
         tmem_ld32_nowait(t_row + as * kAccCols + 0 * kCh1, v0);
         tmem_ld32_nowait(t_row + as * kAccCols + 1 * kCh1, v1);
         tmem_wait_ld();
+        tmem_ld32_nowait(t_row + as * kAccCols + 2 * kCh1, v2);  // in flight behind the maxima of the first two windows
         if (g == 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) best[j] = fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j]));
@@ -213,11 +216,11 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
 #pragma unroll
           for (int j = 0; j < 32; ++j) best[j] = fmaxf(fmaxf(best[j], __uint_as_float(v0[j])), __uint_as_float(v1[j]));
         }
-        tmem_ld32(t_row + as * kAccCols + 2 * kCh1, v0);
+        tmem_wait_ld();
         fence_before();
         mbar_arrive(BAR1(kAccEmpty + as));  // this thread's part of the accumulator set is in registers
 #pragma unroll
-        for (int j = 0; j < 32; ++j) best[j] = fmaxf(best[j], __uint_as_float(v0[j]));
+        for (int j = 0; j < 32; ++j) best[j] = fmaxf(best[j], __uint_as_float(v2[j]));
       }
       __syncwarp();  // the previous tile's staging reads are done
 #pragma unroll
@@ -233,11 +236,28 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
       __syncwarp();
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int64_t pix0 = tile * kPix1 + (warp & 3) * 32;  // first pixel of this warp's 32
+      if (OBF16) {
+        __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int q = 4 * i + (lane >> 3), c = lane & 7;  // pixel of the warp, 16-byte chunk of its 128-byte half-row
-        const float4 v = *reinterpret_cast<const float4*>(stage + q * kStagePitch + 4 * c);
-        if (pix0 + q < total_pix) *reinterpret_cast<float4*>(out + (pix0 + q) * kCh1 + 32 * half + 4 * c) = v;
+        for (int i = 0; i < 4; ++i) {
+          const int q = 8 * i + (lane >> 2), c = lane & 3;  // pixel of the warp, 16-byte chunk of its 64-byte half-row
+          const float4 a = *reinterpret_cast<const float4*>(stage + q * kStagePitch + 8 * c);
+          const float4 b = *reinterpret_cast<const float4*>(stage + q * kStagePitch + 8 * c + 4);
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+          const __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+          uint4 v;
+          v.x = *reinterpret_cast<const uint32_t*>(&p0); v.y = *reinterpret_cast<const uint32_t*>(&p1);
+          v.z = *reinterpret_cast<const uint32_t*>(&p2); v.w = *reinterpret_cast<const uint32_t*>(&p3);
+          if (pix0 + q < total_pix) *reinterpret_cast<uint4*>(out + (pix0 + q) * kCh1 + 32 * half + 8 * c) = v;
+        }
+      } else {
+        float* out = static_cast<float*>(out_);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int q = 4 * i + (lane >> 3), c = lane & 7;  // pixel of the warp, 16-byte chunk of its 128-byte half-row
+          const float4 v = *reinterpret_cast<const float4*>(stage + q * kStagePitch + 4 * c);
+          if (pix0 + q < total_pix) *reinterpret_cast<float4*>(out + (pix0 + q) * kCh1 + 32 * half + 4 * c) = v;
+        }
       }
     }
   }
@@ -251,15 +271,27 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
 }  // namespace
 }  // namespace afs
 
-extern "C" int afs_conv1_bn_act_pool3_fwd_tf32(const float* x, int32_t N, int32_t H, int32_t Wd,
-                                               const float* w_folded_host, const float* shift_host, int32_t C,
-                                               float negative_slope, float* out, afs_stream_t stream_) {
-  using namespace afs;
+namespace afs {
+namespace {
+
+template <bool LEAKY, bool OBF16>
+int launch_conv1_tc(const float* x, int64_t total, int H, int Wd, int PH, int PW, float slope, void* out,
+                    const Conv1TcParams& prm, unsigned blocks, size_t smem, cudaStream_t stream) {
+  AFS_CUDA_TRY(cudaFuncSetAttribute(conv1_tc_kernel<LEAKY, OBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+  conv1_tc_kernel<LEAKY, OBF16><<<blocks, kThreads1, smem, stream>>>(x, total, H, Wd, PH, PW, slope, out, prm);
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
+}
+
+int conv1_tc_fwd(const float* x, int32_t N, int32_t H, int32_t Wd, const float* w_folded_host, const float* shift_host,
+                 int32_t C, float negative_slope, void* out, bool out_bf16, afs_stream_t stream_) {
   if (x == nullptr || w_folded_host == nullptr || shift_host == nullptr || out == nullptr || N < 0 || H < 3 ||
       Wd < 3 || negative_slope < 0.f)
     return AFS_ERR_INVALID_ARG;
   if (C != kCh1) return AFS_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return AFS_ERR_INVALID_ARG;
+  if (negative_slope >= 1.f) return AFS_ERR_UNSUPPORTED;  // the activation is max(v, slope v)
   if (N == 0) return AFS_OK;
   const int PH = H / 3, PW = Wd / 3;
   const int64_t total = static_cast<int64_t>(N) * PH * PW;
@@ -269,15 +301,25 @@ extern "C" int afs_conv1_bn_act_pool3_fwd_tf32(const float* x, int32_t N, int32_
   for (int i = 0; i < kCh1; ++i) prm.shift[i] = shift_host[i];
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t smem = kNBuf1 * kTileBytes + kWBytes + 8 * kStageBytes;
-  int64_t blocks = n_tiles < kNumSMs ? n_tiles : kNumSMs;  // persistent: one CTA per SM
-  if (negative_slope >= 1.f) return AFS_ERR_UNSUPPORTED;  // the activation is max(v, slope v)
-  if (negative_slope > 0.f) {
-    AFS_CUDA_TRY(cudaFuncSetAttribute(conv1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    conv1_tc_kernel<true><<<static_cast<unsigned>(blocks), kThreads1, smem, stream>>>(x, total, H, Wd, PH, PW, negative_slope, out, prm);
-  } else {
-    AFS_CUDA_TRY(cudaFuncSetAttribute(conv1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    conv1_tc_kernel<false><<<static_cast<unsigned>(blocks), kThreads1, smem, stream>>>(x, total, H, Wd, PH, PW, negative_slope, out, prm);
-  }
-  AFS_LAUNCH_CHECK();
-  return AFS_OK;
+  const unsigned blocks = static_cast<unsigned>(n_tiles < kNumSMs ? n_tiles : kNumSMs);  // persistent: one CTA per SM
+  const bool leaky = negative_slope > 0.f;
+  if (leaky && out_bf16) return launch_conv1_tc<true, true>(x, total, H, Wd, PH, PW, negative_slope, out, prm, blocks, smem, stream);
+  if (leaky) return launch_conv1_tc<true, false>(x, total, H, Wd, PH, PW, negative_slope, out, prm, blocks, smem, stream);
+  if (out_bf16) return launch_conv1_tc<false, true>(x, total, H, Wd, PH, PW, negative_slope, out, prm, blocks, smem, stream);
+  return launch_conv1_tc<false, false>(x, total, H, Wd, PH, PW, negative_slope, out, prm, blocks, smem, stream);
+}
+
+}  // namespace
+}  // namespace afs
+
+extern "C" int afs_conv1_bn_act_pool3_fwd_tf32(const float* x, int32_t N, int32_t H, int32_t Wd,
+                                               const float* w_folded_host, const float* shift_host, int32_t C,
+                                               float negative_slope, float* out, afs_stream_t stream_) {
+  return afs::conv1_tc_fwd(x, N, H, Wd, w_folded_host, shift_host, C, negative_slope, out, false, stream_);
+}
+
+extern "C" int afs_conv1_bn_act_pool3_fwd_tf32_bf16out(const float* x, int32_t N, int32_t H, int32_t Wd,
+                                                       const float* w_folded_host, const float* shift_host, int32_t C,
+                                                       float negative_slope, void* out_bf16, afs_stream_t stream_) {
+  return afs::conv1_tc_fwd(x, N, H, Wd, w_folded_host, shift_host, C, negative_slope, out_bf16, true, stream_);
 }

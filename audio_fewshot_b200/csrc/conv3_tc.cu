@@ -35,6 +35,8 @@
 
 #include <atomic>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -49,14 +51,37 @@ constexpr int kRing3 = 4;                     // operand ring stages (8 input ch
 constexpr int kAhead3 = 3;                    // stages a producer keeps in flight before it must signal the oldest
 constexpr uint32_t kTapKcBytes = 2u * kC3 * 16u;          // weights of one (tap, 8-channel group): 2 KB
 constexpr uint32_t kWBytes3 = 9u * 8u * kTapKcBytes;      // 147 456 B
+// bf16 operands (kind::f16, K = 16 per MMA): a ring stage holds 16 input channels in the same 32 bytes per pixel, the
+// weights of one (tap, 16-channel group) are the same 2 KB, there are 4 groups instead of 8 -> half the MMAs per tile,
+// and the resident weights shrink to 72 KB, which pays for an 8-stage ring (two tiles of look-ahead).
+constexpr int kRing3B = 8;
+constexpr int kAhead3B = 6;
+constexpr uint32_t kWBytes3B = 9u * 4u * kTapKcBytes;     // 73 728 B
 constexpr int kMaxPix3 = 9;                   // 16-byte copies per producer thread and stage (halo <= 576)
 constexpr int kCg3 = 8;                       // channels per epilogue pass
 constexpr int kStagePitch = 12;               // floats per staged position (8 channels + pad: conflict-free stores)
 
-struct Bars3 {
-  uint64_t full[kRing3], empty[kRing3];
+template <int RING>
+struct Bars3T {
+  uint64_t full[RING], empty[RING];
   uint64_t acc_full[2], acc_empty[2];
 };
+
+// kind::f16 instruction descriptor with bf16 operands (a_format = b_format = 1), fp32 accumulate, both K-major
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 v;
+  v.x = *reinterpret_cast<const uint32_t*>(&lo);
+  v.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = v;
+}
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -76,10 +101,11 @@ struct Conv3Geom {
 // 8-channel group, so a warp reads 16 whole 32-byte sectors and writes 512 contiguous shared-memory bytes per
 // instruction.  dst already carries the 32-byte swizzle (16-byte chunk index ^= bit 2 of the pixel index).
 struct ProducerPlan {
-  const float* src[kMaxPix3];
+  const char* src[kMaxPix3];
   uint32_t dst[kMaxPix3], nbytes[kMaxPix3];
 
-  __device__ __forceinline__ void setup(const float* x, const Conv3Geom& g, int ptid, int n, int y0) {
+  // esz: bytes per activation element (4: fp32 / TF32 stages of 8 channels, 2: bf16 stages of 16 channels)
+  __device__ __forceinline__ void setup(const char* x, int esz, const Conv3Geom& g, int ptid, int n, int y0) {
     const int half = ptid & 1;
 #pragma unroll
     for (int i = 0; i < kMaxPix3; ++i) {
@@ -87,7 +113,7 @@ struct ProducerPlan {
       const int hr = h / g.HP, hc = h - hr * g.HP;
       const int y = y0 - 1 + hr, xx = hc - 1;
       const bool ok = h < g.halo && hr <= g.R + 1 && y >= 0 && y < g.H && xx >= 0 && xx < g.W;
-      src[i] = (ok ? x + ((static_cast<int64_t>(n) * g.H + y) * g.W + xx) * kC3 : x) + half * 4;
+      src[i] = (ok ? x + ((static_cast<int64_t>(n) * g.H + y) * g.W + xx) * (kC3 * esz) : x) + half * 16;
       nbytes[i] = ok ? 16u : 0u;   // 0 -> the 16 destination bytes are zero-filled (padding)
       dst[i] = static_cast<uint32_t>(h) * 32u + ((static_cast<uint32_t>(half) ^ ((static_cast<uint32_t>(h) >> 2) & 1u)) << 4);
     }
@@ -95,7 +121,7 @@ struct ProducerPlan {
   __device__ __forceinline__ void issue(uint32_t stage_addr, int kc, int ptid, int halo) const {
 #pragma unroll
     for (int i = 0; i < kMaxPix3; ++i) {
-      if ((ptid >> 1) + 64 * i < halo) cp_async16(stage_addr + dst[i], src[i] + kc * 8, nbytes[i]);
+      if ((ptid >> 1) + 64 * i < halo) cp_async16(stage_addr + dst[i], src[i] + kc * 32, nbytes[i]);
     }
     cp_async_commit();
   }
@@ -104,8 +130,8 @@ struct ProducerPlan {
 // Producer loop over this CTA's tiles.  RING stages, at most AHEAD of them in flight before the oldest is handed
 // over; a thread that is about to block on a slot the tensor core still reads first hands over everything it has in
 // flight.  next_tile(j) returns the j-th tile of this CTA or -1.
-template <int RING, int AHEAD, class NextTile>
-__device__ __forceinline__ void producer_loop(const float* x, const Conv3Geom& g, int ptid, int lane, uint32_t ring_base,
+template <int RING, int AHEAD, int KC, class NextTile>
+__device__ __forceinline__ void producer_loop(const char* x, int esz, const Conv3Geom& g, int ptid, int lane, uint32_t ring_base,
                                               uint32_t stage_bytes, uint64_t* full, uint64_t* empty, NextTile next_tile) {
   uint32_t gs = 0;       // stages issued so far (all tiles)
   uint32_t pending = 0;  // issued, not yet signalled: stages gs - pending .. gs - 1
@@ -115,9 +141,9 @@ __device__ __forceinline__ void producer_loop(const float* x, const Conv3Geom& g
     const int n = tile / g.tiles_per_img;
     const int y0 = (tile - n * g.tiles_per_img) * g.R;
     ProducerPlan plan;
-    plan.setup(x, g, ptid, n, y0);
+    plan.setup(x, esz, g, ptid, n, y0);
 #pragma unroll 1
-    for (int kc = 0; kc < 8; ++kc, ++gs) {
+    for (int kc = 0; kc < KC; ++kc, ++gs) {
       const uint32_t st = gs % RING, ph = (gs / RING) & 1u;
       uint32_t ready = lane == 0 ? (mbar_test(smem_u32(&empty[st]), ph ^ 1u) ? 1u : 0u) : 0u;
       ready = __shfl_sync(0xffffffffu, ready, 0);
@@ -145,9 +171,9 @@ __device__ __forceinline__ void producer_loop(const float* x, const Conv3Geom& g
 // Epilogue of one tile by the four epilogue warps (accumulator row == TMEM lane == tid): tcgen05.ld 8 channels at a
 // time, + folded shift, activation, then a direct channels-last store or the 3x3/3 max-pool through the staging tile.
 // release() is called once per warp as soon as the accumulator set has been read completely.
-template <int NM, class Release>
+template <int NM, typename TOut, class Release>
 __device__ __forceinline__ void epilogue_tile(const Conv3Geom& g, int n, int y0, bool store, uint32_t d0, float* s_stage,
-                                              const float* s_shift, float* __restrict__ out, int tid, Release release) {
+                                              const float* s_shift, TOut* __restrict__ out, int tid, Release release) {
 #pragma unroll 1
   for (int cg = 0; cg < kC3 / kCg3; ++cg) {
     uint32_t v[NM][kCg3];
@@ -175,9 +201,9 @@ __device__ __forceinline__ void epilogue_tile(const Conv3Geom& g, int n, int y0,
       } else {
         const int yy = q / g.HP, xx = q - yy * g.HP;
         if (store && yy < g.R && y0 + yy < g.H && xx < g.W) {
-          float4* d = reinterpret_cast<float4*>(out + ((static_cast<int64_t>(n) * g.H + y0 + yy) * g.W + xx) * kC3 + cg * kCg3);
-          d[0] = make_float4(r[0], r[1], r[2], r[3]);
-          d[1] = make_float4(r[4], r[5], r[6], r[7]);
+          TOut* d = out + ((static_cast<int64_t>(n) * g.H + y0 + yy) * g.W + xx) * kC3 + cg * kCg3;
+          store4(d, r[0], r[1], r[2], r[3]);
+          store4(d + 4, r[4], r[5], r[6], r[7]);
         }
       }
     }
@@ -202,7 +228,8 @@ __device__ __forceinline__ void epilogue_tile(const Conv3Geom& g, int n, int y0,
               best.z = fmaxf(best.z, t.z); best.w = fmaxf(best.w, t.w);
             }
           }
-          *reinterpret_cast<float4*>(out + ((static_cast<int64_t>(n) * g.PH + py) * g.PW + px) * kC3 + cg * kCg3 + c4 * 4) = best;
+          store4(out + ((static_cast<int64_t>(n) * g.PH + py) * g.PW + px) * kC3 + cg * kCg3 + c4 * 4, best.x, best.y, best.z,
+                 best.w);
         }
       }
       epi_bar();
@@ -211,12 +238,19 @@ __device__ __forceinline__ void epilogue_tile(const Conv3Geom& g, int n, int y0,
 }
 
 // ---- one CTA per SM ------------------------------------------------------------------------------------------------
-template <int NM>
+// BF16 = false: fp32 activations, TF32 MMAs (K = 8 channels per stage, 8 stages per tile).  BF16 = true: bf16
+// activations and weights, kind::f16 MMAs (K = 16 channels per stage, 4 stages per tile) -- the separately stated
+// reduced-precision path (Conv64F(precision="bf16")).  TOut: element type of the channels-last output.
+template <int NM, bool BF16, typename TOut>
 __global__ void __launch_bounds__(kThreads3, 1)
-conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk, const float* __restrict__ shift,
-                      float* __restrict__ out, const Conv3Geom g) {
+conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, const float* __restrict__ shift,
+                      TOut* __restrict__ out, const Conv3Geom g) {
+  constexpr int RING = BF16 ? kRing3B : kRing3;
+  constexpr int AHEAD = BF16 ? kAhead3B : kAhead3;
+  constexpr int KC = BF16 ? 4 : 8;                       // ring stages (K groups) per tile
+  constexpr uint32_t kWB = BF16 ? kWBytes3B : kWBytes3;  // resident weights
   extern __shared__ __align__(16) uint8_t s_dyn_raw[];  // [weights][ring][staging][shift] after 256-byte alignment
-  __shared__ __align__(8) Bars3 bars;
+  __shared__ __align__(8) Bars3T<RING> bars;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x;
@@ -225,20 +259,20 @@ conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk
   const uint32_t stage_bytes = static_cast<uint32_t>(g.halo) * 32u;
   uint8_t* s_dyn = s_dyn_raw + ((256u - (smem_u32(s_dyn_raw) & 255u)) & 255u);  // swizzle atoms are 256 B
   const uint32_t w_base = smem_u32(s_dyn);
-  const uint32_t ring_base = w_base + kWBytes3;
-  float* s_stage = reinterpret_cast<float*>(s_dyn + kWBytes3 + kRing3 * stage_bytes);
+  const uint32_t ring_base = w_base + kWB;
+  float* s_stage = reinterpret_cast<float*>(s_dyn + kWB + RING * stage_bytes);
   float* s_shift = s_stage + NM * 128 * kStagePitch;
   constexpr uint32_t kTmemCols = NM == 1 ? 128u : (NM == 2 ? 256u : 512u);  // 2 x NM accumulators of 64 columns
-  constexpr uint32_t kIdesc = idesc_tf32(128, kC3);
+  constexpr uint32_t kIdesc = BF16 ? idesc_bf16(128, kC3) : idesc_tf32(128, kC3);
 
   {  // resident weights (already in operand layout) and the folded shift
     const uint4* src = reinterpret_cast<const uint4*>(wpk);
     uint4* dst = reinterpret_cast<uint4*>(s_dyn);
-    for (int i = tid; i < static_cast<int>(kWBytes3 / 16); i += kThreads3) dst[i] = __ldg(src + i);
+    for (int i = tid; i < static_cast<int>(kWB / 16); i += kThreads3) dst[i] = __ldg(src + i);
     if (tid < kC3) s_shift[tid] = shift[tid];
   }
   if (tid == 0) {
-    for (int s = 0; s < kRing3; ++s) {
+    for (int s = 0; s < RING; ++s) {
       mbar_init(smem_u32(&bars.full[s]), 128);  // every producer thread arrives
       mbar_init(smem_u32(&bars.empty[s]), NM);  // one tcgen05.commit per MMA-issuing warp
     }
@@ -262,7 +296,8 @@ conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk
 
   if (warp >= 4 && warp < 8) {
     // ======================= producers =======================
-    producer_loop<kRing3, kAhead3>(x, g, tid - 128, lane, ring_base, stage_bytes, bars.full, bars.empty, next_tile);
+    producer_loop<RING, AHEAD, KC>(static_cast<const char*>(x), BF16 ? 2 : 4, g, tid - 128, lane, ring_base, stage_bytes,
+                                   bars.full, bars.empty, next_tile);
   } else if (warp >= 8) {
     // ======================= MMA issuers: warp 8 + m owns accumulator m of every tile =======================
     // (a single issuing thread spends ~80 cycles per tcgen05.mma on descriptor arithmetic and the election
@@ -281,16 +316,19 @@ conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk
         fence_after();
         const uint32_t d_tmem = tmem_base + ab * (NM * kC3) + m * kC3;
 #pragma unroll 1
-        for (int kc = 0; kc < 8; ++kc, ++gs) {
-          const uint32_t st = gs % kRing3, ph = (gs / kRing3) & 1u;
+        for (int kc = 0; kc < KC; ++kc, ++gs) {
+          const uint32_t st = gs % RING, ph = (gs / RING) & 1u;
           mbar_wait(smem_u32(&bars.full[st]), ph);
           fence_after();
           const uint64_t da_st = a_desc0 + ((st * stage_bytes) >> 4);
           const uint64_t db_kc = b_desc0 + static_cast<uint32_t>(kc) * (kTapKcBytes >> 4);
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap)
-            mma_tf32(d_tmem, da_st + tap_off[tap], db_kc + static_cast<uint32_t>(tap) * (8u * kTapKcBytes >> 4), kIdesc,
-                     (kc | tap) != 0);
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t da = da_st + tap_off[tap];
+            const uint64_t db = db_kc + static_cast<uint32_t>(tap) * (static_cast<uint32_t>(KC) * kTapKcBytes >> 4);
+            if (BF16) mma_f16(d_tmem, da, db, kIdesc, (kc | tap) != 0);
+            else mma_tf32(d_tmem, da, db, kIdesc, (kc | tap) != 0);
+          }
           commit(smem_u32(&bars.empty[st]));  // stage reusable once these MMAs have read it
         }
         commit(smem_u32(&bars.acc_full[ab]));
@@ -308,7 +346,7 @@ conv3x3_c64_tc_kernel(const float* __restrict__ x, const float* __restrict__ wpk
       const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
       mbar_wait_warp(smem_u32(&bars.acc_full[ab]), aph, lane);
       fence_after();
-      epilogue_tile<NM>(g, n, y0, true, tmem_base + ab * (NM * kC3) + t_lane, s_stage, s_shift, out, tid, [&]() {
+      epilogue_tile<NM, TOut>(g, n, y0, true, tmem_base + ab * (NM * kC3) + t_lane, s_stage, s_shift, out, tid, [&]() {
         if (lane == 0) mbar_arrive(smem_u32(&bars.acc_empty[ab]));
       });
     }
@@ -400,7 +438,8 @@ conv3x3_c64_tc_pair_kernel(const float* __restrict__ x, const float* __restrict_
 
   if (warp >= 4 && warp < 8) {
     // ======================= producers (both CTAs fill their own ring) =======================
-    producer_loop<kRingP, kAheadP>(x, g, tid - 128, lane, ring_base, stage_bytes, bars.full, bars.empty, next_tile);
+    producer_loop<kRingP, kAheadP, 8>(reinterpret_cast<const char*>(x), 4, g, tid - 128, lane, ring_base, stage_bytes,
+                                      bars.full, bars.empty, next_tile);
   } else if (warp >= 8) {
     const int m = warp - 8;
     if (leader) {
@@ -457,7 +496,7 @@ conv3x3_c64_tc_pair_kernel(const float* __restrict__ x, const float* __restrict_
       const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
       mbar_wait_warp(smem_u32(&bars.acc_full[ab]), aph, lane);
       fence_after();
-      epilogue_tile<NM>(g, n, y0, store, tmem_base + ab * (NM * kC3) + t_lane, s_stage, s_shift, out, tid, [&]() {
+      epilogue_tile<NM, float>(g, n, y0, store, tmem_base + ab * (NM * kC3) + t_lane, s_stage, s_shift, out, tid, [&]() {
         if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&bars.acc_empty[ab]), 0));
       });
     }
@@ -505,18 +544,46 @@ int launch_conv3_pair(const float* x, const float* wpk_pair, const float* shift,
   return AFS_OK;
 }
 
-template <int NM>
-int launch_conv3(const float* x, const float* wpk, const float* shift, float* out, Conv3Geom g, cudaStream_t stream) {
+template <int NM, bool BF16, typename TOut>
+int launch_conv3(const void* x, const void* wpk, const float* shift, TOut* out, Conv3Geom g, cudaStream_t stream) {
   g.halo = (NM * 128 + 2 * g.HP + 2 + 7) & ~7;
-  const size_t smem = kWBytes3 + kRing3 * (g.halo * 32u) + static_cast<size_t>(NM) * 128 * kStagePitch * 4 + kC3 * 4 + 256;
+  const size_t smem = (BF16 ? kWBytes3B : kWBytes3) + (BF16 ? kRing3B : kRing3) * (g.halo * 32u) +
+                      static_cast<size_t>(NM) * 128 * kStagePitch * 4 + kC3 * 4 + 256;
   if (smem + 256u > 232448u) return AFS_ERR_UNSUPPORTED;  // 227 KB per CTA, static barriers included
-  AFS_CUDA_TRY(cudaFuncSetAttribute(conv3x3_c64_tc_kernel<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  AFS_CUDA_TRY(cudaFuncSetAttribute(conv3x3_c64_tc_kernel<NM, BF16, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
   const int total = g.N * g.tiles_per_img;
   const int blocks = total < kNumSMs ? total : kNumSMs;  // persistent: one CTA per SM
-  conv3x3_c64_tc_kernel<NM><<<blocks, kThreads3, smem, stream>>>(x, wpk, shift, out, g);
+  conv3x3_c64_tc_kernel<NM, BF16, TOut><<<blocks, kThreads3, smem, stream>>>(x, wpk, shift, out, g);
   AFS_LAUNCH_CHECK();
   return AFS_OK;
+}
+
+template <bool BF16, typename TOut>
+int dispatch_conv3(int NM, const void* x, const void* wpk, const float* shift, TOut* out, const Conv3Geom& g,
+                   cudaStream_t stream) {
+  switch (NM) {
+    case 1: return launch_conv3<1, BF16, TOut>(x, wpk, shift, out, g, stream);
+    case 2: return launch_conv3<2, BF16, TOut>(x, wpk, shift, out, g, stream);
+    default: return launch_conv3<3, BF16, TOut>(x, wpk, shift, out, g, stream);
+  }
+}
+
+// Tile geometry shared by the TF32 and the bf16 entry point.  Returns NM (accumulators per tile) or an AFS_ERR_* code (< 0).
+int conv3_geometry(int32_t N, int32_t H, int32_t Wd, float negative_slope, int32_t pool3, Conv3Geom* gp) {
+  Conv3Geom& g = *gp;
+  g.N = N; g.H = H; g.W = Wd; g.HP = Wd + 2; g.pool = pool3 ? 1 : 0; g.slope = negative_slope;
+  g.PH = H / 3; g.PW = Wd / 3;
+  const int rows_needed = pool3 ? 3 * g.PH : H;  // rows below the last complete pooling window are never used
+  // rows per tile: as many as fit 384 accumulator rows (a multiple of 3 when pooling)
+  int R = 384 / g.HP;
+  if (R > rows_needed) R = rows_needed;
+  if (pool3) R -= R % 3;
+  if (R < 1) return AFS_ERR_UNSUPPORTED;  // image rows wider than the tile (W > 126 when pooling)
+  g.R = R;
+  g.tiles_per_img = (rows_needed + R - 1) / R;
+  if (static_cast<int64_t>(N) * g.tiles_per_img > 0x7fffffffLL) return AFS_ERR_UNSUPPORTED;
+  return (R * g.HP + 127) / 128;
 }
 
 // 0: one CTA per SM (default).  1: CTA pairs (cta_group::2).  Initialised from AFS_CONV3_PAIR.
@@ -524,6 +591,14 @@ std::atomic<int> g_pair_mode{[] {
   const char* e = getenv("AFS_CONV3_PAIR");
   return (e != nullptr && e[0] == '1') ? 1 : 0;
 }()};
+
+inline uint16_t round_bf16_host(float v) {  // round to nearest even (what __float2bfloat16_rn does); NaN kept quiet
+  uint32_t b;
+  memcpy(&b, &v, 4);
+  if ((b & 0x7f800000u) == 0x7f800000u) return static_cast<uint16_t>((b >> 16) | ((b & 0xffffu) ? 0x40u : 0u));
+  b += 0x7fffu + ((b >> 16) & 1u);
+  return static_cast<uint16_t>(b >> 16);
+}
 
 inline float round_tf32_host(float v) {  // cvt.rna.tf32.f32: nearest, ties away from zero
   uint32_t b;
@@ -575,18 +650,8 @@ extern "C" int afs_conv3x3_c64_bn_act_fwd_tf32(const float* x, int32_t N, int32_
   if (Wd > 61) return AFS_ERR_UNSUPPORTED;  // the operand ring of wider rows does not fit next to the weights
   if (N == 0) return AFS_OK;
   Conv3Geom g;
-  g.N = N; g.H = H; g.W = Wd; g.HP = Wd + 2; g.pool = pool3 ? 1 : 0; g.slope = negative_slope;
-  g.PH = H / 3; g.PW = Wd / 3;
-  const int rows_needed = pool3 ? 3 * g.PH : H;  // rows below the last complete pooling window are never used
-  // rows per tile: as many as fit 384 accumulator rows (a multiple of 3 when pooling)
-  int R = 384 / g.HP;
-  if (R > rows_needed) R = rows_needed;
-  if (pool3) R -= R % 3;
-  if (R < 1) return AFS_ERR_UNSUPPORTED;  // image rows wider than the tile (W > 126 when pooling)
-  g.R = R;
-  g.tiles_per_img = (rows_needed + R - 1) / R;
-  if (static_cast<int64_t>(N) * g.tiles_per_img > 0x7fffffffLL) return AFS_ERR_UNSUPPORTED;
-  const int NM = (R * g.HP + 127) / 128;
+  const int NM = conv3_geometry(N, H, Wd, negative_slope, pool3, &g);
+  if (NM < 0) return NM;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (g_pair_mode.load(std::memory_order_relaxed) != 0 && static_cast<int64_t>(N) * g.tiles_per_img >= 2) {
     const float* w_pair = w_packed + kWBytes3 / 4;
@@ -596,9 +661,42 @@ extern "C" int afs_conv3x3_c64_bn_act_fwd_tf32(const float* x, int32_t N, int32_
       default: return launch_conv3_pair<3>(x, w_pair, shift, out, g, stream);
     }
   }
-  switch (NM) {
-    case 1: return launch_conv3<1>(x, w_packed, shift, out, g, stream);
-    case 2: return launch_conv3<2>(x, w_packed, shift, out, g, stream);
-    default: return launch_conv3<3>(x, w_packed, shift, out, g, stream);
-  }
+  return dispatch_conv3<false, float>(NM, x, w_packed, shift, out, g, stream);
+}
+
+extern "C" size_t afs_conv3x3_c64_packed_bf16_elems(void) { return afs::kWBytes3B / 2; }
+
+extern "C" int afs_conv3x3_c64_pack_weights_bf16(const float* w_folded_host, uint16_t* packed_host) {
+  using namespace afs;
+  if (w_folded_host == nullptr || packed_host == nullptr) return AFS_ERR_INVALID_ARG;
+  // packed[tap][kc][chunk][cout][8] <- bf16(w[cout][cin = 16 kc + 8 chunk + i][ky][kx]), tap = 3 ky + kx
+  for (int tap = 0; tap < 9; ++tap)
+    for (int kc = 0; kc < 4; ++kc)
+      for (int ch = 0; ch < 2; ++ch)
+        for (int co = 0; co < kC3; ++co)
+          for (int i = 0; i < 8; ++i) {
+            const int ci = 16 * kc + 8 * ch + i;
+            packed_host[(((tap * 4 + kc) * 2 + ch) * kC3 + co) * 8 + i] = round_bf16_host(w_folded_host[(co * kC3 + ci) * 9 + tap]);
+          }
+  return AFS_OK;
+}
+
+extern "C" int afs_conv3x3_c64_bn_act_fwd_bf16(const void* x, int32_t N, int32_t H, int32_t Wd, const void* w_packed,
+                                               const float* shift, float negative_slope, int32_t pool3, void* out,
+                                               int32_t out_bf16, afs_stream_t stream_) {
+  using namespace afs;
+  if (x == nullptr || w_packed == nullptr || shift == nullptr || out == nullptr || N < 0 || H < 1 || Wd < 1 ||
+      negative_slope < 0.f)
+    return AFS_ERR_INVALID_ARG;
+  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w_packed)) & 15) != 0)
+    return AFS_ERR_INVALID_ARG;
+  if (pool3 && (H < 3 || Wd < 3)) return AFS_ERR_INVALID_ARG;
+  if (Wd > 61) return AFS_ERR_UNSUPPORTED;
+  if (N == 0) return AFS_OK;
+  Conv3Geom g;
+  const int NM = conv3_geometry(N, H, Wd, negative_slope, pool3, &g);
+  if (NM < 0) return NM;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (out_bf16) return dispatch_conv3<true, __nv_bfloat16>(NM, x, w_packed, shift, static_cast<__nv_bfloat16*>(out), g, stream);
+  return dispatch_conv3<true, float>(NM, x, w_packed, shift, static_cast<float*>(out), g, stream);
 }

@@ -126,11 +126,12 @@ class LogMelPlan:
 
 
 # --------------------------------------------------------------------------- backbone stem
-def conv1_bn_act_pool3(x, w_folded, shift, negative_slope=0.0, tf32=False):
+def conv1_bn_act_pool3(x, w_folded, shift, negative_slope=0.0, tf32=False, out_dtype=torch.float32):
     """Fused eval-mode first block of Conv64F.  x [N,1,H,W] CUDA fp32; w_folded [C,9] / shift [C]:
     contiguous float32 numpy arrays (BatchNorm already folded).  Returns a channels_last
     [N, C, H//3, W//3] tensor.  tf32=True runs the tcgen05 tensor-core kernel (TF32 operands, the precision
-    class of cuDNN's default convolutions); tf32=False the exact-fp32 SIMT kernel."""
+    class of cuDNN's default convolutions); tf32=False the exact-fp32 SIMT kernel.  out_dtype=torch.bfloat16
+    (tensor-core kernel only) writes the activation as bf16 for the bf16 blocks (conv3x3_c64_bn_act_bf16)."""
     _need_cuda(x, "x")
     if x.dim() != 4 or x.shape[1] != 1:
         raise ValueError("x must be [N, 1, H, W]")
@@ -139,9 +140,14 @@ def conv1_bn_act_pool3(x, w_folded, shift, negative_slope=0.0, tf32=False):
     Cc = int(shift.shape[0])
     w_folded = np.ascontiguousarray(w_folded, dtype=np.float32).reshape(Cc, 9)
     shift = np.ascontiguousarray(shift, dtype=np.float32)
-    out = torch.empty((N, Cc, H // 3, Wd // 3), dtype=torch.float32, device=x.device,
+    if out_dtype not in (torch.float32, torch.bfloat16) or (out_dtype == torch.bfloat16 and not tf32):
+        raise ValueError("out_dtype must be float32, or bfloat16 with tf32=True")
+    out = torch.empty((N, Cc, H // 3, Wd // 3), dtype=out_dtype, device=x.device,
                       memory_format=torch.channels_last)
-    fn = _lib.lib().afs_conv1_bn_act_pool3_fwd_tf32 if tf32 else _lib.lib().afs_conv1_bn_act_pool3_fwd
+    if out_dtype == torch.bfloat16:
+        fn = _lib.lib().afs_conv1_bn_act_pool3_fwd_tf32_bf16out
+    else:
+        fn = _lib.lib().afs_conv1_bn_act_pool3_fwd_tf32 if tf32 else _lib.lib().afs_conv1_bn_act_pool3_fwd
     _lib.check(fn(_ptr(x), N, H, Wd, w_folded.ctypes.data_as(C.c_void_p), shift.ctypes.data_as(C.c_void_p), Cc,
                   float(negative_slope), _ptr(out), _stream()), "afs_conv1_bn_act_pool3_fwd")
     return out
@@ -255,6 +261,42 @@ def conv3x3_c64_bn_act(x, w_packed, shift, negative_slope=0.0, pool=False):
     _lib.check(_lib.lib().afs_conv3x3_c64_bn_act_fwd_tf32(_ptr(x), N, H, Wd, _ptr(w_packed), _ptr(shift.contiguous()),
                                                           float(negative_slope), 1 if pool else 0, _ptr(out),
                                                           _stream()), "afs_conv3x3_c64_bn_act_fwd_tf32")
+    return out
+
+
+def conv3x3_c64_pack_weights_bf16(w_folded):
+    """BatchNorm-folded [64, 64, 3, 3] weights -> the packed bf16 operand buffer of conv3x3_c64_bn_act_bf16 (a uint16
+    numpy array of bf16 bit patterns, round to nearest even; upload with torch.from_numpy(p).view(torch.bfloat16))."""
+    w = np.ascontiguousarray(w_folded.detach().float().cpu().numpy() if isinstance(w_folded, torch.Tensor)
+                             else w_folded, dtype=np.float32)
+    if w.shape != (64, 64, 3, 3):
+        raise ValueError("weights must be [64, 64, 3, 3]")
+    h = _lib.lib()
+    packed = np.empty((int(h.afs_conv3x3_c64_packed_bf16_elems()),), dtype=np.uint16)
+    _lib.check(h.afs_conv3x3_c64_pack_weights_bf16(w.ctypes.data_as(C.c_void_p), packed.ctypes.data_as(C.c_void_p)),
+               "afs_conv3x3_c64_pack_weights_bf16")
+    return packed
+
+
+def conv3x3_c64_bn_act_bf16(x, w_packed, shift, negative_slope=0.0, pool=False, out_dtype=torch.bfloat16):
+    """The bf16 variant of conv3x3_c64_bn_act (stated separately from the TF32 parity path): x channels_last
+    [N, 64, H, W] CUDA bf16; w_packed: CUDA bf16 tensor from conv3x3_c64_pack_weights_bf16; shift: CUDA fp32 [64].
+    fp32 accumulation, shift and activation; the channels_last result is bf16 or fp32 (out_dtype)."""
+    _need_cuda(x, "x", torch.bfloat16)
+    _need_cuda(w_packed, "w_packed", torch.bfloat16)
+    _need_cuda(shift, "shift")
+    if not conv3x3_c64_supported(x):
+        raise ValueError("x must be [N, 64, H, W] with W <= 61")
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("out_dtype must be float32 or bfloat16")
+    x = x.contiguous(memory_format=torch.channels_last)
+    N, Cc, H, Wd = x.shape
+    oh, ow = (H // 3, Wd // 3) if pool else (H, Wd)
+    out = torch.empty((N, Cc, oh, ow), dtype=out_dtype, device=x.device, memory_format=torch.channels_last)
+    _lib.check(_lib.lib().afs_conv3x3_c64_bn_act_fwd_bf16(_ptr(x), N, H, Wd, _ptr(w_packed), _ptr(shift.contiguous()),
+                                                          float(negative_slope), 1 if pool else 0, _ptr(out),
+                                                          1 if out_dtype == torch.bfloat16 else 0, _stream()),
+               "afs_conv3x3_c64_bn_act_fwd_bf16")
     return out
 
 

@@ -190,6 +190,22 @@ int afs_conv3x3_c64_bn_act_fwd_tf32(const float* x, int32_t N, int32_t H, int32_
                                     const float* shift, float negative_slope, int32_t pool3, float* out,
                                     afs_stream_t stream);
 
+/* (1b-bf16) The separately stated bf16 path of the same blocks (north star: "bf16 tensor-core path stated separately";
+ * SURVEY 8f row 4 "channels-last/bf16 backbone"): bf16 activations and weights, tcgen05 kind::f16 MMAs with K = 16
+ * (half the MMAs and half the activation bytes of the TF32 kernel), fp32 accumulation, fp32 BatchNorm shift and
+ * activation.  NOT the parity path: logits move by ~1e-2 relative; the host side reports the argmax-flip rate.
+ * x [N, H, Wd, 64] bf16 NHWC (device); w_packed (device, afs_conv3x3_c64_packed_bf16_elems() bf16 values, 16-byte
+ * aligned) from afs_conv3x3_c64_pack_weights_bf16 (round to nearest even); out NHWC, bf16 when out_bf16 != 0 else
+ * fp32.  The stem variant writes the first block's output as bf16 for it (TF32 arithmetic inside, as (1b')).    */
+size_t afs_conv3x3_c64_packed_bf16_elems(void);
+int afs_conv3x3_c64_pack_weights_bf16(const float* w_folded_host, uint16_t* packed_host);
+int afs_conv3x3_c64_bn_act_fwd_bf16(const void* x, int32_t N, int32_t H, int32_t Wd, const void* w_packed,
+                                    const float* shift, float negative_slope, int32_t pool3, void* out,
+                                    int32_t out_bf16, afs_stream_t stream);
+int afs_conv1_bn_act_pool3_fwd_tf32_bf16out(const float* x, int32_t N, int32_t H, int32_t Wd,
+                                            const float* w_folded_host, const float* shift_host, int32_t C,
+                                            float negative_slope, void* out_bf16, afs_stream_t stream);
+
 /* (1c) MaxPool2d(3, 3) on channels-last activations: x [N, H, W, C] -> out [N, H/3, W/3, C], fp32,
  * C % 4 == 0, 16-byte aligned.  Replaces the nn.MaxPool2d(3, 3) after each Conv64F block
  * (libfewshot_core/model/backbone/conv_four.py:65,71,77,84) on the inference path.           */

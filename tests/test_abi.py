@@ -113,3 +113,25 @@ def test_conv3x3_weight_packing_layouts_and_tf32_rounding():
     assert np.array_equal(single, ref.transpose(4, 1, 2, 0, 3))
     assert np.array_equal(pair, ref.reshape(2, 32, 8, 2, 4, 9).transpose(0, 5, 2, 3, 1, 4))
     assert h.afs_conv3x3_c64_pack_weights(None, packed.ctypes.data_as(ctypes.c_void_p)) == -1
+
+
+def test_conv3x3_bf16_weight_packing_layout_and_rounding():
+    """afs_conv3x3_c64_pack_weights_bf16 (host code): [tap][kc][chunk][cout][8] with cin = 16 kc + 8 chunk + i, values
+    rounded to the nearest bf16, ties to even -- torch's float32 -> bfloat16 conversion."""
+    import numpy as np
+    import torch
+    from audio_fewshot_b200 import _lib
+    h = _lib.lib()
+    rng = np.random.default_rng(1)
+    w = (rng.standard_normal((64, 64, 3, 3)) * 0.1).astype(np.float32)
+    w[0, 0, 0, 0] = np.float32(1.0) + np.float32(2.0 ** -8)   # a tie: rounds to the even neighbour 1.0
+    w[0, 1, 0, 0] = np.float32(1.0) + np.float32(3 * 2.0 ** -8)  # a tie: rounds up to 1 + 2^-6
+    n = int(h.afs_conv3x3_c64_packed_bf16_elems())
+    assert n == 9 * 4 * 2 * 64 * 8
+    packed = np.empty(n, np.uint16)
+    assert h.afs_conv3x3_c64_pack_weights_bf16(w.ctypes.data_as(ctypes.c_void_p), packed.ctypes.data_as(ctypes.c_void_p)) == 0
+    want = torch.from_numpy(w).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)  # [co][ci][ky][kx]
+    assert want[0, 0, 0, 0] == 0x3F80 and want[0, 1, 0, 0] == 0x3F82
+    ref = want.reshape(64, 4, 2, 8, 9)  # [co][kc][chunk][i][tap]
+    assert np.array_equal(packed.reshape(9, 4, 2, 64, 8), ref.transpose(4, 1, 2, 0, 3))
+    assert h.afs_conv3x3_c64_pack_weights_bf16(None, packed.ctypes.data_as(ctypes.c_void_p)) == -1

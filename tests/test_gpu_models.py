@@ -157,6 +157,71 @@ def test_conv3x3_block_cta_pair_variant_is_bit_identical(cuda, N, H, Wd, pool):
     assert torch.equal(one, two)
 
 
+@pytest.mark.parametrize("N,H,Wd,slope,pool,out_dtype", [
+    (5, 42, 52, 0.0, True, torch.bfloat16),     # Conv64F block 2 of the bf16 path
+    (3, 14, 17, 0.0, True, torch.float32),      # block 3: fp32 output for block 4
+    (2, 14, 17, 0.2, False, torch.bfloat16),    # un-pooled, LeakyReLU, ragged last tile
+    (7, 4, 5, 0.0, False, torch.float32),
+    (2, 10, 61, 0.1, False, torch.float32),     # widest supported row
+    (300, 42, 52, 0.0, True, torch.bfloat16),   # more tiles than SMs: 8-stage ring wrap-around, both accumulator sets
+])
+def test_conv3x3_block_bf16_kernel(cuda, N, H, Wd, slope, pool, out_dtype):
+    """The separately stated bf16 variant of csrc/conv3_tc.cu (kind::f16 MMAs, K = 16, fp32 accumulation).  With bf16
+    inputs every product is exact in fp32, so against an fp64 convolution of the SAME bf16 activations and bf16-rounded
+    weights only the accumulation order differs: <= 2e-5 of the output range for the fp32 output, one bf16 rounding
+    (2^-8 relative) more for the bf16 output.  Repeated launches are bit-identical."""
+    from audio_fewshot_b200 import ops
+    rng = np.random.default_rng(N * 1000 + H * 10 + Wd + 1)
+    x = torch.from_numpy(rng.standard_normal((N, 64, H, Wd)).astype(np.float32)).to(cuda).to(torch.bfloat16)
+    x = x.contiguous(memory_format=torch.channels_last)
+    w = torch.from_numpy((rng.standard_normal((64, 64, 3, 3)) * 0.06).astype(np.float32)).to(cuda)
+    w[5] *= -1.0
+    b = torch.from_numpy(rng.standard_normal(64).astype(np.float32)).to(cuda)
+    packed = torch.from_numpy(ops.conv3x3_c64_pack_weights_bf16(w)).to(cuda).view(torch.bfloat16)
+    got = ops.conv3x3_c64_bn_act_bf16(x, packed, b, slope, pool=pool, out_dtype=out_dtype)
+    wq = w.to(torch.bfloat16).double()
+    want = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x.double(), wq, b.double(), padding=1), slope)
+    if pool:
+        want = torch.nn.functional.max_pool2d(want, 3, 3)
+    assert got.shape == want.shape and got.dtype == out_dtype
+    assert got.is_contiguous(memory_format=torch.channels_last) or got.shape[2] * got.shape[3] == 1
+    err = (got.double() - want).abs().max().item()
+    tol = (2e-5 if out_dtype == torch.float32 else 2.0 ** -8) * want.abs().max().item()
+    assert err <= tol, (err, tol)
+    assert torch.equal(got, ops.conv3x3_c64_bn_act_bf16(x, packed, b, slope, pool=pool, out_dtype=out_dtype))
+
+
+def test_stem_bf16_output_is_the_rounded_fp32_output(cuda):
+    """csrc/conv1_tc.cu with bf16 output does the same TF32 arithmetic and rounds to nearest even at the store."""
+    from audio_fewshot_b200 import ops
+    rng = np.random.default_rng(21)
+    for (N, H, Wd, slope) in [(3, 128, 157, 0.0), (130, 9, 10, 0.1)]:
+        x = torch.from_numpy(rng.standard_normal((N, 1, H, Wd)).astype(np.float32)).to(cuda)
+        w = rng.standard_normal((64, 9)).astype(np.float32) * 0.3
+        b = rng.standard_normal(64).astype(np.float32)
+        f32 = ops.conv1_bn_act_pool3(x, w, b, slope, tf32=True)
+        b16 = ops.conv1_bn_act_pool3(x, w, b, slope, tf32=True, out_dtype=torch.bfloat16)
+        assert b16.dtype == torch.bfloat16 and b16.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(b16, f32.to(torch.bfloat16))
+
+
+def test_conv64f_bf16_path_is_close_and_keeps_predictions(cuda):
+    """Conv64F(precision='bf16') -- stated separately from the parity path: features within 3e-2 of the feature range
+    of the TF32 path, and the ProtoNet predictions of well separated synthetic episodes unchanged."""
+    from audio_fewshot_b200 import model as arch
+    net = _net(cuda, "conv64f_flat")
+    x = torch.from_numpy((np.random.default_rng(7).standard_normal((24, 1, 128, 157)) * 0.7).astype(np.float32)).to(cuda)
+    with torch.no_grad():
+        net.stem_tf32, net.block_tc = True, True
+        ref = net(x)
+        net.precision = "bf16"
+        fast = net(x)
+        assert torch.equal(fast, net(x))
+    assert fast.dtype == torch.float32 and fast.shape == ref.shape
+    assert (fast - ref).abs().max().item() <= 3e-2 * ref.abs().max().item()
+    assert not torch.equal(fast, ref)  # the bf16 kernels did run
+
+
 def test_conv64f_tensor_core_blocks_match_fp32_path(cuda):
     """Whole Conv64F inference path with the tcgen05 stem and blocks (TF32) against the exact-fp32 path."""
     net = _net(cuda, "conv64f_flat")
