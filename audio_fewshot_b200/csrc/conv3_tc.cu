@@ -47,15 +47,17 @@ using namespace tc;
 
 constexpr int kC3 = 64;                       // channels in == channels out == UMMA N
 constexpr int kThreads3 = 256 + 32 * 3;        // 4 epilogue + 4 producer warps + up to 3 MMA-issuing warps
+constexpr int kThreads3E2 = kThreads3 + 128;   // + a second group of 4 epilogue warps (warps 11-14)
 constexpr int kRing3 = 4;                     // operand ring stages (8 input channels each)
 constexpr int kAhead3 = 3;                    // stages a producer keeps in flight before it must signal the oldest
 constexpr uint32_t kTapKcBytes = 2u * kC3 * 16u;          // weights of one (tap, 8-channel group): 2 KB
 constexpr uint32_t kWBytes3 = 9u * 8u * kTapKcBytes;      // 147 456 B
 // bf16 operands (kind::f16, K = 16 per MMA): a ring stage holds 16 input channels in the same 32 bytes per pixel, the
 // weights of one (tap, 16-channel group) are the same 2 KB, there are 4 groups instead of 8 -> half the MMAs per tile,
-// and the resident weights shrink to 72 KB, which pays for an 8-stage ring (two tiles of look-ahead).
-constexpr int kRing3B = 8;
-constexpr int kAhead3B = 6;
+// and the resident weights shrink to 72 KB, which pays for a 6-stage ring (one and a half tiles of look-ahead) and the
+// second epilogue group's staging tile.
+constexpr int kRing3B = 6;
+constexpr int kAhead3B = 4;
 constexpr uint32_t kWBytes3B = 9u * 4u * kTapKcBytes;     // 73 728 B
 constexpr int kMaxPix3 = 9;                   // 16-byte copies per producer thread and stage (halo <= 576)
 constexpr int kCg3 = 8;                       // channels per epilogue pass
@@ -83,7 +85,7 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, float a, float b, float
   *reinterpret_cast<uint2*>(p) = v;
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 struct Conv3Geom {
   int N, H, W, HP;        // HP = W + 2: padded row pitch
@@ -168,19 +170,23 @@ __device__ __forceinline__ void producer_loop(const char* x, int esz, const Conv
   for (; pending > 0; --pending) mbar_arrive(smem_u32(&full[(gs - pending) % RING]));
 }
 
-// Epilogue of one tile by the four epilogue warps (accumulator row == TMEM lane == tid): tcgen05.ld 8 channels at a
-// time, + folded shift, activation, then a direct channels-last store or the 3x3/3 max-pool through the staging tile.
-// release() is called once per warp as soon as the accumulator set has been read completely.
+// Epilogue passes cg0 .. cg1-1 (8 channels each) of one tile by a group of four epilogue warps (accumulator row ==
+// TMEM lane == tid): tcgen05.ld 8 channels at a time, + folded shift, activation, then a direct channels-last store or
+// the 3x3/3 max-pool through the group's staging tile (synchronised on the group's named barrier `bar`).  A pass is a
+// chain of latencies (TMEM load, staging store, barrier, staging reads, store, barrier: ~1 300 clk) rather than of
+// work, so a second group running the other half of the passes on its own staging tile halves the epilogue time.
+// release() is called once per warp as soon as the warp's share of the accumulator set has been read completely.
 template <int NM, typename TOut, class Release>
 __device__ __forceinline__ void epilogue_tile(const Conv3Geom& g, int n, int y0, bool store, uint32_t d0, float* s_stage,
-                                              const float* s_shift, TOut* __restrict__ out, int tid, Release release) {
+                                              const float* s_shift, TOut* __restrict__ out, int tid, int cg0, int cg1,
+                                              int bar, Release release) {
 #pragma unroll 1
-  for (int cg = 0; cg < kC3 / kCg3; ++cg) {
+  for (int cg = cg0; cg < cg1; ++cg) {
     uint32_t v[NM][kCg3];
 #pragma unroll
     for (int m = 0; m < NM; ++m) tmem_ld8(d0 + m * kC3 + cg * kCg3, v[m]);
     tmem_wait_ld();
-    if (cg == kC3 / kCg3 - 1) {  // every value of this accumulator set is in registers: hand it back
+    if (cg == cg1 - 1) {  // every value of this accumulator set this warp needs is in registers: hand it back
       fence_before();
       __syncwarp();
       release();
@@ -208,7 +214,7 @@ __device__ __forceinline__ void epilogue_tile(const Conv3Geom& g, int n, int y0,
       }
     }
     if (g.pool) {
-      epi_bar();
+      epi_bar(bar);
       const int prt = g.R / 3;                 // pooled rows of this tile
       const int npp = prt * g.PW;
       const int items = npp * 2;               // (4-channel half of the group, pooled pixel): pixel fastest, so
@@ -232,7 +238,7 @@ __device__ __forceinline__ void epilogue_tile(const Conv3Geom& g, int n, int y0,
                  best.w);
         }
       }
-      epi_bar();
+      epi_bar(bar);
     }
   }
 }
@@ -241,8 +247,11 @@ __device__ __forceinline__ void epilogue_tile(const Conv3Geom& g, int n, int y0,
 // BF16 = false: fp32 activations, TF32 MMAs (K = 8 channels per stage, 8 stages per tile).  BF16 = true: bf16
 // activations and weights, kind::f16 MMAs (K = 16 channels per stage, 4 stages per tile) -- the separately stated
 // reduced-precision path (Conv64F(precision="bf16")).  TOut: element type of the channels-last output.
-template <int NM, bool BF16, typename TOut>
-__global__ void __launch_bounds__(kThreads3, 1)
+// EPI2: a second group of four epilogue warps (warps 11-14) with its own staging tile runs passes 4-7 while the first
+// runs passes 0-3 -- the bf16 kernel has half the MMAs per tile and would otherwise wait for the epilogue (the TF32
+// kernel has no shared memory left for a second staging tile, and is MMA-bound).
+template <int NM, bool BF16, typename TOut, bool EPI2>
+__global__ void __launch_bounds__(EPI2 ? kThreads3E2 : kThreads3, 1)
 conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, const float* __restrict__ shift,
                       TOut* __restrict__ out, const Conv3Geom g) {
   constexpr int RING = BF16 ? kRing3B : kRing3;
@@ -261,14 +270,14 @@ conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, 
   const uint32_t w_base = smem_u32(s_dyn);
   const uint32_t ring_base = w_base + kWB;
   float* s_stage = reinterpret_cast<float*>(s_dyn + kWB + RING * stage_bytes);
-  float* s_shift = s_stage + NM * 128 * kStagePitch;
+  float* s_shift = s_stage + (EPI2 ? 2 : 1) * NM * 128 * kStagePitch;
   constexpr uint32_t kTmemCols = NM == 1 ? 128u : (NM == 2 ? 256u : 512u);  // 2 x NM accumulators of 64 columns
   constexpr uint32_t kIdesc = BF16 ? idesc_bf16(128, kC3) : idesc_tf32(128, kC3);
 
   {  // resident weights (already in operand layout) and the folded shift
     const uint4* src = reinterpret_cast<const uint4*>(wpk);
     uint4* dst = reinterpret_cast<uint4*>(s_dyn);
-    for (int i = tid; i < static_cast<int>(kWB / 16); i += kThreads3) dst[i] = __ldg(src + i);
+    for (int i = tid; i < static_cast<int>(kWB / 16); i += (EPI2 ? kThreads3E2 : kThreads3)) dst[i] = __ldg(src + i);
     if (tid < kC3) s_shift[tid] = shift[tid];
   }
   if (tid == 0) {
@@ -278,7 +287,7 @@ conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bars.acc_full[s]), NM);
-      mbar_init(smem_u32(&bars.acc_empty[s]), 4);  // one arrival per epilogue warp
+      mbar_init(smem_u32(&bars.acc_empty[s]), EPI2 ? 8 : 4);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -298,7 +307,7 @@ conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, 
     // ======================= producers =======================
     producer_loop<RING, AHEAD, KC>(static_cast<const char*>(x), BF16 ? 2 : 4, g, tid - 128, lane, ring_base, stage_bytes,
                                    bars.full, bars.empty, next_tile);
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 11) {
     // ======================= MMA issuers: warp 8 + m owns accumulator m of every tile =======================
     // (a single issuing thread spends ~80 cycles per tcgen05.mma on descriptor arithmetic and the election
     // wrapper, more than the 48 cycles the tensor core needs for M=128, N=64, K=8 from shared memory)
@@ -335,9 +344,12 @@ conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, 
       }
     }
   } else {
-    // ======================= epilogue (warps 0-3) =======================
+    // ======================= epilogue (warps 0-3; with EPI2 also warps 11-14) =======================
+    // a warp may only read the TMEM lanes 32 (warp % 4) .. + 31: that quarter is its share of the accumulator rows
     uint32_t lt = 0;
-    const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+    const int part = warp >= 11 ? 1 : 0;
+    const int etid = (warp & 3) * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>((warp & 3) * 32) << 16;
     for (int j = 0;; ++j, ++lt) {
       const int tile = next_tile(j);
       if (tile < 0) break;
@@ -346,7 +358,9 @@ conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, 
       const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
       mbar_wait_warp(smem_u32(&bars.acc_full[ab]), aph, lane);
       fence_after();
-      epilogue_tile<NM, TOut>(g, n, y0, true, tmem_base + ab * (NM * kC3) + t_lane, s_stage, s_shift, out, tid, [&]() {
+      epilogue_tile<NM, TOut>(g, n, y0, true, tmem_base + ab * (NM * kC3) + t_lane,
+                              s_stage + part * (NM * 128 * kStagePitch), s_shift, out, etid, EPI2 ? 4 * part : 0,
+                              EPI2 ? 4 * part + 4 : 8, 1 + part, [&]() {
         if (lane == 0) mbar_arrive(smem_u32(&bars.acc_empty[ab]));
       });
     }
@@ -496,7 +510,7 @@ conv3x3_c64_tc_pair_kernel(const float* __restrict__ x, const float* __restrict_
       const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
       mbar_wait_warp(smem_u32(&bars.acc_full[ab]), aph, lane);
       fence_after();
-      epilogue_tile<NM, float>(g, n, y0, store, tmem_base + ab * (NM * kC3) + t_lane, s_stage, s_shift, out, tid, [&]() {
+      epilogue_tile<NM, float>(g, n, y0, store, tmem_base + ab * (NM * kC3) + t_lane, s_stage, s_shift, out, tid, 0, 8, 1, [&]() {
         if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&bars.acc_empty[ab]), 0));
       });
     }
@@ -544,28 +558,48 @@ int launch_conv3_pair(const float* x, const float* wpk_pair, const float* shift,
   return AFS_OK;
 }
 
-template <int NM, bool BF16, typename TOut>
+template <int NM, bool BF16, typename TOut, bool EPI2>
 int launch_conv3(const void* x, const void* wpk, const float* shift, TOut* out, Conv3Geom g, cudaStream_t stream) {
   g.halo = (NM * 128 + 2 * g.HP + 2 + 7) & ~7;
   const size_t smem = (BF16 ? kWBytes3B : kWBytes3) + (BF16 ? kRing3B : kRing3) * (g.halo * 32u) +
-                      static_cast<size_t>(NM) * 128 * kStagePitch * 4 + kC3 * 4 + 256;
+                      static_cast<size_t>(EPI2 ? 2 : 1) * NM * 128 * kStagePitch * 4 + kC3 * 4 + 256;
   if (smem + 256u > 232448u) return AFS_ERR_UNSUPPORTED;  // 227 KB per CTA, static barriers included
-  AFS_CUDA_TRY(cudaFuncSetAttribute(conv3x3_c64_tc_kernel<NM, BF16, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  AFS_CUDA_TRY(cudaFuncSetAttribute(conv3x3_c64_tc_kernel<NM, BF16, TOut, EPI2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
   const int total = g.N * g.tiles_per_img;
   const int blocks = total < kNumSMs ? total : kNumSMs;  // persistent: one CTA per SM
-  conv3x3_c64_tc_kernel<NM, BF16, TOut><<<blocks, kThreads3, smem, stream>>>(x, wpk, shift, out, g);
+  conv3x3_c64_tc_kernel<NM, BF16, TOut, EPI2><<<blocks, EPI2 ? kThreads3E2 : kThreads3, smem, stream>>>(x, wpk, shift, out, g);
   AFS_LAUNCH_CHECK();
   return AFS_OK;
+}
+
+// Epilogue groups: AFS_CONV3_EPI2 = 0 / 1 forces one / two groups of four warps; default: two for the bf16 kernel
+// (its MMA phase is half as long), one for the TF32 kernel (MMA-bound, and a second staging tile does not fit next to
+// its 144 KB of weights: the launch returns AFS_ERR_UNSUPPORTED for the widest rows if forced).
+inline bool conv3_epi2(bool bf16) {
+  static const int forced = [] {
+    const char* e = getenv("AFS_CONV3_EPI2");
+    return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
+  }();
+  return forced < 0 ? bf16 : forced == 1;
 }
 
 template <bool BF16, typename TOut>
 int dispatch_conv3(int NM, const void* x, const void* wpk, const float* shift, TOut* out, const Conv3Geom& g,
                    cudaStream_t stream) {
+  if (conv3_epi2(BF16)) {
+    int rc;
+    switch (NM) {
+      case 1: rc = launch_conv3<1, BF16, TOut, true>(x, wpk, shift, out, g, stream); break;
+      case 2: rc = launch_conv3<2, BF16, TOut, true>(x, wpk, shift, out, g, stream); break;
+      default: rc = launch_conv3<3, BF16, TOut, true>(x, wpk, shift, out, g, stream); break;
+    }
+    if (rc != AFS_ERR_UNSUPPORTED) return rc;  // else: no room for the second staging tile -> one group
+  }
   switch (NM) {
-    case 1: return launch_conv3<1, BF16, TOut>(x, wpk, shift, out, g, stream);
-    case 2: return launch_conv3<2, BF16, TOut>(x, wpk, shift, out, g, stream);
-    default: return launch_conv3<3, BF16, TOut>(x, wpk, shift, out, g, stream);
+    case 1: return launch_conv3<1, BF16, TOut, false>(x, wpk, shift, out, g, stream);
+    case 2: return launch_conv3<2, BF16, TOut, false>(x, wpk, shift, out, g, stream);
+    default: return launch_conv3<3, BF16, TOut, false>(x, wpk, shift, out, g, stream);
   }
 }
 

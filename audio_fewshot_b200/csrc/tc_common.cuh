@@ -200,6 +200,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
       : "r"(taddr));
 }
 
+// 4 consecutive accumulator columns of this thread's TMEM lane (no wait: pair with tmem_wait_ld)
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr));
+}
+
 // 16 consecutive accumulator columns of this thread's TMEM lane (no wait: pair with tmem_wait_ld)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(

@@ -27,6 +27,9 @@ Keys of the JSON line (default mode `eval`):
            HBM kernels against the copy peak, tcgen05 TF32 kernels against a TF32 matmul peak measured in this run.
 `gpu_eager_baseline` the reference's op sequence in plain PyTorch on the same GPU (torch.stft log-mel, the
            nn.Module graph, broadcast ProtoLayer arithmetic): SURVEY 8d's "real bar".
+`bf16_backbone` the same step with Conv64F.precision = "bf16" (stem writes bf16, blocks 2-3 as bf16 tcgen05 MMAs):
+           the reduced-precision path the north star asks to be stated separately, with its argmax-flip count and
+           logit deviation against this run's TF32 logits.  Never folded into `value`.
 `s1`       the same pipeline on BASELINE configs[0]'s clips (1 s @ 16 kHz, hop 102 -> the same [1,128,157]).
 `cpu_baseline` / `--impl reference`: the oracle port of the reference path (torch.stft front-end spec ->
            reference Conv64F arithmetic -> ProtoLayer -> majority vote) on the box's host cores, at the same
@@ -65,6 +68,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if 
 METRIC = "episodes/sec (5w5s15q, waveform->logits)"
 WORKLOAD = "ProtoNet Conv64F 5w5s15q, 100 clips/episode, 5 s @ 16 kHz -> log-mel [1,128,157] (C1, shape S5)"
 CONV1_FLOP_PER_CLIP = 2 * 9 * 64 * 128 * 157                 # block 1: 3x3, 1 -> 64 channels, useful flops
+CONV1_BYTES_PER_CLIP = 4 * 128 * 157 + 4 * 64 * 42 * 52          # block 1: image read + pooled NHWC output written
 CONV3_FLOP_PER_CLIP = 2 * 9 * 64 * 64 * (42 * 52 + 14 * 17)  # blocks 2 + 3: 3x3, 64 -> 64 channels
 
 
@@ -389,6 +393,10 @@ def roofline_all(rows, n_clips, hbm_peak, tf32_peak):
             entry.update(bound="tensor", achieved=ach, peak=tf32_peak, unit="TFLOP/s", frac=ach / tf32_peak,
                          note="useful TF32 flops (zero padding of K and junk GEMM rows not counted) over a TF32 "
                               "torch.matmul 8192^3 measured in this run")
+            if "conv1_tc" in name:  # K = 9 taps: the stem's floor is its NHWC output, not the tensor pipe
+                hb = CONV1_BYTES_PER_CLIP * n_clips / (us * 1e-6) / 1e9
+                entry.update(hbm_achieved=hb, hbm_frac=hb / hbm_peak,
+                             hbm_note="4*128*157 B read + 4*64*42*52 B written per clip over the copy peak")
         out.append(entry)
     return out
 
@@ -527,6 +535,30 @@ def run_eval(args, rank, world, local_rank):
                 "note": "same public call, host waveforms quantised to int16 PCM (afs_logmel_fwd_pcm16 converts on "
                         "load); `e2e` above is the fp32-host-buffer figure"}
             del host_pcm
+
+            # ---- the separately stated bf16 backbone path (north star): same step, same inputs,
+            # Conv64F.precision = "bf16" (stem writes bf16, blocks 2-3 as bf16 tcgen05 MMAs).  Extra key, not `value`.
+            ref_logits = [step_device(b)[0].clone() for b in range(2)]
+            emb.precision = "bf16"
+            try:
+                for i in range(args.warmup):
+                    step_device(i)
+                ms_b16, (_, acc_b16) = timed(ranks, lambda i: step_device(i), args.steps)
+                flips, dev_rel = 0, 0.0
+                for b in range(2):
+                    lb = step_device(b)[0]
+                    flips += int((lb.argmax(1) != ref_logits[b].argmax(1)).sum().item())
+                    dev_rel = max(dev_rel, float(((lb - ref_logits[b]).abs().max() / ref_logits[b].abs().max()).item()))
+            finally:
+                emb.precision = None
+            extras["bf16_backbone"] = {
+                "value": args.steps * E * world / (ms_b16 * 1e-3), "unit": "episodes/sec",
+                "ms_per_step": ms_b16 / args.steps, "accuracy_pct": float(acc_b16.item()),
+                "argmax_flips": flips, "queries_compared": 2 * E * W * Q, "max_logit_deviation_rel": dev_rel,
+                "note": "reduced-precision path stated separately from `value` (which stays in the reference's TF32 "
+                        "class): bf16 activations between blocks 1-3, bf16 weights, fp32 accumulation; flips and "
+                        "deviation are against this run's TF32 logits on the two bench batches"}
+            del ref_logits
 
         if rank == 0 and not args.no_extras:
             hbm_peak, _ = peaks()
