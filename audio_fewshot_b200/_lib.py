@@ -94,6 +94,8 @@ SIGNATURES = {
                                         C.c_void_p]),
     "afs_add_bias_act_pool_nhwc_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                                  C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]),
+    "afs_add_bias_act_pool_nhwc_bf16_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                      C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "afs_proto_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "afs_proto_tc_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "afs_proto_fwd_tc": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -33,6 +33,10 @@ class FoldedTrunkMixin:
     """Shared by ResNet and ResNetBdc: the folded channels-last evaluation of layer1..layer4."""
 
     fast_eval = True
+    # "bf16": the separately stated reduced-precision inference trunk (SURVEY 8f row 4): bf16 channels-last cuDNN
+    # convolutions with the BatchNorms folded in, the block tails as csrc/pool.cu's bf16 kernel (fp32 arithmetic), the
+    # last block's output in fp32 for the heads.  None / "tf32": the reference's precision class (the parity path).
+    precision = None
 
     def _inference_ok(self, x):
         return (self.fast_eval and not self.training and not torch.is_grad_enabled() and x.is_cuda
@@ -62,7 +66,36 @@ class FoldedTrunkMixin:
         self._trunk_cache = {"key": key, "blocks": blocks}
         return blocks
 
+    def _folded_trunk_bf16(self):
+        blocks = self._folded_trunk()
+        cache = self._trunk_cache
+        if "bf16" not in cache:
+            to16 = lambda w: None if w is None else w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            cache["bf16"] = [(to16(w1), b1, to16(w2), b2, to16(w3), b3, to16(wd), slope, k)
+                             for (w1, b1, w2, b2, w3, b3, wd, slope, k) in blocks]
+        return cache["bf16"]
+
+    def _trunk_inference_bf16(self, x):
+        x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        if x.shape[1] == 1:
+            n, c, h, w = x.shape
+            x = x.as_strided((n, c, h, w), (h * w, 1, w, 1))
+        layers = (self.layer1, self.layer2, self.layer3, self.layer4)
+        for i, (layer, (w1, b1, w2, b2, w3, b3, wd, slope, k)) in enumerate(zip(layers, self._folded_trunk_bf16())):
+            layer[0].num_batches_tracked += 1
+            o = ops.add_bias_act_pool_bf16(F.conv2d(x, w1, padding=1), None, b1, slope, 1, inplace=True)
+            o = ops.add_bias_act_pool_bf16(F.conv2d(o, w2, padding=1), None, b2, slope, 1, inplace=True)
+            o = F.conv2d(o, w3, padding=1)
+            r = x if wd is None else F.conv2d(x, wd)
+            x = ops.add_bias_act_pool_bf16(o, r, b3, slope, k,
+                                           out_dtype=torch.float32 if i == len(layers) - 1 else torch.bfloat16)
+        return x
+
     def _trunk_inference(self, x):
+        if self.precision == "bf16":
+            return self._trunk_inference_bf16(x)
+        if self.precision not in (None, "tf32"):
+            raise ValueError("precision must be None, 'tf32' or 'bf16'")
         x = x.contiguous(memory_format=torch.channels_last)
         if x.shape[1] == 1:
             # a 1-channel tensor is both NCHW- and NHWC-contiguous; give it unambiguous channels-last strides so

@@ -67,7 +67,7 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
   extern __shared__ __align__(128) uint8_t s_buf[];  // [kNBuf1][kTileBytes] patches | [kWBytes] weights | [8][kStageBytes] output staging
   __shared__ __align__(8) uint64_t s_bars[kBars1];
   __shared__ uint32_t s_tmem;
-  __shared__ float s_shift[kCh1];
+  __shared__ __align__(16) float s_shift[kCh1];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -207,28 +207,32 @@ conv1_tc_kernel(const float* __restrict__ x, int64_t total_pix, int H, int Wd, i
         uint32_t v0[32], v1[32], v2[32];
         tmem_ld32_nowait(t_row + as * kAccCols + 0 * kCh1, v0);
         tmem_ld32_nowait(t_row + as * kAccCols + 1 * kCh1, v1);
-        tmem_wait_ld();
-        tmem_ld32_nowait(t_row + as * kAccCols + 2 * kCh1, v2);  // in flight behind the maxima of the first two windows
-        if (g == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) best[j] = fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) best[j] = fmaxf(fmaxf(best[j], __uint_as_float(v0[j])), __uint_as_float(v1[j]));
-        }
+        tmem_ld32_nowait(t_row + as * kAccCols + 2 * kCh1, v2);
         tmem_wait_ld();
         fence_before();
         mbar_arrive(BAR1(kAccEmpty + as));  // this thread's part of the accumulator set is in registers
+        if (g == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) best[j] = fmaxf(best[j], __uint_as_float(v2[j]));
+          for (int j = 0; j < 32; ++j)
+            best[j] = fmaxf(fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])), __uint_as_float(v2[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            best[j] = fmaxf(fmaxf(best[j], __uint_as_float(v0[j])), __uint_as_float(v1[j]));
+            best[j] = fmaxf(best[j], __uint_as_float(v2[j]));
+          }
+        }
       }
       __syncwarp();  // the previous tile's staging reads are done
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
+        // one 128-bit broadcast load of four shifts (a scalar load per channel was 12 % of the kernel's stall samples)
+        const float4 sh4 = *reinterpret_cast<const float4*>(s_shift + 32 * half + 4 * c4);
+        const float sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
         float q[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float v = best[4 * c4 + k] + s_shift[32 * half + 4 * c4 + k];
+          const float v = best[4 * c4 + k] + sh[k];
           q[k] = LEAKY ? fmaxf(v, v * slope) : fmaxf(v, 0.f);  // 0 <= slope < 1: max(v, slope v) is LeakyReLU
         }
         *reinterpret_cast<float4*>(stage + lane * kStagePitch + 4 * c4) = make_float4(q[0], q[1], q[2], q[3]);

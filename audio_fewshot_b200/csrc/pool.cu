@@ -6,6 +6,8 @@
 // one thread per output element, scalar loads.  Here a thread owns 4 consecutive channels of one pooled
 // pixel: nine 128-bit loads (consecutive threads -> consecutive channels: fully coalesced), one 128-bit
 // store.  HBM-bound: 4*C*(H*W + (H/3)*(W/3)) bytes per image.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace afs {
@@ -81,8 +83,112 @@ add_bias_act_pool_nhwc_kernel(const float4* __restrict__ a, const float4* __rest
   }
 }
 
+// The same tail for the separately stated bf16 trunk (ResNet.precision = "bf16"): a and b are bf16 channels-last
+// convolution outputs, a thread owns 8 consecutive channels of one pooled pixel (one 128-bit load per operand and window
+// position), sum, max, bias and activation in fp32, one rounding at the store (bf16) or none (fp32 output of the last
+// block, which feeds the fp32 heads).
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+template <int K, bool OUT_F32>
+__global__ void __launch_bounds__(256)
+add_bias_act_pool_nhwc_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const float4* __restrict__ bias,
+                                   int64_t total, int H, int W, int C8, int PH, int PW, float slope, void* out_) {
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C8);
+    int64_t r = idx / C8;
+    const int pw = static_cast<int>(r % PW);
+    r /= PW;
+    const int ph = static_cast<int>(r % PH);
+    const int64_t n = r / PH;
+    const int64_t base = ((n * H + K * ph) * W + K * pw) * C8 + c;
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < K; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) {
+        const int64_t o = base + (static_cast<int64_t>(dy) * W + dx) * C8;
+        float v[8];
+        unpack8(a[o], v);  // plain loads: `out` may alias `a` when K == 1 and the output is bf16
+        if (b != nullptr) {
+          float w[8];
+          unpack8(__ldg(b + o), w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += w[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+      }
+    }
+    if (bias != nullptr) {
+      const float4 b0 = __ldg(bias + 2 * c), b1 = __ldg(bias + 2 * c + 1);
+      m[0] += b0.x; m[1] += b0.y; m[2] += b0.z; m[3] += b0.w;
+      m[4] += b1.x; m[5] += b1.y; m[6] += b1.z; m[7] += b1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = m[i] > 0.f ? m[i] : m[i] * slope;
+    if (OUT_F32) {
+      float4* o = static_cast<float4*>(out_) + 2 * idx;
+      o[0] = make_float4(m[0], m[1], m[2], m[3]);
+      o[1] = make_float4(m[4], m[5], m[6], m[7]);
+    } else {
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(m[0], m[1]), p1 = __floats2bfloat162_rn(m[2], m[3]);
+      const __nv_bfloat162 p2 = __floats2bfloat162_rn(m[4], m[5]), p3 = __floats2bfloat162_rn(m[6], m[7]);
+      uint4 v;
+      v.x = *reinterpret_cast<const uint32_t*>(&p0); v.y = *reinterpret_cast<const uint32_t*>(&p1);
+      v.z = *reinterpret_cast<const uint32_t*>(&p2); v.w = *reinterpret_cast<const uint32_t*>(&p3);
+      static_cast<uint4*>(out_)[idx] = v;
+    }
+  }
+}
+
+template <int K>
+void launch_tail_bf16(unsigned g, cudaStream_t st, const uint4* a, const uint4* b, const float4* bias, int64_t total, int H,
+                      int W, int C8, int PH, int PW, float slope, void* out, bool out_f32) {
+  if (out_f32) add_bias_act_pool_nhwc_bf16_kernel<K, true><<<g, 256, 0, st>>>(a, b, bias, total, H, W, C8, PH, PW, slope, out);
+  else add_bias_act_pool_nhwc_bf16_kernel<K, false><<<g, 256, 0, st>>>(a, b, bias, total, H, W, C8, PH, PW, slope, out);
+}
+
 }  // namespace
 }  // namespace afs
+
+extern "C" int afs_add_bias_act_pool_nhwc_bf16_fwd(const void* a, const void* b, const float* bias, int32_t N, int32_t H,
+                                                   int32_t W, int32_t C, float negative_slope, int32_t k, void* out,
+                                                   int32_t out_f32, afs_stream_t stream_) {
+  using namespace afs;
+  if (a == nullptr || out == nullptr || N < 0 || k < 1 || k > 3 || H < k || W < k || C < 8 || (C & 7) != 0 ||
+      negative_slope < 0.f)
+    return AFS_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(bias) |
+       reinterpret_cast<uintptr_t>(out)) & 15)
+    return AFS_ERR_INVALID_ARG;
+  if (out == a && (k != 1 || out_f32)) return AFS_ERR_INVALID_ARG;  // in place only without pooling, same dtype
+  if (N == 0) return AFS_OK;
+  const int PH = H / k, PW = W / k, C8 = C / 8;
+  const int64_t total = static_cast<int64_t>(N) * PH * PW * C8;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+  const uint4* a8 = static_cast<const uint4*>(a);
+  const uint4* b8 = static_cast<const uint4*>(b);
+  const float4* s4 = reinterpret_cast<const float4*>(bias);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const unsigned g = static_cast<unsigned>(blocks);
+  if (k == 1) launch_tail_bf16<1>(g, st, a8, b8, s4, total, H, W, C8, PH, PW, negative_slope, out, out_f32 != 0);
+  else if (k == 2) launch_tail_bf16<2>(g, st, a8, b8, s4, total, H, W, C8, PH, PW, negative_slope, out, out_f32 != 0);
+  else launch_tail_bf16<3>(g, st, a8, b8, s4, total, H, W, C8, PH, PW, negative_slope, out, out_f32 != 0);
+  AFS_LAUNCH_CHECK();
+  return AFS_OK;
+}
 
 extern "C" int afs_add_bias_act_pool_nhwc_fwd(const float* a, const float* b, const float* bias, int32_t N, int32_t H,
                                               int32_t W, int32_t C, float negative_slope, int32_t k, float* out,

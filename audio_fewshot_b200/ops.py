@@ -363,6 +363,36 @@ def add_bias_act_pool(a, b=None, bias=None, negative_slope=0.0, k=1, inplace=Fal
     return out
 
 
+def add_bias_act_pool_bf16(a, b=None, bias=None, negative_slope=0.0, k=1, inplace=False, out_dtype=torch.bfloat16):
+    """add_bias_act_pool for the bf16 trunk: a, b channels_last [N, C, H, W] CUDA bf16 (C % 8 == 0), bias fp32; the
+    arithmetic is fp32; the result is bf16 (optionally in place when k == 1) or fp32."""
+    _need_cuda(a, "a", torch.bfloat16)
+    if a.dim() != 4 or a.shape[1] % 8 != 0:
+        raise ValueError("a must be [N, C, H, W] with C % 8 == 0")
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("out_dtype must be float32 or bfloat16")
+    if not a.is_contiguous(memory_format=torch.channels_last):
+        a = a.contiguous(memory_format=torch.channels_last)
+    if b is not None:
+        _need_cuda(b, "b", torch.bfloat16)
+        if b.shape != a.shape:
+            raise ValueError("a and b must have the same shape")
+        b = b.contiguous(memory_format=torch.channels_last)
+    if bias is not None:
+        _need_cuda(bias, "bias")
+        bias = bias.contiguous()
+    N, Cc, H, Wd = a.shape
+    if inplace and (k != 1 or out_dtype != torch.bfloat16):
+        raise ValueError("in-place only without pooling and with a bf16 result")
+    out = a if inplace else torch.empty((N, Cc, H // k, Wd // k), dtype=out_dtype, device=a.device,
+                                        memory_format=torch.channels_last)
+    _lib.check(_lib.lib().afs_add_bias_act_pool_nhwc_bf16_fwd(_ptr(a), _ptr(b), _ptr(bias), N, H, Wd, Cc,
+                                                              float(negative_slope), int(k), _ptr(out),
+                                                              1 if out_dtype == torch.float32 else 0, _stream()),
+               "afs_add_bias_act_pool_nhwc_bf16_fwd")
+    return out
+
+
 # --------------------------------------------------------------------------- heads
 def _proto_call(feat, cls_row, E, W, S, mode, want_pred):
     _need_cuda(feat, "feat")

@@ -46,6 +46,9 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--module-graph", action="store_true",
                     help="run the backbones as the plain module graph (the reference's op sequence) for comparison")
+    ap.add_argument("--bf16", action="store_true",
+                    help="run the backbones on the separately stated bf16 path (emb_func.precision = 'bf16') and report "
+                         "the argmax flips against the parity path on the same batches")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench_configs.py needs a CUDA device (no CPU fallback)")
@@ -72,6 +75,13 @@ def main():
                 model.emb_func._inference_ok = lambda x: False
         with torch.no_grad():
             step = lambda i: model([batches[i % 2], None, repeats, E * W * S], **fwd_kw)
+            if args.bf16 and hasattr(model.emb_func, "precision"):
+                ref = [step(b)[0].clone() for b in range(2)]
+                model.emb_func.precision = "bf16"
+                flips = sum(int((step(b)[0].argmax(1) != ref[b].argmax(1)).sum().item()) for b in range(2))
+                what += " [bf16 backbone]"
+                note += "; argmax flips vs the parity path: %d of %d queries" % (flips, 2 * ref[0].shape[0])
+                del ref
             step(0)
             l0 = ops.launch_count()
             step(1)

@@ -230,6 +230,13 @@ int afs_add_bias_act_pool_nhwc_fwd(const float* a, const float* b, const float* 
                                    int32_t W, int32_t C, float negative_slope, int32_t k, float* out,
                                    afs_stream_t stream);
 
+/* (1d-bf16) The same tail for the separately stated bf16 trunk (ResNet.precision = "bf16"): a, b bf16
+ * NHWC (b nullable), bias fp32 [C] (nullable), C % 8 == 0; sum, max, bias and activation in fp32; out bf16, or fp32 when
+ * out_f32 != 0 (the last block feeds the fp32 heads).  out may alias a when k == 1 and out_f32 == 0.                  */
+int afs_add_bias_act_pool_nhwc_bf16_fwd(const void* a, const void* b, const float* bias, int32_t N, int32_t H,
+                                        int32_t W, int32_t C, float negative_slope, int32_t k, void* out,
+                                        int32_t out_f32, afs_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Episode row table shared by the heads (replaces the host slicing of
  * AbstractModel.split_by_episode, libfewshot_core/model/abstract_model.py:176-332).

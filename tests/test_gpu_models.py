@@ -250,6 +250,55 @@ def test_resnet12_inference_path_equals_module_graph(cuda, name):
     assert (fast - slow).abs().max().item() <= 1e-4 * slow.abs().max().item()
 
 
+def test_add_bias_act_pool_bf16_kernel(cuda):
+    """csrc/pool.cu, bf16 operands: fp32 arithmetic on the bf16 inputs, one rounding at the bf16 store, none at the
+    fp32 store; in place for k == 1."""
+    from audio_fewshot_b200 import ops
+    F = torch.nn.functional
+    for (shape, k, slope, with_b, with_bias, odt) in [((3, 64, 128, 157), 2, 0.1, True, True, torch.bfloat16),
+                                                      ((2, 160, 64, 78), 2, 0.1, True, True, torch.bfloat16),
+                                                      ((2, 640, 16, 19), 1, 0.1, True, True, torch.float32),
+                                                      ((2, 8, 7, 9), 3, 0.0, False, True, torch.float32),
+                                                      ((2, 64, 5, 6), 1, 0.0, False, False, torch.bfloat16)]:
+        a = torch.randn(shape, device=cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        b = torch.randn(shape, device=cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if with_b else None
+        bias = torch.randn(shape[1], device=cuda) if with_bias else None
+        want = a.float() if b is None else a.float() + b.float()
+        if bias is not None:
+            want = want + bias.view(1, -1, 1, 1)
+        want = F.leaky_relu(want, slope)
+        if k > 1:
+            want = F.max_pool2d(want, k, k)
+        got = ops.add_bias_act_pool_bf16(a, b, bias, slope, k, out_dtype=odt)
+        assert got.shape == want.shape and got.dtype == odt
+        if odt == torch.float32:
+            assert (got - want).abs().max().item() <= 1e-6 * max(want.abs().max().item(), 1.0)
+        else:
+            assert torch.equal(got, want.to(torch.bfloat16))
+        if k == 1 and odt == torch.bfloat16:
+            a2 = a.clone(memory_format=torch.channels_last)
+            r = ops.add_bias_act_pool_bf16(a2, b, bias, slope, 1, inplace=True)
+            assert r.data_ptr() == a2.data_ptr() and torch.equal(r, got)
+
+
+@pytest.mark.parametrize("name", ["resnet12", "resnet12bdc"])
+def test_resnet12_bf16_trunk_is_close_to_the_parity_path(cuda, name):
+    """ResNet.precision = 'bf16' (stated separately from the parity path): bf16 cuDNN convolutions + the bf16 tail
+    kernel; features stay within 5e-2 of the fp32 path's feature range, fp32 output, our kernels on the path."""
+    from audio_fewshot_b200 import ops
+    net = _net(cuda, name)
+    x = torch.from_numpy((np.random.default_rng(10).standard_normal((5, 1, 128, 157)) * 0.7).astype(np.float32)).to(cuda)
+    with torch.no_grad():
+        ref = net(x)
+        net.precision = "bf16"
+        n0 = ops.launch_count()
+        fast = net(x)
+        assert ops.launch_count() >= n0 + 12
+    assert fast.dtype == torch.float32 and fast.shape == ref.shape
+    assert not torch.equal(fast, ref)
+    assert (fast - ref).abs().max().item() <= 5e-2 * ref.abs().max().item()
+
+
 def test_add_bias_act_pool_kernel(cuda):
     from audio_fewshot_b200 import ops
     F = torch.nn.functional

@@ -1,3 +1,3 @@
-python -m pytest tests/test_gpu_models.py -x -q -m gpu -k "conv3x3 or conv64f or bf16 or repeat" 2>&1 | tail -3
-echo "conv3 default (bf16: two epilogue groups)"; python tools/run_backbone_bf16.py 2>&1 | grep -E "block|Conv64F"
-echo "conv3 EPI2=0"; AFS_CONV3_EPI2=0 python tools/run_backbone_bf16.py 2>&1 | grep -E "block|Conv64F"
+python -m pytest tests/test_gpu_models.py -x -q -m gpu -k "conv1 or stem or repeat or conv64f" 2>&1 | tail -2
+python tools/run_backbone_bf16.py 2>&1 | grep -E "stem|Conv64F"
+python -m pytest tests/test_gpu_models.py -x -q -m gpu -k "bf16 or resnet12 or add_bias" 2>&1 | tail -3
