@@ -87,6 +87,9 @@ def main():
     ms, mn = timeit(lambda: ops.conv1_bn_act_pool3(img, w, b, 0.0, tf32=True), flush=flush)
     report("conv1_tc_kernel (tcgen05 TF32)", "clip", 800, 4 * 128 * 157 + 4 * 64 * 42 * 52, ms, mn,
            flops_per_unit=2 * 64 * 42 * 52 * 81, note="useful flops; the MMAs pad K 9 -> 16")
+    ms, mn = timeit(lambda: ops.conv1_bn_act_pool3(img, w, b, 0.0, tf32=True, out_dtype=torch.bfloat16), flush=flush)
+    report("conv1_tc_kernel, bf16 output (stated separately)", "clip", 800, 4 * 128 * 157 + 2 * 64 * 42 * 52, ms, mn,
+           flops_per_unit=2 * 64 * 42 * 52 * 81, note="same TF32 arithmetic, rounded to bf16 at the store")
     act = torch.randn(800, 64, 42, 52, device=dev).contiguous(memory_format=torch.channels_last)
     ms, mn = timeit(lambda: ops.maxpool3_channels_last(act), flush=flush)
     report("maxpool3_nhwc_kernel [800,64,42,52]", "clip", 800, 4 * 64 * (42 * 52 + 14 * 17), ms, mn)
@@ -103,6 +106,11 @@ def main():
         ms, mn = timeit(lambda: ops.conv3x3_c64_bn_act(act, packed, bias, 0.0, pool=True), flush=flush)
         report("conv3x3_c64_tc_kernel " + tag, "clip", 800, nbytes, ms, mn, flops_per_unit=flops,
                note="tcgen05 TF32, pool fused; useful flops")
+        act16 = act.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        packed16 = torch.from_numpy(ops.conv3x3_c64_pack_weights_bf16(wt)).to(dev).view(torch.bfloat16)
+        ms, mn = timeit(lambda: ops.conv3x3_c64_bn_act_bf16(act16, packed16, bias, 0.0, pool=True), flush=flush)
+        report("conv3x3_c64_tc_kernel bf16 (stated separately) " + tag, "clip", 800, nbytes // 2, ms, mn, flops_per_unit=flops,
+               note="tcgen05 kind::f16 bf16 operands, K = 16, two epilogue groups, bf16 in / bf16 out; useful flops")
         torch.backends.cudnn.allow_tf32 = True
         ms, mn = timeit(lambda: ops.maxpool3_channels_last(
             torch.cudnn_convolution_relu(act, wcl, bias, (1, 1), (1, 1), (1, 1), 1)), flush=flush)
