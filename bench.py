@@ -83,6 +83,9 @@ def parse():
                     help="episodes per rank per step (default: 32 for eval, 2 for train, 4 for eval10k)")
     ap.add_argument("--episodes", type=int, default=10000, help="eval10k: total episodes of the job")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bf16-backbone", action="store_true",
+                    help="mode eval10k only: run the trunk on the separately stated bf16 path (emb_func.precision = "
+                         "'bf16'); the line says so in dtype and config")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline_all / gpu_eager_baseline / s1 / pcm16 legs")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bound of the cpu_baseline sample")
     ap.add_argument("--ref-seconds", type=float, default=150.0, help="--impl reference: bound of the whole run")
@@ -775,6 +778,8 @@ def run_eval10k(args, rank, world, local_rank):
                                              num_channels=1))
     model = arch.ProtoNet(way_num=w, shot_num=s, query_num=q, test_way=w, test_shot=s, test_query=q,
                           emb_func=emb, device=dev).to(dev).eval()
+    if args.bf16_backbone:
+        emb.precision = "bf16"
     front = LogMelFrontEnd(sample_rate=SR, hop_length=HOP, n_mels=N_MELS, mean=mean, std=std).to(dev).eval()
     repeats = torch.ones(E * w * q, dtype=torch.long)
     target = torch.arange(w, device=dev).repeat_interleave(q)
@@ -817,10 +822,12 @@ def run_eval10k(args, rank, world, local_rank):
         return
     emit({"metric": "episodes/sec (5w1s15q ResNet-12, waveform->logits, %d episodes incl. accuracy gather + 95%% CI)" % n_total,
           "value": n_total / (ms * 1e-3), "unit": "episodes/sec", "n_gpus": world, "steps": steps, "warmup": args.warmup,
-          "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+          "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+          "dtype": "bf16 trunk (stated separately), f32 front-end and head" if args.bf16_backbone else "f32",
           "data": "synthetic",
           "config": {"workload": "ProtoNet ResNet-12 5w1s15q, 80 clips/episode, 5 s @ 16 kHz (BASELINE configs[1], C2)",
                      "mode": "eval10k", "episodes": n_total, "episodes_per_step_per_gpu": E,
+                     "backbone_precision": "bf16 (opt-in reduced-precision path)" if args.bf16_backbone else "tf32 class (parity path)",
                      "parallelism": "episodes sharded round-robin over %d rank(s); ONE all_gather of %d per-episode "
                                     "accuracies per rank (%d bytes) at the end, then mean_confidence_interval"
                                     % (world, steps * E, 4 * steps * E),
