@@ -671,7 +671,8 @@ def run_eval(args, rank, world, local_rank):
                 "accuracy_pct": acc_e2e, "h2d_gbs_per_gpu": e2e_gbs, "h2d_probe_gbs_per_gpu": probe_gbs,
                 "host_roofline_frac": e2e_gbs / probe_gbs,
                 "note": "h2d_probe = plain pinned cudaMemcpyAsync of the same buffers by all %d rank(s) at once "
-                        "(slowest rank); the e2e leg is bound by that copy, not by the 3.2 ms of device work" % world},
+                        "(slowest rank); the e2e leg is bound by that copy, not by the %.1f ms of device work"
+                        % (world, ms_dev / args.steps)},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "logmel_pair_kernel<false, float, true> (fused waveform->log-mel, warp-per-frame-pair engine)",
                      "bound": "hbm",
