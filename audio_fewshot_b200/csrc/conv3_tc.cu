@@ -46,10 +46,9 @@ namespace {
 using namespace tc;
 
 constexpr int kC3 = 64;                       // channels in == channels out == UMMA N
-constexpr int kThreads3 = 256 + 32 * 3;        // 4 epilogue + 4 producer warps + up to 3 MMA-issuing warps
-constexpr int kThreads3E2 = kThreads3 + 128;   // + a second group of 4 epilogue warps (warps 11-14)
+constexpr int kThreads3 = 256 + 32 * 4;        // 4 epilogue + 4 producer warps + up to 4 MMA-issuing warps
+constexpr int kThreads3E2 = kThreads3 + 128;   // + a second group of 4 epilogue warps (warps 12-15)
 constexpr int kRing3 = 4;                     // operand ring stages (8 input channels each)
-constexpr int kAhead3 = 3;                    // stages a producer keeps in flight before it must signal the oldest
 constexpr uint32_t kTapKcBytes = 2u * kC3 * 16u;          // weights of one (tap, 8-channel group): 2 KB
 constexpr uint32_t kWBytes3 = 9u * 8u * kTapKcBytes;      // 147 456 B
 // bf16 operands (kind::f16, K = 16 per MMA): a ring stage holds 16 input channels in the same 32 bytes per pixel, the
@@ -57,11 +56,16 @@ constexpr uint32_t kWBytes3 = 9u * 8u * kTapKcBytes;      // 147 456 B
 // and the resident weights shrink to 72 KB, which pays for a 6-stage ring (one and a half tiles of look-ahead) and the
 // second epilogue group's staging tile.
 constexpr int kRing3B = 6;
-constexpr int kAhead3B = 4;
 constexpr uint32_t kWBytes3B = 9u * 4u * kTapKcBytes;     // 73 728 B
-constexpr int kMaxPix3 = 9;                   // 16-byte copies per producer thread and stage (halo <= 576)
+constexpr int kMaxPix3 = 10;                  // 16-byte copies per producer thread and stage (halo <= 640)
 constexpr int kCg3 = 8;                       // channels per epilogue pass
 constexpr int kStagePitch = 12;               // floats per staged position (8 channels + pad: conflict-free stores)
+
+// Ring depth.  Four accumulators per tile (9 image rows of block 2 instead of 6: 95 % instead of 81 % of the accumulator
+// rows are useful) need 20 KB stages and a 24 KB staging tile: next to the 144 KB of TF32 weights that leaves 3 stages.
+__host__ __device__ constexpr int ring_stages(bool bf16, int nm) {
+  return bf16 ? (nm == 4 ? 5 : kRing3B) : (nm == 4 ? 3 : kRing3);
+}
 
 template <int RING>
 struct Bars3T {
@@ -91,6 +95,8 @@ struct Conv3Geom {
   int N, H, W, HP;        // HP = W + 2: padded row pitch
   int R;                  // image rows per tile
   int tiles_per_img;
+  int rows;               // image rows the tiles cover (a multiple of 3 when pooling)
+  int stage_pos;          // positions the pooling staging tile holds: R * HP rounded up to 8
   int halo;               // padded pixels held per stage: NM*128 + 2*HP + 2, rounded up to a multiple of 8
   int pool;               // 1: MaxPool2d(3,3) fused
   int PH, PW;             // pooled extent (pool == 1)
@@ -201,9 +207,11 @@ __device__ __forceinline__ void epilogue_tile(const Conv3Geom& g, int n, int y0,
       }
       const int q = m * 128 + tid;  // linear position inside the tile
       if (g.pool) {
-        float4* d = reinterpret_cast<float4*>(s_stage + q * kStagePitch);
-        d[0] = make_float4(r[0], r[1], r[2], r[3]);
-        d[1] = make_float4(r[4], r[5], r[6], r[7]);
+        if (q < g.stage_pos) {  // positions past the tile's last row are junk rows of the last accumulator
+          float4* d = reinterpret_cast<float4*>(s_stage + q * kStagePitch);
+          d[0] = make_float4(r[0], r[1], r[2], r[3]);
+          d[1] = make_float4(r[4], r[5], r[6], r[7]);
+        }
       } else {
         const int yy = q / g.HP, xx = q - yy * g.HP;
         if (store && yy < g.R && y0 + yy < g.H && xx < g.W) {
@@ -254,8 +262,8 @@ template <int NM, bool BF16, typename TOut, bool EPI2>
 __global__ void __launch_bounds__(EPI2 ? kThreads3E2 : kThreads3, 1)
 conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, const float* __restrict__ shift,
                       TOut* __restrict__ out, const Conv3Geom g) {
-  constexpr int RING = BF16 ? kRing3B : kRing3;
-  constexpr int AHEAD = BF16 ? kAhead3B : kAhead3;
+  constexpr int RING = ring_stages(BF16, NM);
+  constexpr int AHEAD = RING - (BF16 ? 2 : 1);
   constexpr int KC = BF16 ? 4 : 8;                       // ring stages (K groups) per tile
   constexpr uint32_t kWB = BF16 ? kWBytes3B : kWBytes3;  // resident weights
   extern __shared__ __align__(16) uint8_t s_dyn_raw[];  // [weights][ring][staging][shift] after 256-byte alignment
@@ -270,8 +278,9 @@ conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, 
   const uint32_t w_base = smem_u32(s_dyn);
   const uint32_t ring_base = w_base + kWB;
   float* s_stage = reinterpret_cast<float*>(s_dyn + kWB + RING * stage_bytes);
-  float* s_shift = s_stage + (EPI2 ? 2 : 1) * NM * 128 * kStagePitch;
+  float* s_shift = s_stage + (EPI2 ? 2 : 1) * g.stage_pos * kStagePitch;
   constexpr uint32_t kTmemCols = NM == 1 ? 128u : (NM == 2 ? 256u : 512u);  // 2 x NM accumulators of 64 columns
+  static_assert(NM >= 1 && NM <= 4, "two sets of NM 64-column accumulators must fit 512 TMEM columns");
   constexpr uint32_t kIdesc = BF16 ? idesc_bf16(128, kC3) : idesc_tf32(128, kC3);
 
   {  // resident weights (already in operand layout) and the folded shift
@@ -307,7 +316,7 @@ conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, 
     // ======================= producers =======================
     producer_loop<RING, AHEAD, KC>(static_cast<const char*>(x), BF16 ? 2 : 4, g, tid - 128, lane, ring_base, stage_bytes,
                                    bars.full, bars.empty, next_tile);
-  } else if (warp >= 8 && warp < 11) {
+  } else if (warp >= 8 && warp < 12) {
     // ======================= MMA issuers: warp 8 + m owns accumulator m of every tile =======================
     // (a single issuing thread spends ~80 cycles per tcgen05.mma on descriptor arithmetic and the election
     // wrapper, more than the 48 cycles the tensor core needs for M=128, N=64, K=8 from shared memory)
@@ -319,7 +328,14 @@ conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, 
       uint32_t tap_off[9];  // start-address advance of tap (dy,dx) in 16-byte units
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>((tap / 3) * g.HP + tap % 3) * 2u;
-      for (int j = 0; next_tile(j) >= 0; ++j, ++lt) {
+      for (int j = 0;; ++j, ++lt) {
+        const int tile = next_tile(j);
+        if (tile < 0) break;
+        // a short last tile of an image (fewer rows than R) may not reach this warp's accumulator: no MMAs then, but
+        // the commits below still arrive so that every barrier keeps its count
+        const int y0 = (tile % g.tiles_per_img) * g.R;
+        const int rows_t = g.rows - y0 < g.R ? g.rows - y0 : g.R;
+        const bool active = m * 128 < rows_t * g.HP;
         const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
         mbar_wait(smem_u32(&bars.acc_empty[ab]), aph ^ 1u);  // epilogue has drained this accumulator set
         fence_after();
@@ -331,12 +347,14 @@ conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, 
           fence_after();
           const uint64_t da_st = a_desc0 + ((st * stage_bytes) >> 4);
           const uint64_t db_kc = b_desc0 + static_cast<uint32_t>(kc) * (kTapKcBytes >> 4);
+          if (active) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint64_t da = da_st + tap_off[tap];
-            const uint64_t db = db_kc + static_cast<uint32_t>(tap) * (static_cast<uint32_t>(KC) * kTapKcBytes >> 4);
-            if (BF16) mma_f16(d_tmem, da, db, kIdesc, (kc | tap) != 0);
-            else mma_tf32(d_tmem, da, db, kIdesc, (kc | tap) != 0);
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint64_t da = da_st + tap_off[tap];
+              const uint64_t db = db_kc + static_cast<uint32_t>(tap) * (static_cast<uint32_t>(KC) * kTapKcBytes >> 4);
+              if (BF16) mma_f16(d_tmem, da, db, kIdesc, (kc | tap) != 0);
+              else mma_tf32(d_tmem, da, db, kIdesc, (kc | tap) != 0);
+            }
           }
           commit(smem_u32(&bars.empty[st]));  // stage reusable once these MMAs have read it
         }
@@ -347,7 +365,7 @@ conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, 
     // ======================= epilogue (warps 0-3; with EPI2 also warps 11-14) =======================
     // a warp may only read the TMEM lanes 32 (warp % 4) .. + 31: that quarter is its share of the accumulator rows
     uint32_t lt = 0;
-    const int part = warp >= 11 ? 1 : 0;
+    const int part = warp >= 12 ? 1 : 0;
     const int etid = (warp & 3) * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>((warp & 3) * 32) << 16;
     for (int j = 0;; ++j, ++lt) {
@@ -359,7 +377,7 @@ conv3x3_c64_tc_kernel(const void* __restrict__ x, const void* __restrict__ wpk, 
       mbar_wait_warp(smem_u32(&bars.acc_full[ab]), aph, lane);
       fence_after();
       epilogue_tile<NM, TOut>(g, n, y0, true, tmem_base + ab * (NM * kC3) + t_lane,
-                              s_stage + part * (NM * 128 * kStagePitch), s_shift, out, etid, EPI2 ? 4 * part : 0,
+                              s_stage + part * (g.stage_pos * kStagePitch), s_shift, out, etid, EPI2 ? 4 * part : 0,
                               EPI2 ? 4 * part + 4 : 8, 1 + part, [&]() {
         if (lane == 0) mbar_arrive(smem_u32(&bars.acc_empty[ab]));
       });
@@ -407,7 +425,7 @@ conv3x3_c64_tc_pair_kernel(const float* __restrict__ x, const float* __restrict_
   const uint32_t w_base = smem_u32(s_dyn);
   const uint32_t ring_base = w_base + kWBytesP;
   float* s_stage = reinterpret_cast<float*>(s_dyn + kWBytesP + kRingP * stage_bytes);
-  float* s_shift = s_stage + NM * 128 * kStagePitch;
+  float* s_shift = s_stage + g.stage_pos * kStagePitch;
   constexpr uint32_t kTmemCols = NM == 1 ? 128u : (NM == 2 ? 256u : 512u);
   constexpr uint32_t kIdesc = idesc_tf32(256, kC3);
 
@@ -526,7 +544,7 @@ template <int NM>
 int launch_conv3_pair(const float* x, const float* wpk_pair, const float* shift, float* out, Conv3Geom g,
                       cudaStream_t stream) {
   g.halo = (NM * 128 + 2 * g.HP + 2 + 7) & ~7;
-  const size_t smem = kWBytesP + kRingP * (g.halo * 32u) + static_cast<size_t>(NM) * 128 * kStagePitch * 4 + kC3 * 4 + 256;
+  const size_t smem = kWBytesP + kRingP * (g.halo * 32u) + static_cast<size_t>(g.stage_pos) * kStagePitch * 4 + kC3 * 4 + 256;
   if (smem + 256u > 232448u) return AFS_ERR_UNSUPPORTED;
   AFS_CUDA_TRY(cudaFuncSetAttribute(conv3x3_c64_tc_pair_kernel<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
@@ -561,8 +579,8 @@ int launch_conv3_pair(const float* x, const float* wpk_pair, const float* shift,
 template <int NM, bool BF16, typename TOut, bool EPI2>
 int launch_conv3(const void* x, const void* wpk, const float* shift, TOut* out, Conv3Geom g, cudaStream_t stream) {
   g.halo = (NM * 128 + 2 * g.HP + 2 + 7) & ~7;
-  const size_t smem = (BF16 ? kWBytes3B : kWBytes3) + (BF16 ? kRing3B : kRing3) * (g.halo * 32u) +
-                      static_cast<size_t>(EPI2 ? 2 : 1) * NM * 128 * kStagePitch * 4 + kC3 * 4 + 256;
+  const size_t smem = (BF16 ? kWBytes3B : kWBytes3) + ring_stages(BF16, NM) * (g.halo * 32u) +
+                      static_cast<size_t>(EPI2 ? 2 : 1) * g.stage_pos * kStagePitch * 4 + kC3 * 4 + 256;
   if (smem + 256u > 232448u) return AFS_ERR_UNSUPPORTED;  // 227 KB per CTA, static barriers included
   AFS_CUDA_TRY(cudaFuncSetAttribute(conv3x3_c64_tc_kernel<NM, BF16, TOut, EPI2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
@@ -592,32 +610,69 @@ int dispatch_conv3(int NM, const void* x, const void* wpk, const float* shift, T
     switch (NM) {
       case 1: rc = launch_conv3<1, BF16, TOut, true>(x, wpk, shift, out, g, stream); break;
       case 2: rc = launch_conv3<2, BF16, TOut, true>(x, wpk, shift, out, g, stream); break;
-      default: rc = launch_conv3<3, BF16, TOut, true>(x, wpk, shift, out, g, stream); break;
+      case 3: rc = launch_conv3<3, BF16, TOut, true>(x, wpk, shift, out, g, stream); break;
+      default: rc = launch_conv3<4, BF16, TOut, true>(x, wpk, shift, out, g, stream); break;
     }
     if (rc != AFS_ERR_UNSUPPORTED) return rc;  // else: no room for the second staging tile -> one group
   }
   switch (NM) {
     case 1: return launch_conv3<1, BF16, TOut, false>(x, wpk, shift, out, g, stream);
     case 2: return launch_conv3<2, BF16, TOut, false>(x, wpk, shift, out, g, stream);
-    default: return launch_conv3<3, BF16, TOut, false>(x, wpk, shift, out, g, stream);
+    case 3: return launch_conv3<3, BF16, TOut, false>(x, wpk, shift, out, g, stream);
+    default: return launch_conv3<4, BF16, TOut, false>(x, wpk, shift, out, g, stream);
   }
 }
 
 // Tile geometry shared by the TF32 and the bf16 entry point.  Returns NM (accumulators per tile) or an AFS_ERR_* code (< 0).
-int conv3_geometry(int32_t N, int32_t H, int32_t Wd, float negative_slope, int32_t pool3, Conv3Geom* gp) {
+// max_nm: 3 or 4 accumulators of 128 rows per tile.  A tile is R image rows (a multiple of 3 when pooling); with 4
+// accumulators block 2 (42 x 52, HP = 54) runs tiles of 9, 9, 9, 9, 6 rows = 19 accumulator-tiles per image (the short
+// last tile skips its fourth accumulator) instead of 7 x 3 = 21.
+int conv3_geometry(int32_t N, int32_t H, int32_t Wd, float negative_slope, int32_t pool3, int max_nm, Conv3Geom* gp) {
   Conv3Geom& g = *gp;
   g.N = N; g.H = H; g.W = Wd; g.HP = Wd + 2; g.pool = pool3 ? 1 : 0; g.slope = negative_slope;
   g.PH = H / 3; g.PW = Wd / 3;
   const int rows_needed = pool3 ? 3 * g.PH : H;  // rows below the last complete pooling window are never used
-  // rows per tile: as many as fit 384 accumulator rows (a multiple of 3 when pooling)
-  int R = 384 / g.HP;
+  int R = max_nm * 128 / g.HP;  // rows per tile: as many as fit the accumulator rows
   if (R > rows_needed) R = rows_needed;
   if (pool3) R -= R % 3;
   if (R < 1) return AFS_ERR_UNSUPPORTED;  // image rows wider than the tile (W > 126 when pooling)
   g.R = R;
+  g.rows = rows_needed;
+  g.stage_pos = (R * g.HP + 7) & ~7;
   g.tiles_per_img = (rows_needed + R - 1) / R;
   if (static_cast<int64_t>(N) * g.tiles_per_img > 0x7fffffffLL) return AFS_ERR_UNSUPPORTED;
   return (R * g.HP + 127) / 128;
+}
+
+// Accumulator-tiles (MMA work) per image of a geometry: what the choice between 3 and 4 accumulators minimises.
+int conv3_acc_tiles(const Conv3Geom& g) {
+  int total = 0;
+  for (int y0 = 0; y0 < g.rows; y0 += g.R) {
+    const int rows_t = g.rows - y0 < g.R ? g.rows - y0 : g.R;
+    total += (rows_t * g.HP + 127) / 128;
+  }
+  return total;
+}
+
+// Geometry with the accumulator count that needs the fewest MMAs (AFS_CONV3_NM4 = 0 / 1 forces three / tries four).
+int conv3_best_geometry(int32_t N, int32_t H, int32_t Wd, float negative_slope, int32_t pool3, Conv3Geom* gp) {
+  static const int forced = [] {
+    const char* e = getenv("AFS_CONV3_NM4");
+    return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
+  }();
+  Conv3Geom g3, g4;
+  const int nm3 = conv3_geometry(N, H, Wd, negative_slope, pool3, 3, &g3);
+  if (nm3 < 0 || forced == 0) {
+    *gp = g3;
+    return nm3;
+  }
+  const int nm4 = conv3_geometry(N, H, Wd, negative_slope, pool3, 4, &g4);
+  if (nm4 == 4 && conv3_acc_tiles(g4) < conv3_acc_tiles(g3)) {
+    *gp = g4;
+    return nm4;
+  }
+  *gp = g3;
+  return nm3;
 }
 
 // 0: one CTA per SM (default).  1: CTA pairs (cta_group::2).  Initialised from AFS_CONV3_PAIR.
@@ -684,7 +739,7 @@ extern "C" int afs_conv3x3_c64_bn_act_fwd_tf32(const float* x, int32_t N, int32_
   if (Wd > 61) return AFS_ERR_UNSUPPORTED;  // the operand ring of wider rows does not fit next to the weights
   if (N == 0) return AFS_OK;
   Conv3Geom g;
-  const int NM = conv3_geometry(N, H, Wd, negative_slope, pool3, &g);
+  int NM = conv3_geometry(N, H, Wd, negative_slope, pool3, 3, &g);
   if (NM < 0) return NM;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (g_pair_mode.load(std::memory_order_relaxed) != 0 && static_cast<int64_t>(N) * g.tiles_per_img >= 2) {
@@ -695,7 +750,13 @@ extern "C" int afs_conv3x3_c64_bn_act_fwd_tf32(const float* x, int32_t N, int32_
       default: return launch_conv3_pair<3>(x, w_pair, shift, out, g, stream);
     }
   }
-  return dispatch_conv3<false, float>(NM, x, w_packed, shift, out, g, stream);
+  NM = conv3_best_geometry(N, H, Wd, negative_slope, pool3, &g);
+  int rc = dispatch_conv3<false, float>(NM, x, w_packed, shift, out, g, stream);
+  if (rc == AFS_ERR_UNSUPPORTED && NM == 4) {  // no shared memory for four accumulators' stages: three
+    NM = conv3_geometry(N, H, Wd, negative_slope, pool3, 3, &g);
+    rc = dispatch_conv3<false, float>(NM, x, w_packed, shift, out, g, stream);
+  }
+  return rc;
 }
 
 extern "C" size_t afs_conv3x3_c64_packed_bf16_elems(void) { return afs::kWBytes3B / 2; }
@@ -728,9 +789,14 @@ extern "C" int afs_conv3x3_c64_bn_act_fwd_bf16(const void* x, int32_t N, int32_t
   if (Wd > 61) return AFS_ERR_UNSUPPORTED;
   if (N == 0) return AFS_OK;
   Conv3Geom g;
-  const int NM = conv3_geometry(N, H, Wd, negative_slope, pool3, &g);
+  int NM = conv3_best_geometry(N, H, Wd, negative_slope, pool3, &g);
   if (NM < 0) return NM;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (out_bf16) return dispatch_conv3<true, __nv_bfloat16>(NM, x, w_packed, shift, static_cast<__nv_bfloat16*>(out), g, stream);
-  return dispatch_conv3<true, float>(NM, x, w_packed, shift, static_cast<float*>(out), g, stream);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int rc = out_bf16 ? dispatch_conv3<true, __nv_bfloat16>(NM, x, w_packed, shift, static_cast<__nv_bfloat16*>(out), g, stream)
+                            : dispatch_conv3<true, float>(NM, x, w_packed, shift, static_cast<float*>(out), g, stream);
+    if (rc != AFS_ERR_UNSUPPORTED || NM != 4) return rc;
+    NM = conv3_geometry(N, H, Wd, negative_slope, pool3, 3, &g);  // no shared memory for four accumulators' stages
+  }
+  return AFS_ERR_UNSUPPORTED;
 }
