@@ -592,20 +592,23 @@ int launch_conv3(const void* x, const void* wpk, const float* shift, TOut* out, 
 }
 
 // Epilogue groups: AFS_CONV3_EPI2 = 0 / 1 forces one / two groups of four warps; default: two for the bf16 kernel
-// (its MMA phase is half as long), one for the TF32 kernel (MMA-bound, and a second staging tile does not fit next to
-// its 144 KB of weights: the launch returns AFS_ERR_UNSUPPORTED for the widest rows if forced).
-inline bool conv3_epi2(bool bf16) {
+// (its MMA phase is half as long), one for the TF32 kernel (MMA-bound; for the large tiles a second staging tile does
+// not fit next to the 144 KB of weights either: the dispatcher falls back to one group when forced).
+inline bool conv3_epi2(bool bf16, int nm) {
   static const int forced = [] {
     const char* e = getenv("AFS_CONV3_EPI2");
     return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
   }();
+  // measured: two groups do not help the TF32 kernel even where they fit (block 3, two accumulators: 0.155 ms with,
+  // 0.144 ms without) -- it is MMA-bound at every tile size
+  (void)nm;
   return forced < 0 ? bf16 : forced == 1;
 }
 
 template <bool BF16, typename TOut>
 int dispatch_conv3(int NM, const void* x, const void* wpk, const float* shift, TOut* out, const Conv3Geom& g,
                    cudaStream_t stream) {
-  if (conv3_epi2(BF16)) {
+  if (conv3_epi2(BF16, NM)) {
     int rc;
     switch (NM) {
       case 1: rc = launch_conv3<1, BF16, TOut, true>(x, wpk, shift, out, g, stream); break;
