@@ -179,7 +179,10 @@ int afs_conv1_train_bwd(const float* x, const float* grad_out, int32_t N, int32_
  * w_packed (device, afs_conv3x3_c64_packed_floats() floats, 16-byte aligned): the BatchNorm-folded weights in
  * operand order (once for the one-CTA kernel, once split in halves for the CTA-pair kernel), produced on the host by afs_conv3x3_c64_pack_weights from w_folded_host [64][64][3][3] (OIHW)
  * with round-to-nearest TF32; shift [64] (device) = (bias - mean)*gamma/sqrt(var+eps) + beta.
- * Built for Wd <= 61; AFS_ERR_UNSUPPORTED otherwise (the caller keeps cuDNN for such shapes).               */
+ * Built for Wd <= 61; AFS_ERR_UNSUPPORTED otherwise (the caller keeps cuDNN for such shapes).
+ * Tiling is chosen per shape (three or four 128-row accumulators per tile, whichever needs fewer MMAs); the
+ * development switches AFS_CONV3_NM4=0 (always three) and AFS_CONV3_EPI2=0/1 (one / two epilogue groups) in the
+ * environment select the measured alternatives; results are bit-identical across them.                       */
 size_t afs_conv3x3_c64_packed_floats(void);
 /* Kernel variant switch (process-wide; default 0, or 1 when AFS_CONV3_PAIR=1 is in the environment): 1 runs the block
  * on CTA pairs (thread-block clusters of 2, tcgen05 cta_group::2: each CTA keeps half of the weights).  Results are
