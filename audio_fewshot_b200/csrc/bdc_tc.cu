@@ -11,9 +11,13 @@
 // nothing extra: an M128 N64 MMA takes as long as an M128 N128 one on this part).  bdc.cu keeps the Gram on the FMA
 // pipe at 0.13 of HBM; here the FMA lanes only build the lo operand and run the epilogue.
 //
-// One persistent CTA per SM, 10 warps: TMA (warp 8), lo-operand builders (warps 4-7), MMA issuer (warp 9), epilogue
-// (warps 0-3: thread = Gram row of one clip: distances, sqrt, row / column sums, double centring, upper triangle --
-// the arithmetic and summation orders of bdc.cu).  Operand ring of 4 stages, two accumulators.
+// One persistent CTA per SM, 14 warps: TMA (warp 8), lo-operand builders (warps 4-7), MMA issuer (warp 9), and TWO
+// epilogue groups (warps 0-3 and 10-13: thread = Gram row of one clip: distances, sqrt, row / column sums, double
+// centring, upper triangle -- the arithmetic and summation orders of bdc.cu).  Operand ring of 4 stages, four
+// accumulators (all 512 TMEM columns): even tiles go to group 0, odd tiles to group 1, each with two accumulators, its
+// own A matrices and named barriers.  The epilogue of a tile is ~1 500 dependent instructions per thread (a chain of
+// latencies, ~20 000 clk) against 7 800 clk of MMAs: with one group the tensor pipe idled 60 % of the time
+// (profiles/r02_bdc_tc_ncu.csv).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -28,7 +32,8 @@ constexpr int kBC = 64;                       // channels
 constexpr int kBStages = 4;
 constexpr uint32_t kBTile = 128u * 128u;      // [128 rows][32 floats]
 constexpr uint32_t kBStage = 2u * kBTile;     // hi | lo
-constexpr int kBThreads = 320;
+constexpr int kBThreads = 448;
+constexpr int kBAcc = 4;                      // accumulators: two per epilogue group
 constexpr int kAStride = kBC + 1;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -48,7 +53,7 @@ EncodeTiledFn encode_tiled_b() {
 }
 
 struct BBars {
-  uint64_t full[kBStages], lo_ready[kBStages], empty[kBStages], acc_full[2], acc_empty[2];
+  uint64_t full[kBStages], lo_ready[kBStages], empty[kBStages], acc_full[kBAcc], acc_empty[kBAcc];
 };
 
 __global__ void __launch_bounds__(kBThreads, 1)
@@ -57,20 +62,20 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
   extern __shared__ __align__(1024) uint8_t b_smem_raw[];
   __shared__ BBars bars;
   __shared__ uint32_t s_tmem;
-  __shared__ float s_diag[2][kBC], s_rowsum[2][kBC], s_colsum[2][kBC];
+  __shared__ float s_diag[4][kBC], s_rowsum[4][kBC], s_colsum[4][kBC];  // [2 * group + clip of the tile]
   uint8_t* sm = b_smem_raw + ((1024u - (smem_u32(b_smem_raw) & 1023u)) & 1023u);
   const uint32_t sb = smem_u32(sm);
-  float* sA = reinterpret_cast<float*>(sm + kBStages * kBStage);  // [2 clips][64][65]
+  float* sA = reinterpret_cast<float*>(sm + kBStages * kBStage);  // [2 groups][2 clips][64][65]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (warp == 0) tmem_alloc(&s_tmem, 256);
+  if (warp == 0) tmem_alloc(&s_tmem, 512);
   if (tid == 32) {
     for (int s = 0; s < kBStages; ++s) {
       mbar_init(smem_u32(&bars.full[s]), 1);
       mbar_init(smem_u32(&bars.lo_ready[s]), 128);
       mbar_init(smem_u32(&bars.empty[s]), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kBAcc; ++s) {
       mbar_init(smem_u32(&bars.acc_full[s]), 1);
       mbar_init(smem_u32(&bars.acc_empty[s]), 128);
     }
@@ -102,8 +107,9 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
       constexpr uint32_t kIdesc = idesc_tf32(128, 128);
       uint32_t it = 0, t = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-        const uint32_t as = t & 1u;
-        mbar_wait_sleep(smem_u32(&bars.acc_empty[as]), ((t >> 1) & 1u) ^ 1u);
+        // local tile t belongs to epilogue group t & 1 and uses that group's accumulator (t >> 1) & 1
+        const uint32_t as = 2u * (t & 1u) + ((t >> 1) & 1u);
+        mbar_wait_sleep(smem_u32(&bars.acc_empty[as]), ((t >> 2) & 1u) ^ 1u);
         for (int kc = 0; kc < n_chunks; ++kc, ++it) {
           const uint32_t st = it % kBStages, par = (it / kBStages) & 1u;
           mbar_wait_sleep(smem_u32(&bars.lo_ready[st]), par);
@@ -121,7 +127,7 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
         commit(smem_u32(&bars.acc_full[as]));
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ===================================================== lo operand: x - (the 19 bits the MMA keeps of x)
     const int s = tid - 128;
     uint32_t it = 0;
@@ -146,20 +152,24 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
       }
     }
   } else {
-    // ===================================================== epilogue: thread = Gram row r of clip (warp >> 1)
-    const int clip_in_tile = warp >> 1;
-    const int r = (warp & 1) * 32 + lane;
-    float* A = sA + clip_in_tile * kBC * kAStride;
+    // ===================================================== epilogue group (warps 0-3 / 10-13): thread = Gram row r of
+    // clip (quarter >> 1), where quarter = warp % 4 is the TMEM lane quarter the warp may read
+    const int group = warp >= 10 ? 1 : 0;
+    const int quarter = warp & 3;
+    const int clip_in_tile = quarter >> 1;
+    const int slot = 2 * group + clip_in_tile;  // scratch row of this (group, clip)
+    const int r = (quarter & 1) * 32 + lane;
+    float* A = sA + slot * kBC * kAStride;
     const float et = expf(__ldg(log_temp));
     const float inv = 1.0f / static_cast<float>(kBC), inv2 = 1.0f / static_cast<float>(kBC * kBC);
-    const int bar_id = 1 + clip_in_tile;  // the two warps of a clip synchronise among themselves
-    uint32_t t = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-      const uint32_t as = t & 1u;
-      mbar_wait_warp_sleep(smem_u32(&bars.acc_full[as]), (t >> 1) & 1u, lane);
+    const int bar_id = 1 + slot;  // the two warps of a clip synchronise among themselves
+    uint32_t t = static_cast<uint32_t>(group);
+    for (int tile = blockIdx.x + group * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, t += 2) {
+      const uint32_t as = 2u * (t & 1u) + ((t >> 1) & 1u);
+      mbar_wait_warp_sleep(smem_u32(&bars.acc_full[as]), (t >> 2) & 1u, lane);
       fence_after();
       uint32_t g0[32], g1[32];
-      const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16) + as * 128u + 64u * clip_in_tile;
+      const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + as * 128u + 64u * clip_in_tile;
       tmem_ld32_nowait(taddr, g0);
       tmem_ld32_nowait(taddr + 32u, g1);
       tmem_wait_ld();
@@ -173,29 +183,29 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
         diag = (c == r) ? __uint_as_float(g0[c]) : diag;
         diag = (c + 32 == r) ? __uint_as_float(g1[c]) : diag;
       }
-      s_diag[clip_in_tile][r] = diag;
+      s_diag[slot][r] = diag;
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
       float rs = 0.f;  // row sum (dcov.bmm(I_M)): fixed order over j, as bdc.cu
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
         const float g = __uint_as_float(c < 32 ? g0[c] : g1[c - 32]);
-        float d = s_diag[clip_in_tile][c] + diag - 2.f * g;
+        float d = s_diag[slot][c] + diag - 2.f * g;
         d = fmaxf(d, 0.f);
         float a;
         asm("sqrt.approx.f32 %0, %1;" : "=f"(a) : "f"(fmaf(et, d, 1e-5f)));  // MUFU.SQRT: 1 ulp-class, tolerance is 1e-4
         A[r * kAStride + c] = a;
         rs += a;
       }
-      s_rowsum[clip_in_tile][r] = rs;
+      s_rowsum[slot][r] = rs;
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
       float cs = 0.f;  // column sum (I_M.bmm(dcov)): fixed order over i
 #pragma unroll 8
       for (int i = 0; i < kBC; ++i) cs += A[i * kAStride + r];
-      s_colsum[clip_in_tile][r] = cs;
+      s_colsum[slot][r] = cs;
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
       float total = 0.f;
 #pragma unroll 8
-      for (int j = 0; j < kBC; ++j) total += s_colsum[clip_in_tile][j];
+      for (int j = 0; j < kBC; ++j) total += s_colsum[slot][j];
       if (b < B) {
         // thread = column c of the output; rows in order: for a fixed row the 64 threads write consecutive addresses
         const int c = r;
@@ -204,13 +214,13 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
           float* ob = out + static_cast<int64_t>(b) * (kBC * (kBC + 1) / 2) + c;
 #pragma unroll 4
           for (int rr = 0; rr < kBC; ++rr) {
-            if (c >= rr) ob[0] = A[rr * kAStride + c] - inv * s_rowsum[clip_in_tile][rr] + colterm;
+            if (c >= rr) ob[0] = A[rr * kAStride + c] - inv * s_rowsum[slot][rr] + colterm;
             ob += kBC - 1 - rr;  // row rr starts at rr*64 - rr(rr-1)/2 - rr: next row is 63 - rr further
           }
         } else {
           float* ob = out + static_cast<int64_t>(b) * kBC * kBC + c;
 #pragma unroll 4
-          for (int rr = 0; rr < kBC; ++rr) ob[rr * kBC] = A[rr * kAStride + c] - inv * s_rowsum[clip_in_tile][rr] + colterm;
+          for (int rr = 0; rr < kBC; ++rr) ob[rr * kBC] = A[rr * kAStride + c] - inv * s_rowsum[slot][rr] + colterm;
         }
       }
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");  // A, the sums and the diagonal are free for the next tile
@@ -218,7 +228,7 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
   }
   fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
@@ -239,7 +249,7 @@ int bdc_fwd_tc(const float* x, int32_t B, int32_t C, int32_t M, const float* log
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return AFS_ERR_UNSUPPORTED;
   const int n_tiles = (B + 1) / 2;
-  const size_t smem = kBStages * kBStage + 2 * kBC * kAStride * sizeof(float) + 1024;
+  const size_t smem = kBStages * kBStage + 4 * kBC * kAStride * sizeof(float) + 1024;
   AFS_CUDA_TRY(cudaFuncSetAttribute(bdc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
   bdc_tc_kernel<<<grid, kBThreads, smem, stream>>>(map, B, (M + 31) / 32, log_temp, triu, out);
