@@ -62,7 +62,7 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
   extern __shared__ __align__(1024) uint8_t b_smem_raw[];
   __shared__ BBars bars;
   __shared__ uint32_t s_tmem;
-  __shared__ float s_diag[4][kBC], s_rowsum[4][kBC], s_colsum[4][kBC];  // [2 * group + clip of the tile]
+  __shared__ __align__(16) float s_diag[4][kBC], s_rowsum[4][kBC], s_colsum[4][kBC];  // [2 * group + clip of the tile]
   uint8_t* sm = b_smem_raw + ((1024u - (smem_u32(b_smem_raw) & 1023u)) & 1023u);
   const uint32_t sb = smem_u32(sm);
   float* sA = reinterpret_cast<float*>(sm + kBStages * kBStage);  // [2 groups][2 clips][64][65]
@@ -185,14 +185,28 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
       }
       s_diag[slot][r] = diag;
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      // distances in place of the Gram values (registers), the diagonal fetched as 128-bit loads: with the stores to A
+      // inside this loop every load of s_diag waited for the previous store (the compiler must assume they alias)
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 dg = *reinterpret_cast<const float4*>(&s_diag[slot][4 * c4]);
+        const float dgs[4] = {dg.x, dg.y, dg.z, dg.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = 4 * c4 + k;
+          const float g = __uint_as_float(c < 32 ? g0[c] : g1[c - 32]);
+          float d = dgs[k] + diag - 2.f * g;
+          d = fmaxf(d, 0.f);
+          float a;
+          asm("sqrt.approx.f32 %0, %1;" : "=f"(a) : "f"(fmaf(et, d, 1e-5f)));  // MUFU.SQRT: 1 ulp-class, tolerance is 1e-4
+          if (c < 32) g0[c] = __float_as_uint(a);
+          else g1[c - 32] = __float_as_uint(a);
+        }
+      }
       float rs = 0.f;  // row sum (dcov.bmm(I_M)): fixed order over j, as bdc.cu
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
-        const float g = __uint_as_float(c < 32 ? g0[c] : g1[c - 32]);
-        float d = s_diag[slot][c] + diag - 2.f * g;
-        d = fmaxf(d, 0.f);
-        float a;
-        asm("sqrt.approx.f32 %0, %1;" : "=f"(a) : "f"(fmaf(et, d, 1e-5f)));  // MUFU.SQRT: 1 ulp-class, tolerance is 1e-4
+        const float a = __uint_as_float(c < 32 ? g0[c] : g1[c - 32]);
         A[r * kAStride + c] = a;
         rs += a;
       }
@@ -204,18 +218,28 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
       s_colsum[slot][r] = cs;
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
       float total = 0.f;
-#pragma unroll 8
-      for (int j = 0; j < kBC; ++j) total += s_colsum[slot][j];
+#pragma unroll
+      for (int j4 = 0; j4 < kBC / 4; ++j4) {  // the same ascending order, four values per load
+        const float4 v = *reinterpret_cast<const float4*>(&s_colsum[slot][4 * j4]);
+        total += v.x; total += v.y; total += v.z; total += v.w;
+      }
       if (b < B) {
         // thread = column c of the output; rows in order: for a fixed row the 64 threads write consecutive addresses
         const int c = r;
         const float colterm = inv2 * total - inv * cs;
         if (triu) {
+          // row rr of the upper triangle starts at rr*64 - rr(rr-1)/2; element (rr, c) sits c - rr further.  Fully
+          // unrolled: every offset is an immediate of the store, the row sums arrive four per load
           float* ob = out + static_cast<int64_t>(b) * (kBC * (kBC + 1) / 2) + c;
-#pragma unroll 4
-          for (int rr = 0; rr < kBC; ++rr) {
-            if (c >= rr) ob[0] = A[rr * kAStride + c] - inv * s_rowsum[slot][rr] + colterm;
-            ob += kBC - 1 - rr;  // row rr starts at rr*64 - rr(rr-1)/2 - rr: next row is 63 - rr further
+#pragma unroll
+          for (int r4 = 0; r4 < kBC / 4; ++r4) {
+            const float4 rs4 = *reinterpret_cast<const float4*>(&s_rowsum[slot][4 * r4]);
+            const float rsv[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr = 4 * r4 + k;
+              if (c >= rr) ob[rr * kBC - rr * (rr - 1) / 2 - rr] = A[rr * kAStride + c] - inv * rsv[k] + colterm;
+            }
           }
         } else {
           float* ob = out + static_cast<int64_t>(b) * kBC * kBC + c;
