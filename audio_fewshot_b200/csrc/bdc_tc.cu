@@ -7,7 +7,9 @@
 //   the 1e-4 tolerance through the cancellation in G_ii + G_jj - 2 G_ij.
 //
 // A tile is TWO clips: 128 rows x 32 positions per K chunk arrive as one TMA box (128-byte swizzle); the accumulator
-// is [128 x 128] of which the two diagonal 64 x 64 blocks are the clips' Gram matrices (the off-diagonal blocks cost
+// is [128 x 256] -- columns 0-127 hold hi hi^T, columns 128-255 hi lo^T + lo hi^T (one N = 256 MMA against B = [hi; lo]
+// and one N = 128 MMA per k step; the epilogue adds the halves) -- of which the two diagonal 64 x 64 blocks of each half
+// are the clips' Gram matrices (the off-diagonal blocks cost
 // nothing extra: an M128 N64 MMA takes as long as an M128 N128 one on this part).  bdc.cu keeps the Gram on the FMA
 // pipe at 0.13 of HBM; here the FMA lanes only build the lo operand and run the epilogue.
 //
@@ -104,12 +106,16 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
   } else if (warp == 9) {
     // ===================================================== MMA issuer
     if (lane == 0) {
+      // hi hi^T and hi lo^T in ONE N = 256 MMA (B = [hi; lo]: the lo tile follows the hi tile in the stage, so the
+      // 128-byte-swizzled operand simply has 256 rows), lo hi^T as an N = 128 MMA onto the second half: 20 KB of
+      // operand reads per k step instead of 24 KB for three N = 128 MMAs; the epilogue adds the two halves
+      constexpr uint32_t kIdesc256 = idesc_tf32(128, 256);
       constexpr uint32_t kIdesc = idesc_tf32(128, 128);
       uint32_t it = 0, t = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-        // local tile t belongs to epilogue group t & 1 and uses that group's accumulator (t >> 1) & 1
-        const uint32_t as = 2u * (t & 1u) + ((t >> 1) & 1u);
-        mbar_wait_sleep(smem_u32(&bars.acc_empty[as]), ((t >> 2) & 1u) ^ 1u);
+        // local tile t belongs to epilogue group t & 1 and uses that group's 256-column accumulator
+        const uint32_t as = t & 1u;
+        mbar_wait_sleep(smem_u32(&bars.acc_empty[as]), ((t >> 1) & 1u) ^ 1u);
         for (int kc = 0; kc < n_chunks; ++kc, ++it) {
           const uint32_t st = it % kBStages, par = (it / kBStages) & 1u;
           mbar_wait_sleep(smem_u32(&bars.lo_ready[st]), par);
@@ -118,9 +124,8 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t dh = desc_sw128(hi + 32 * k), dl = desc_sw128(lo + 32 * k);
-            mma_tf32(tmem + as * 128u, dh, dh, kIdesc, kc > 0 || k > 0);
-            mma_tf32(tmem + as * 128u, dh, dl, kIdesc, true);
-            mma_tf32(tmem + as * 128u, dl, dh, kIdesc, true);
+            mma_tf32(tmem + as * 256u, dh, dh, kIdesc256, kc > 0 || k > 0);  // [hi hi^T | hi lo^T]
+            mma_tf32(tmem + as * 256u + 128u, dl, dh, kIdesc, true);          // second half += lo hi^T
           }
           commit(smem_u32(&bars.empty[st]));
         }
@@ -165,14 +170,24 @@ bdc_tc_kernel(const __grid_constant__ CUtensorMap map_x, int B, int n_chunks, co
     const int bar_id = 1 + slot;  // the two warps of a clip synchronise among themselves
     uint32_t t = static_cast<uint32_t>(group);
     for (int tile = blockIdx.x + group * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, t += 2) {
-      const uint32_t as = 2u * (t & 1u) + ((t >> 1) & 1u);
-      mbar_wait_warp_sleep(smem_u32(&bars.acc_full[as]), (t >> 2) & 1u, lane);
+      const uint32_t as = t & 1u;
+      mbar_wait_warp_sleep(smem_u32(&bars.acc_full[as]), (t >> 1) & 1u, lane);
       fence_after();
       uint32_t g0[32], g1[32];
-      const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + as * 128u + 64u * clip_in_tile;
-      tmem_ld32_nowait(taddr, g0);
-      tmem_ld32_nowait(taddr + 32u, g1);
-      tmem_wait_ld();
+      const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + as * 256u + 64u * clip_in_tile;
+      {  // Gram row = first half (hi hi^T) + second half (hi lo^T + lo hi^T), 32 columns at a time
+        uint32_t x[32];
+        tmem_ld32_nowait(taddr, g0);
+        tmem_ld32_nowait(taddr + 128u, x);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) g0[c] = __float_as_uint(__uint_as_float(g0[c]) + __uint_as_float(x[c]));
+        tmem_ld32_nowait(taddr + 32u, g1);
+        tmem_ld32_nowait(taddr + 160u, x);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) g1[c] = __float_as_uint(__uint_as_float(g1[c]) + __uint_as_float(x[c]));
+      }
       fence_before();
       mbar_arrive(smem_u32(&bars.acc_empty[as]));
       const int b = 2 * tile + clip_in_tile;
