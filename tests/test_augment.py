@@ -63,7 +63,7 @@ def test_kernel_matches_reference_golden(cuda, golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(3, 2, 128, 157), (5, 64, 31), (128, 157), (1, 1, 7, 300)])
+@pytest.mark.parametrize("shape", [(3, 2, 128, 157), (5, 64, 31), (128, 157), (1, 1, 7, 300), (2, 1, 9, 200), (3, 7, 31)])
 def test_kernel_matches_oracle_on_other_shapes(cuda, shape):
     """Every type, default (drawn) parameters, 2-/3-/4-D inputs incl. the smoothed noise_matching branch the
     reference cannot execute (restated as intended: reflect pad of the last axis + box filter)."""
