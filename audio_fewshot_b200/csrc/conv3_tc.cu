@@ -17,17 +17,22 @@
 // address bits (checked on B200: the descriptor's base-offset field must stay 0 for shifted starts).  Positions
 // with x >= W are junk rows of the GEMM (2 of every HP) and are simply not stored.
 //
-// A tile is R image rows of one image = NM*128 accumulator rows (R*HP <= NM*128; block 2: R = 6, HP = 54, NM = 3).
-// Roles (one persistent CTA per SM, 352 threads):
-//   warps 4-7  producers: cp.async 16-byte copies of the tile's padded pixels, 8 channels (two chunks) per ring
-//              stage, zero-filled outside the image; stages are released to the tensor core with
-//              cp.async.wait_group + fence.proxy.async + mbarrier.arrive.  The ring is rolling: stage kc of the
-//              NEXT tile is loaded as soon as the nine taps of the current tile have consumed stage kc.
-//   warps 8-10 MMA issuers, one per accumulator: per stage 9 taps of tcgen05.mma.kind::tf32 (M = 128, N = 64,
-//              K = 8) into its 64 TMEM columns, double-buffered across tiles; tcgen05.commit frees the stage.
-//   warps 0-3  epilogue: tcgen05.ld 8 channels at a time, + folded shift, activation, then either a direct
-//              channels-last store or the 3x3/3 max-pool through a small shared staging tile.
-// All 64x64x9 folded weights stay resident in shared memory (144 KB, pre-packed and TF32-rounded on the host).
+// A tile is R image rows of one image = NM*128 accumulator rows (R*HP <= NM*128; block 2, HP = 54: R = 9, NM = 4 --
+// tiles of 9, 9, 9, 9, 6 rows, 95 % of the accumulator rows useful; R = 6, NM = 3 is the alternative the host compares
+// it with per shape, conv3_best_geometry).
+// Roles (one persistent CTA per SM, 384 threads; 512 with the second epilogue group):
+//   warps 4-7   producers: cp.async 16-byte copies of the tile's padded pixels, 8 channels (two chunks) per ring
+//               stage, zero-filled outside the image; stages are released to the tensor core with
+//               cp.async.wait_group + fence.proxy.async + mbarrier.arrive.  The ring is rolling: stage kc of the
+//               NEXT tile is loaded as soon as the nine taps of the current tile have consumed stage kc.
+//   warps 8-11  MMA issuers, one per accumulator: per stage 9 taps of tcgen05.mma.kind::tf32 (M = 128, N = 64,
+//               K = 8) into its 64 TMEM columns, double-buffered across tiles (2 x NM x 64 = up to all 512 columns);
+//               tcgen05.commit frees the stage.  A short last tile skips the accumulators it does not reach.
+//   warps 0-3   epilogue: tcgen05.ld 8 channels at a time, + folded shift, activation, then either a direct
+//               channels-last store or the 3x3/3 max-pool through a small shared staging tile.
+//   warps 12-15 (bf16 kernel) a second epilogue group with its own staging tile: passes 4-7 while the first runs 0-3.
+// All 64x64x9 folded weights stay resident in shared memory (144 KB, pre-packed and TF32-rounded on the host; 72 KB
+// as bf16).  The bf16 instantiation (kind::f16, K = 16: half the MMAs) is the separately stated reduced-precision path.
 // A second kernel below runs the same scheme on CTA pairs (tcgen05 cta_group::2); see its comment for the outcome.
 #include <stdio.h>
 #include <stdlib.h>
