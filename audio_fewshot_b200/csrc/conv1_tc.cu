@@ -6,28 +6,32 @@
 // pooled pixel: 0.37 ms per 800 clips, 69 % of the fp32 FMA peak).  The reference runs its convolutions in
 // TF32 by default (torch.backends.cudnn.allow_tf32 = True), and under that setting this kernel is used.
 //
-// Formulation: a tile is 128 POOLED pixels = 128 accumulator rows = 128 TMEM lanes.  For each of the 9 positions d
-// of the pooling window one GEMM  D_d[128 x 64] = P_d[128 x 16] . Wf^T[16 x 64]  (K = 9 taps zero-padded to 16)
-// gives the conv output at that window position for all 64 channels; the max over d is an elementwise max over
-// nine accumulators that all sit in the SAME lane, so the pooling needs no cross-thread traffic at all.
+// Formulation: a tile is 128 POOLED pixels = 128 accumulator rows = 128 TMEM lanes.  The conv output at each of the 9
+// positions of the pooling window is an accumulator column block of the SAME lane, so the max-pool is an elementwise
+// max over nine accumulators and needs no cross-thread traffic at all.  One operand row serves a whole window ROW g:
+// A_g[128 x 16] holds patch rows g..g+2 x all five patch columns (K index 5 r + c, K 15 = 0) and ONE resident weight
+// tile B[16 x 192] has column 64 dx + ch = tap (r, c - dx) of channel ch (zero where c - dx is outside 0..2):
+//   D_g[128 x 192] = A_g . B   = the three window columns dx of row g, side by side  (2 MMAs M128 N192 K8 per row).
+// (The first tensor-core version ran one [128 x 16].[16 x 64] GEMM per window position: 18 N = 64 MMAs and 72 KB of
+// im2col stores per tile instead of 6 N = 192 MMAs and 24 KB; N <= 64 MMAs cost >= 50 clk whatever N is.)
 //
-// One persistent CTA per SM, 13 warps in three roles chained by mbarriers (round 2; the round-1 kernel ran build ->
-// MMA -> TMEM read as phases of one 128-thread CTA and spent 5 800 clk per tile where the 18 MMAs need 900):
-//   BUILD warps 0-3   thread = pooled pixel: 5x5 input patch (prefetched one tile ahead), TF32 rounding, the nine
-//                     im2col rows of the tile (K-major no-swizzle UMMA layout, conflict-free 128-bit stores) into one
-//                     of two 72 KB operand buffers
-//   EPI   warps 4-11  thread = (pooled pixel, 32-channel half): tcgen05.ld, running max over the nine windows,
-//                     + folded shift, activation, warp transpose through a padded staging tile so that every store
-//                     instruction writes whole 128-byte half-rows of the NHWC output (a thread storing its own 32
-//                     channels touched 32 different lines per instruction)
-//   MMA   warp 12     one thread: per window row 3 x 2 tcgen05.mma M128 N64 K8 (TF32) into one of two 192-column
+// One persistent CTA per SM, 13 warps in three roles chained by mbarriers:
+//   BUILD warps 0-3   thread = pooled pixel: 5x5 input patch (prefetched one tile ahead), TF32 rounding, the three
+//                     operand rows of the tile (K-major no-swizzle UMMA layout, conflict-free 128-bit stores) into one
+//                     of four 24 KB operand buffers
+//   EPI   warps 4-11  thread = (pooled pixel, 32-channel half): the three windows of a row with three tcgen05.ld behind
+//                     one wait, accumulators handed back, FMNMX3 folds into the running max, + folded shift,
+//                     activation, warp transpose through a padded staging tile so that every store instruction writes
+//                     whole 128-byte half-rows of the NHWC output (64-byte half-rows of the bf16 output)
+//   MMA   warp 12     one thread: per window row 2 tcgen05.mma M128 N192 K8 (TF32) into one of two 192-column
 //                     accumulator sets; tcgen05.commit hands accumulators to the epilogue and operand buffers back
 //                     to BUILD
-// Measured on B200, 3 200 clips (profiles/r02_conv1_tc_variants.txt): round-1 kernel 1.08 ms; this structure with
-// per-thread stores 0.95 ms, with the staged stores 0.77 ms.  At that point the shared-memory / L1 data path is ~70 %
-// busy (im2col stores 55 KB + operand reads 108 KB + staging 64 KB per tile) and BUILD and EPI are busy 88 % / 78 % of
-// the time at ~0.2 IPC per warp.  Tried and slower: 16 EPI warps of 16 channels (0.91-1.07 ms, with and without a
-// setmaxnreg register split), two BUILD groups (1.00 ms at 96 registers per thread).
+// Measured on B200, 3 200 clips (profiles/r02_conv1_tc_variants.txt): round-1 kernel 1.08 ms; warp-specialised with
+// per-thread stores 0.95 ms, staged stores 0.77-0.83 ms, window-row operands 0.67-0.69 ms, trimmed epilogue 0.637 ms.
+// What bounds it now (profiles/r02_stem_rows_ncu.txt): the EPI warps' own latency chain -- TMEM-load data and
+// fixed-latency dependencies at two EPI warps per scheduler; they never wait for the tensor core.  Tried and slower:
+// 16 EPI warps of 16 channels (with and without a setmaxnreg register split), two BUILD groups, a software-pipelined
+// epilogue over 8-channel groups (0.691 ms), spinning instead of suspended mbarrier waits (no change).
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
