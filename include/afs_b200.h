@@ -133,8 +133,9 @@ int afs_conv1_bn_act_pool3_fwd(const float* x, int32_t N, int32_t H, int32_t Wd,
                                const float* w_folded_host, const float* shift_host, int32_t C,
                                float negative_slope, float* out, afs_stream_t stream);
 
-/* (1b') The same block on the tensor cores: nine tcgen05 TF32 GEMMs per tile of 128 pooled pixels (one per
- * pooling-window position, K = 9 taps padded to 16), max over the nine accumulators taken in tensor memory
+/* (1b') The same block on the tensor cores: per tile of 128 pooled pixels three tcgen05 TF32 GEMMs
+ * [128 x 16].[16 x 192] (one per pooling-window row: patch rows g..g+2 x five columns against a weight tile whose
+ * columns hold the three window columns side by side), max over the nine accumulator blocks taken in tensor memory
  * lanes.  TF32 operands, fp32 accumulation -- the precision class of the reference's default convolutions
  * (torch.backends.cudnn.allow_tf32 = True); afs_conv1_bn_act_pool3_fwd stays the exact-fp32 kernel.        */
 int afs_conv1_bn_act_pool3_fwd_tf32(const float* x, int32_t N, int32_t H, int32_t Wd,
