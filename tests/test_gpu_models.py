@@ -477,6 +477,58 @@ def test_pipeline_waveform_to_logits_and_cuda_graph(cuda):
     assert torch.equal(out_g2, out_p2)
 
 
+def test_full_size_step_is_episode_separable_and_repeatable(cuda):
+    """BASELINE.json's metric configuration at FULL size (32 episodes x 100 clips x 5 s = 1 GB of waveform, the bench
+    step), checked through size-independent properties -- the oracle cannot run this size in seconds.  Episodes are
+    independent, so (a) the log-mel images of any slice of the batch equal the slice of the full batch's images bit for
+    bit (different run boundaries of the persistent pair engine), (b) the logits of two 16-episode steps and of an
+    8-episode slice taken in the middle equal the 32-episode step's -- bit for bit through our own kernels (stem tiles
+    of 128 pooled pixels crossing clips, four-accumulator block-2 tiles, tail, head); block 4 is a cuDNN call whose
+    algorithm may depend on the batch size, hence 1e-5 of the logit range plus identical argmax rather than equality,
+    (c) a second run is bit-identical, (d) the separately stated bf16 backbone keeps the argmax of at least 99.9 % of
+    the queries on these class-structured episodes, (e) accuracy is what the per-query argmax says."""
+    from audio_fewshot_b200 import model as arch
+    from audio_fewshot_b200.frontend import LogMelFrontEnd
+    from audio_fewshot_b200.synthetic import name_seeded_weights_, synthetic_clip_batch_device
+    W, S, Q, L, E = 5, 5, 15, 80000, 32
+    mean, std = -15.114207, 26.22313
+    torch.manual_seed(0)
+    emb = name_seeded_weights_(arch.Conv64F(is_flatten=True, num_channels=1))
+    model = arch.ProtoNet(way_num=W, shot_num=S, query_num=Q, test_way=W, test_shot=S, test_query=Q, emb_func=emb,
+                          device=cuda).to(cuda).eval()
+    front = LogMelFrontEnd(sample_rate=16000, hop_length=512, n_mels=128, mean=mean, std=std).to(cuda).eval()
+    wav = synthetic_clip_batch_device(11, 0, E, W, S, Q, L, cuda)
+    per = W * (S + Q)
+
+    def run(first, n):
+        with torch.no_grad():
+            image = front(wav[first * per:(first + n) * per], first_clip_index=0)
+            out, acc = model.set_forward([image, None, torch.ones(n * W * Q, dtype=torch.long), n * W * S])
+        return image, out, acc
+
+    image, full, acc = run(0, E)
+    assert image.shape == (E * per, 1, 128, 157)
+    assert full.shape == (E * W * Q, W) and torch.isfinite(full).all()
+    image2, again, _ = run(0, E)
+    assert torch.equal(image, image2) and torch.equal(full, again)
+    tol = 1e-5 * full.abs().max().item()
+    for first, n in ((0, 16), (16, 16), (13, 8)):
+        img, out, _ = run(first, n)
+        assert torch.equal(image[first * per:(first + n) * per], img), (first, n)
+        ref = full[first * W * Q:(first + n) * W * Q]
+        assert (out - ref).abs().max().item() <= tol, (first, n)
+        assert torch.equal(out.argmax(1), ref.argmax(1)), (first, n)
+    target = torch.arange(W, device=cuda).repeat_interleave(Q).repeat(E)
+    assert acc.item() == pytest.approx((full.argmax(1) == target).float().mean().item() * 100.0, abs=1e-3)
+    emb.precision = "bf16"
+    try:
+        _, low, _ = run(0, E)
+    finally:
+        emb.precision = None
+    assert (low.argmax(1) == full.argmax(1)).float().mean().item() >= 0.999
+    assert (low - full).abs().max().item() <= 5e-2 * full.abs().max().item()
+
+
 def test_pipeline_stream_overlaps_copies_and_matches_single_calls(cuda):
     from audio_fewshot_b200 import model as arch
     from audio_fewshot_b200.frontend import LogMelFrontEnd
