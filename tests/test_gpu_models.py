@@ -529,6 +529,36 @@ def test_full_size_step_is_episode_separable_and_repeatable(cuda):
     assert (low - full).abs().max().item() <= 5e-2 * full.abs().max().item()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_full_size_dn4_step_is_episode_separable(cuda, precision):
+    """BASELINE configs[2] (DN4 / Conv64F maps, 5w5s15q, n_k = 3) at the per-config bench size (8 episodes = 800
+    images): a 3-episode slice scores as it does inside the full step (both heads are per-episode; own kernels up to
+    block 3, then one cuDNN block: 1e-5 of the score range + identical argmax), and a second run is bit-identical."""
+    from audio_fewshot_b200 import model as arch
+    from audio_fewshot_b200.synthetic import name_seeded_weights_
+    W, S, Q, E = 5, 5, 15, 8
+    torch.manual_seed(2)
+    emb = name_seeded_weights_(arch.Conv64F(is_flatten=False, last_pool=False, num_channels=1))
+    model = arch.DN4(n_k=3, precision=precision, way_num=W, shot_num=S, query_num=Q, test_way=W, test_shot=S,
+                     test_query=Q, emb_func=emb, device=cuda).to(cuda).eval()
+    per = W * (S + Q)
+    g = torch.Generator().manual_seed(5)
+    images = (torch.randn(E * per, 1, 128, 157, generator=g) * 0.7).to(cuda)
+
+    def run(first, n):
+        with torch.no_grad():
+            return model.set_forward([images[first * per:(first + n) * per], None,
+                                      torch.ones(n * W * Q, dtype=torch.long), n * W * S])[0]
+
+    full = run(0, E)
+    assert full.shape == (E * W * Q, W) and torch.isfinite(full).all()
+    assert torch.equal(full, run(0, E))
+    part = run(4, 3)
+    ref = full[4 * W * Q:7 * W * Q]
+    assert (part - ref).abs().max().item() <= 1e-5 * full.abs().max().item()
+    assert torch.equal(part.argmax(1), ref.argmax(1))
+
+
 def test_pipeline_stream_overlaps_copies_and_matches_single_calls(cuda):
     from audio_fewshot_b200 import model as arch
     from audio_fewshot_b200.frontend import LogMelFrontEnd
